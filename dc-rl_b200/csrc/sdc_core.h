@@ -1,0 +1,703 @@
+// sdc_core.h -- scalar (one-thread-per-env) part of the SustainDC step, shared by the CUDA kernels
+// (sdc_kernels.cu) and by the host test harness (tests/hostsim), which compiles these same functions
+// with g++ to unit-test the device logic without a GPU.
+//
+// Everything here is written from SURVEY.md Appendix A; each block cites the reference lines it
+// implements (paths relative to the reference root).  Arithmetic is fp64 like the reference; the
+// reward window is stored in fp32 (the 40 KB/env that dominates HBM traffic).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/sdc_b200.h"
+
+#if defined(__CUDACC__)
+#define SDC_HD __host__ __device__ __forceinline__
+#define SDC_HDN __host__ __device__
+#else
+#define SDC_HD inline
+#define SDC_HDN inline
+#endif
+
+namespace sdc {
+
+constexpr int kQueueMax = 1000;       // sustaindc_env.py:148-149
+constexpr int kListCap = 32;          // sorted quartile bracket, one element per lane
+constexpr int kWidenMargin = 4;       // extend a bracket side when fewer ranks than this remain
+constexpr double kSpMin = 15.0, kSpMax = 21.6;   // utils/make_envs_pyenv.py:124-126
+
+// ---- info table columns: keep in sync with dc-rl_b200/info_layout.py -------------------------
+enum InfoCol {
+    I_BAT_ACTION = 0, I_BAT_SOC, I_BAT_CO2, I_BAT_AVG_CI, I_BAT_E_WITHOUT, I_BAT_E_WITH, I_BAT_MAX_CAP,
+    I_BAT_DCLOAD_MIN, I_BAT_DCLOAD_MAX,
+    I_LS_ORIG_WORKLOAD, I_LS_SHIFTED_WORKLOAD, I_LS_ACTION, I_LS_NORM_LOAD_LEFT, I_LS_UNASSIGNED, I_LS_PENALTY_FLAG,
+    I_LS_QUEUE_MAX_LEN, I_LS_TASKS_IN_QUEUE, I_LS_NORM_TASKS_IN_QUEUE, I_LS_TASKS_DROPPED, I_LS_CURRENT_HOUR,
+    I_LS_TASKS_PROCESSED, I_LS_ENFORCED, I_LS_OLDEST_AGE, I_LS_AVG_AGE, I_LS_OVERDUE, I_LS_COMPUTED_TASKS,
+    I_LS_HIST0, I_LS_HIST1, I_LS_HIST2, I_LS_HIST3, I_LS_HIST4,
+    I_DC_ITE_KW, I_DC_CT_KW, I_DC_COMP_KW, I_DC_HVAC_KW, I_DC_TOTAL_KW, I_DC_SP_DELTA, I_DC_SP, I_DC_CPU_FRAC,
+    I_DC_INT_TEMP, I_DC_AMBIENT, I_DC_POWER_LB, I_DC_POWER_UB, I_DC_CW_PUMP, I_DC_CT_PUMP, I_DC_WATER,
+    I_OUTSIDE_TEMP, I_DAY, I_HOUR, I_NORM_CI,
+    I_FORECAST0, I_FORECAST1, I_FORECAST2, I_FORECAST3, I_FORECAST4, I_FORECAST5, I_FORECAST6, I_FORECAST7,
+    I_ISTERMINAL,
+    I_COUNT
+};
+static_assert(I_COUNT == 59, "info layout");
+
+enum Metric {
+    M_ENERGY = 0, M_CO2, M_WATER, M_TASKS_IN_QUEUE, M_TASKS_DROPPED, M_ITE_KW, M_CT_KW, M_COMP_KW, M_HVAC_KW,
+    M_STEPS, M_REWARD_SUM, M_EPISODES, M_REWARD_LS, M_REWARD_DC, M_OVERDUE, M_TOTAL_KW
+};
+
+// ---- device-resident tables and per-env state (structure of arrays) --------------------------
+struct LocTables {
+    const double* workload; const uint8_t* ns; const uint8_t* sh; const double* ci; const double* ci_min30;
+    const double* ci_max30; const double* temp_base; const double* wetb_base;
+};
+
+struct State {
+    int32_t n_envs, ep_len, hist_cap, ls_mask, win_len, n_loc, n_cfg, pad0;
+    const LocTables* loc;          // [n_loc]
+    const sdc_dc_params* dc;       // [n_cfg]
+    const double* hour_cos;        // [96]
+    const double* hour_sin;        // [96]
+    const uint8_t* loc_id;         // [N]
+    const uint8_t* cfg_id;         // [N]
+    const int16_t* day_lo;         // [N]
+    const int16_t* day_hi;         // [N]
+    const uint64_t* seed;          // [N]
+    uint32_t* episode;             // [N] episodes started (RNG counter)
+    // exogenous
+    int32_t* t;                    // trace index == quarter-hour stamp day*96+hour*4
+    int32_t* t0;                   // episode start index
+    int32_t* step_in_ep;
+    double* ci_min; double* ci_max;          // CI_Manager 30-day normalisation    managers.py:435-437
+    double* t_min; double* t_max;            // Weather_Manager normalisation      managers.py:606-608
+    double* weather;               // [N][2][win_len]: realised dry bulb, wet bulb of the episode
+    // load shifting queue as a ring of per-quarter-hour task counts
+    int32_t* ls_head; int32_t* ls_len; int32_t* ls_sum;
+    uint16_t* ls_bins;             // [N][4] tasks aged [0,6) [6,12) [12,18) [18,24) hours
+    uint8_t* ls_ring;              // [N][ls_mask+1]
+    // data centre
+    double* setpoint; int32_t* dc_run; int32_t* dc_scale; int8_t* dc_last;
+    // battery
+    double* bat_load;
+    // reward window + quartile brackets
+    float* hist;                   // [N][hist_cap]
+    int32_t* hist_len; int32_t* hist_head;
+    float* qlist;                  // [N][2][kListCap] sorted order statistics around the quartile ranks
+    int32_t* q_a;                  // [N][2] rank of qlist[.][0]
+    int32_t* q_m;                  // [N][2] elements in the list
+    int32_t* err;                  // [N] SDC_F_* bits
+    // staged ("injected") next episodes; null until sdc_stage_episode is used
+    uint8_t* pend_valid; int32_t* pend_day; int32_t* pend_hour; double* pend_tmin; double* pend_tmax;
+    double* pend_weather;          // [N][2][win_len]
+};
+
+SDC_HD double round_dec(double x, double scale) { return rint(x * scale) / scale; }   // np.round(x, d)
+SDC_HD double sigmoid(double x) { return 1.0 / (1.0 + exp(-x)); }
+SDC_HD double clampd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+
+// ---- observation features (sustaindc_env.py:266-433) -----------------------------------------
+// OLS slope of y[0..n) against 0..n-1 (what np.polyfit(range(n), y, 1)[0] solves).
+template <int N>
+SDC_HD double ols_slope(const double* y) {
+    const double xm = (N - 1) * 0.5;
+    double sxy = 0.0, sxx = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double dx = i - xm;
+        sxy += dx * y[i];
+        sxx += dx * dx;
+    }
+    return sxy / sxx;
+}
+
+// mean, std, (cur-mean)/(std+1e-8), first-peak/len, first-valley/len of `v[0..N)` given `cur`
+// (sustaindc_env.py:273-286 and 366-384; np.gradient of [cur, v...]).
+template <int N>
+SDC_HD void trend_features(double cur, const double* v, double* out5) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) s += v[i];
+    const double mean = s / N;
+    double ss = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const double d = v[i] - mean; ss += d * d; }
+    const double sd = sqrt(ss / N);
+    // gradient over the N+1 points x[0]=cur, x[i]=v[i-1]
+    double g_prev = v[0] - cur;                      // one-sided at the start
+    int peak = N, valley = N;
+#pragma unroll
+    for (int i = 1; i <= N; ++i) {
+        const double xm1 = (i == 1) ? cur : v[i - 2];
+        const double g = (i < N) ? (v[i] - xm1) * 0.5 : (v[N - 1] - v[N - 2]);   // central / one-sided end
+        if (peak == N && g_prev > 0.0 && g <= 0.0) peak = i - 1;
+        if (valley == N && g_prev < 0.0 && g >= 0.0) valley = i - 1;
+        g_prev = g;
+    }
+    out5[0] = mean; out5[1] = sd; out5[2] = (cur - mean) / (sd + 1e-8);
+    out5[3] = (double)peak / N; out5[4] = (double)valley / N;
+}
+
+struct LsStats { double oldest, avg, norm_q, hist[5]; };
+
+// Builds the three observations at trace index t. Sink: void operator()(int agent, int idx, float v).
+// Layouts: SURVEY.md A.6 / sustaindc_env.py:302-433.
+template <class Sink>
+SDC_HDN void build_obs(const State& S, int env, int t, const LsStats& ls, double soc, Sink& sink) {
+    const LocTables& L = S.loc[S.loc_id[env]];
+    const double cmin = S.ci_min[env], crng = S.ci_max[env] - S.ci_min[env];
+    const double tmin = S.t_min[env], trng = S.t_max[env] - S.t_min[env];
+    const double* wtemp = S.weather + (size_t)env * 2 * S.win_len;
+    const int wi = t - S.t0[env];
+    const int hq = t % 96;
+    const double cos_h = S.hour_cos[hq], sin_h = S.hour_sin[hq];
+
+    // carbon-intensity features: x[0..8] = cur, fut[8]; past[16]
+    double x[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[i] = (L.ci[t + i] - cmin) / crng;
+    double f_ci[7];
+    {
+        double sm[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) sm[i] = (((x[i] + x[i + 1]) + x[i + 2]) + x[i + 3]) / 4;
+        f_ci[0] = ols_slope<6>(sm);
+        if (t >= 16) {
+            double p[17];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) p[i] = (L.ci[t - 16 + i] - cmin) / crng;
+            p[16] = x[0];
+            double smp[14];
+#pragma unroll
+            for (int i = 0; i < 14; ++i) smp[i] = (((p[i] + p[i + 1]) + p[i + 2]) + p[i + 3]) / 4;
+            f_ci[1] = ols_slope<14>(smp);
+        } else {
+            f_ci[1] = 0.0;   // empty past window at the start of the year
+        }
+        trend_features<8>(x[0], x + 1, f_ci + 2);
+    }
+    // temperature features: nt[0..16] = normT[t..t+16]
+    double nt[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) nt[i] = (wtemp[wi + i] - tmin) / trng;
+    double f_t[6];
+    f_t[0] = ols_slope<17>(nt);
+    trend_features<16>(nt[0], nt + 1, f_t + 1);
+    const double w = L.workload[t], w_next = L.workload[t + 1];
+
+    // agent_ls [26]
+    int k = 0;
+    sink(0, k++, (float)cos_h); sink(0, k++, (float)sin_h); sink(0, k++, (float)x[0]);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) sink(0, k++, (float)f_ci[i]);
+    sink(0, k++, (float)ls.oldest); sink(0, k++, (float)ls.avg); sink(0, k++, (float)ls.norm_q);
+    sink(0, k++, (float)w); sink(0, k++, (float)nt[0]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sink(0, k++, (float)f_t[i]);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) sink(0, k++, (float)ls.hist[i]);
+    // agent_dc [14] (+ zero padding to 26)
+    k = 0;
+    sink(1, k++, (float)cos_h); sink(1, k++, (float)sin_h); sink(1, k++, (float)x[0]);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) sink(1, k++, (float)f_ci[i]);
+    sink(1, k++, (float)w); sink(1, k++, (float)w_next); sink(1, k++, (float)nt[0]); sink(1, k++, (float)nt[1]);
+    for (; k < SDC_OBS_DIM; ++k) sink(1, k, 0.0f);
+    // agent_bat [13]
+    k = 0;
+    sink(2, k++, (float)cos_h); sink(2, k++, (float)sin_h); sink(2, k++, (float)x[0]);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) sink(2, k++, (float)f_ci[i]);
+    sink(2, k++, (float)w); sink(2, k++, (float)nt[0]); sink(2, k++, (float)soc);
+    for (; k < SDC_OBS_DIM; ++k) sink(2, k, 0.0f);
+}
+
+// ---- EnergyPlus-style electric chiller (envs/datacenter.py:356-429) ---------------------------
+SDC_HD double chiller_power(double max_cap, double load, double ambient) {
+    const double d_t = (ambient - 35.0) / 2.778 - (6.67 - 35.0);
+    const double rat = 0.94483600 + (-0.05700880) * d_t + 0.00185486 * (d_t * d_t);
+    const double avail = (rat != 0.0) ? max_cap * rat : 0.0;
+    const double fpr = 2.333 + (-1.975) * rat + 0.6121 * (rat * rat);
+    const double plr = (avail > 0.0) ? fmax(0.05, fmin(load / avail, 1.0)) : 0.0;
+    const double ffl = 0.03303 + 0.6852 * plr + 0.2818 * (plr * plr);
+    double opl = 0.0;
+    if (avail > 0.0) opl = (load / avail < 0.05) ? load / avail : plr;
+    const double frac = (opl < 0.05) ? fmin(1.0, opl / 0.05) : 1.0;
+    const double power = ffl * fpr * avail / 3.0 * frac;
+    return (opl > 0.0) ? power : 0.0;
+}
+
+// Result of the scalar phase of one env-step that the reward phase needs.
+struct StepResult {
+    double energy;        // bat_total_energy_with_battery_KWh -> appended to the reward window
+    double nci_next;      // norm_CI of the next step (ci_i_future[0], sustaindc_env.py:681)
+    double ls_penalty;    // (-0.3*sqrt(overdue)+0.3) + (-0.1*oldest_age)   reward_creator.py:67-82
+    int terminal;
+    // logger metrics of this step
+    double co2, water, ite_kw, ct_kw, comp_kw, hvac_kw, total_kw;
+    int tasks_in_queue, tasks_dropped, overdue;
+};
+
+// One env-step of the three sub-envs + managers + observations + info (everything except the
+// reward normaliser).  InfoSink: void operator()(int col, float v).
+template <class ObsSink, class InfoSink>
+SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat, ObsSink& obs, InfoSink& info,
+                          StepResult& out) {
+    const LocTables& L = S.loc[S.loc_id[env]];
+    const sdc_dc_params& P = S.dc[S.cfg_id[env]];
+    int err = 0;
+    const int t = S.t[env];
+    const int q = t;                                     // quarter-hour stamp == trace index
+    if (t + 18 > SDC_YEAR_STEPS) err |= SDC_F_TRACE_DOMAIN;    // the reference crashes here
+    a_ls = a_ls < 0 ? 0 : (a_ls > 2 ? 2 : a_ls);
+    a_dc = a_dc < 0 ? 0 : (a_dc > 2 ? 2 : a_dc);
+    a_bat = a_bat < 0 ? 0 : (a_bat > 2 ? 2 : a_bat);
+
+    // ------------------------------------------------------------------------------------------
+    // Load shifting (envs/carbon_ls.py:172-324).  The FIFO is a ring of task counts per stamp.
+    // ------------------------------------------------------------------------------------------
+    const double w = L.workload[t];
+    if (w < 0.0 || w > 1.0) err |= SDC_F_WORKLOAD_RANGE;
+    const int ns = L.ns[t], sh = L.sh[t];
+    uint8_t* ring = S.ls_ring + (size_t)env * (S.ls_mask + 1);
+    const int mask = S.ls_mask;
+    int head = S.ls_head[env], len = S.ls_len[env], sum = S.ls_sum[env];
+    int b0 = S.ls_bins[env * 4 + 0], b1 = S.ls_bins[env * 4 + 1], b2 = S.ls_bins[env * 4 + 2], b3 = S.ls_bins[env * 4 + 3];
+    int m4 = 0;
+    if (len > 0) {
+        // the clock moved one quarter-hour: tasks reaching an age of exactly 6/12/18/24 h change bin
+        const int m1 = ring[(q - 24) & mask], m2 = ring[(q - 48) & mask], m3 = ring[(q - 72) & mask];
+        m4 = ring[(q - 96) & mask];
+        b0 -= m1; b1 += m1 - m2; b2 += m2 - m3; b3 += m3 - m4;
+    }
+    int b4 = len - (b0 + b1 + b2 + b3);
+    const int over = b4 - m4;                            // age > 24 h, strict          carbon_ls.py:208-209
+    // pops the `m` oldest tasks
+    auto pop_oldest = [&](int m) {
+        while (m > 0 && len > 0) {
+            const int c = ring[head & mask];
+            const int take = c < m ? c : m;
+            ring[head & mask] = (uint8_t)(c - take);
+            m -= take; len -= take; sum -= take * head;
+            const int age_bin = (q - head) / 24;
+            if (age_bin == 0) b0 -= take; else if (age_bin == 1) b1 -= take; else if (age_bin == 2) b2 -= take;
+            else if (age_bin == 3) b3 -= take;
+            if (c == take && len > 0) {
+                if (head >= q) { err |= SDC_F_BRACKET; len = 0; break; }      // corrupted ring (bug guard)
+                do { ++head; } while (ring[head & mask] == 0 && head < q);
+            }
+        }
+    };
+    int cap = 90 - (ns + sh);
+    int otp = 0;
+    if (cap > 0 && over > 0) { otp = over < cap ? over : cap; pop_oldest(otp); }     // carbon_ls.py:212-226
+    cap = 90 - (ns + sh + otp);
+    int dropped = 0, proc = 0;
+    double util;
+    if (a_ls == 0) {                                                                  // defer   :231-242
+        int add = kQueueMax - len; add = sh < add ? sh : add;
+        dropped = sh - add;
+        if (add > 0) {
+            if (len == 0) head = q;
+            ring[q & mask] = (uint8_t)(ring[q & mask] + add);
+            len += add; sum += add * q; b0 += add;
+        }
+        util = (double)(otp + (sh - add)) / 100;
+    } else if (a_ls == 2) {                                                           // process :244-264
+        if (cap >= 1) {
+            proc = sh < cap ? sh : cap; proc = proc < len ? proc : len;
+            pop_oldest(proc);
+            util = (double)(sh + proc + otp) / 100;
+        } else {
+            util = (double)(sh + otp) / 100;
+        }
+    } else {
+        util = (double)(sh + otp) / 100;
+    }
+    util += (double)ns / 100;                                                         // :275-276
+    LsStats ls;
+    if (len > 0) {
+        ls.oldest = ((double)(q - head) / 4.0) / 24;
+        ls.avg = (((double)((long long)len * q - sum) / 4.0) / len) / 24;
+    } else {
+        ls.oldest = 0.0; ls.avg = 0.0;
+    }
+    b4 = len - (b0 + b1 + b2 + b3);
+    const int dl = len > 1 ? len : 1;
+    ls.hist[0] = (double)b0 / dl; ls.hist[1] = (double)b1 / dl; ls.hist[2] = (double)b2 / dl; ls.hist[3] = (double)b3 / dl;
+    ls.hist[4] = b4 > 0 ? 1.0 : 0.0;                                                  // :63-73
+    ls.norm_q = (double)len / kQueueMax;
+    S.ls_head[env] = head; S.ls_len[env] = len; S.ls_sum[env] = sum;
+    S.ls_bins[env * 4 + 0] = (uint16_t)b0; S.ls_bins[env * 4 + 1] = (uint16_t)b1;
+    S.ls_bins[env * 4 + 2] = (uint16_t)b2; S.ls_bins[env * 4 + 3] = (uint16_t)b3;
+    const double hour_now = (double)(t % 96) * 0.25;
+    info(I_LS_ORIG_WORKLOAD, (float)w); info(I_LS_SHIFTED_WORKLOAD, (float)util); info(I_LS_ACTION, (float)a_ls);
+    info(I_LS_NORM_LOAD_LEFT, 0.f); info(I_LS_UNASSIGNED, 0.f); info(I_LS_PENALTY_FLAG, 0.f);
+    info(I_LS_QUEUE_MAX_LEN, (float)kQueueMax); info(I_LS_TASKS_IN_QUEUE, (float)len);
+    info(I_LS_NORM_TASKS_IN_QUEUE, (float)ls.norm_q); info(I_LS_TASKS_DROPPED, (float)dropped);
+    info(I_LS_CURRENT_HOUR, (float)hour_now); info(I_LS_TASKS_PROCESSED, (float)proc); info(I_LS_ENFORCED, 0.f);
+    info(I_LS_OLDEST_AGE, (float)ls.oldest); info(I_LS_AVG_AGE, (float)ls.avg); info(I_LS_OVERDUE, (float)over);
+    info(I_LS_COMPUTED_TASKS, (float)(int)(util * 100));
+#pragma unroll
+    for (int i = 0; i < 5; ++i) info(I_LS_HIST0 + i, (float)ls.hist[i]);
+
+    // ------------------------------------------------------------------------------------------
+    // Data centre (envs/dc_gym.py:142-237; envs/datacenter.py)
+    // ------------------------------------------------------------------------------------------
+    if (!(util >= 0.0 && util <= 1.0)) { err |= SDC_F_CPU_LOAD_RANGE; util = clampd(util, 0.0, 1.0); }
+    const int delta = a_dc - 1;                                   // {0:-1, 1:0, 2:+1}  make_envs_pyenv.py:127-131
+    int run = S.dc_run[env], scale = S.dc_scale[env];
+    const int last = S.dc_last[env];                              // 2 == None (after reset, dc_gym.py:115)
+    if (delta == last && a_dc != 0) { run += 1; } else { run = 1; scale = 1; }    // dc_gym.py:163-167
+    if (run > 3) scale += 1;                                                          // :170-171
+    double sp = S.setpoint[env] + (double)(delta * scale);
+    sp = fmax(fmin(sp, kSpMax), kSpMin);                                              // :173-174
+    S.setpoint[env] = sp; S.dc_run[env] = run; S.dc_scale[env] = scale; S.dc_last[env] = (int8_t)delta;
+    const double* wtemp = S.weather + (size_t)env * 2 * S.win_len;
+    const double* wwetb = wtemp + S.win_len;
+    const int wi = t - S.t0[env];
+    const double ambient = wtemp[wi], wet_bulb = wwetb[wi];
+
+    const double load_pct = util * 100;
+    double p_it = 0.0, sum_out = 0.0;
+    for (int c = 0; c < P.n_classes; ++c) {                      // datacenter.py:157-181,250-317 per rack class
+        const double t_in = P.cls_supply[c] + sp;
+        const double base = (P.m_cpu + 0.05) * t_in + P.c_cpu;
+        const double ratio = base + P.shift_cpu * (load_pct / 100);
+        const double n = P.cls_ncpu[c];
+        const double pc = fmax(P.cls_idle[c], P.cls_full[c] * ratio) * n;
+        const double v = (P.m_fan * 10 * t_in + P.c_fan * 5) + P.shift_fan * (load_pct / 20);
+        const double pf = (P.itfan_ref_p * (v / P.itfan_ref_v_ratio)) * n;
+        const double vf = (P.itfan_full_load_v * v) * n;
+        const double power_term = pow(pc + pf, 1.096);
+        const double airflow_term = P.c_air * P.rho_air * pow(vf, 0.824) * 0.526;
+        const double t_out = t_in + 1.918 * power_term / airflow_term + (-14.01);
+        if (t_out - t_in < 2.0) err |= SDC_F_OUTLET_DELTA;                            // :295-300
+        p_it += P.cls_mult[c] * (pc + pf);
+        sum_out += P.cls_mult[c] * t_out;
+    }
+    const double mean_out = sum_out / P.n_racks;
+    const double t_ret = P.ret_mean + mean_out;                                       // :531-541
+    // HVAC (datacenter.py:432-474)
+    const double m_sys = P.rho_air * P.crac_supply_flow_pu * p_it;
+    const double q_crac = m_sys * P.c_air * fmax(0.0, t_ret - sp);
+    const double comp = chiller_power(P.ct_fan_ref_p, q_crac, ambient);
+    double ct = 0.0;
+    if (!(ambient < 5.0)) {
+        const double dlt = fmax(50 - (ambient - sp), 1.0);
+        const double v_air = q_crac / (P.c_air * dlt) / P.rho_air;
+        const double r = fmin(v_air / P.ctafr, 1.0);
+        ct = P.ct_fan_ref_p * (r * r * r);
+    }
+    // cooling-tower water (datacenter.py:325-353)
+    double wtr = 0.044 * wet_bulb + (0.3528 * (t_ret - sp) + 0.101);
+    wtr = fmax(wtr, 0.0);
+    wtr += wtr * 0.01;
+    const double water = round_dec((wtr * 1000) / 4, 1e4);
+    const double total_kw = (p_it + ct + comp) / 1e3;
+    info(I_DC_ITE_KW, (float)(p_it / 1e3)); info(I_DC_CT_KW, (float)(ct / 1e3)); info(I_DC_COMP_KW, (float)(comp / 1e3));
+    info(I_DC_HVAC_KW, (float)((ct + comp) / 1e3)); info(I_DC_TOTAL_KW, (float)total_kw);
+    info(I_DC_SP_DELTA, (float)delta); info(I_DC_SP, (float)sp); info(I_DC_CPU_FRAC, (float)util);
+    info(I_DC_INT_TEMP, (float)mean_out); info(I_DC_AMBIENT, (float)ambient);
+    info(I_DC_POWER_LB, (float)P.power_lb_kw); info(I_DC_POWER_UB, (float)P.power_ub_kw);
+    info(I_DC_CW_PUMP, (float)P.cw_pump_w); info(I_DC_CT_PUMP, (float)P.ct_pump_w); info(I_DC_WATER, (float)water);
+
+    // ------------------------------------------------------------------------------------------
+    // Battery (envs/bat_env_fwd_view.py:84-126,194-284; envs/battery_model.py:94-139)
+    // ------------------------------------------------------------------------------------------
+    const double dcl = total_kw / 1e3;                           // MW                 sustaindc_env.py:652
+    const double ci_now = L.ci[t];
+    const double capb = P.bat_capacity_mwh;
+    double b = S.bat_load[env];
+    const double soc0 = b / capb;
+    double energy, co2;
+    if (a_bat == 0) {                                            // charge
+        const double t_u = round_dec(0.5 * (1 - sigmoid(10 * (soc0 - 0.5))), 1e4) * 15 / 60;
+        const double max_c = fmin(capb * 0.1, (capb - b) / (t_u - (-0.04)));
+        const double chg = fmin(max_c, capb) * t_u;
+        b = round_dec(b + chg, 1e8);
+        energy = dcl * 1e3 * 0.25 + chg * 1e3;
+        co2 = energy * ci_now;
+    } else if (a_bat == 1) {                                     // discharge
+        const double t_u = fmax(0.5, 4 * sigmoid(10 * (soc0 - 0.25))) * 15 / 60;
+        const double max_d = fmin(fmin(capb, b / (0.01 + t_u)), dcl / 4);
+        b = round_dec(b - fmin(max_d, capb) * t_u, 1e8);
+        const double dis = (max_d < capb) ? max_d * t_u : capb * t_u;
+        if (!(dcl * 1e3 * 0.25 >= dis * 1e3)) err |= SDC_F_BATTERY;
+        energy = dcl * 1e3 * 0.25 - dis * 1e3;
+        co2 = fmax(energy, 0.0) * ci_now;
+    } else {                                                     // idle
+        energy = dcl * 1e3 * 0.25;
+        co2 = energy * ci_now;
+    }
+    S.bat_load[env] = b;
+    const double soc = b / capb;
+    info(I_BAT_ACTION, (float)a_bat); info(I_BAT_SOC, (float)soc); info(I_BAT_CO2, (float)co2);
+    info(I_BAT_AVG_CI, (float)ci_now); info(I_BAT_E_WITHOUT, (float)(dcl * 1e3 * 0.25)); info(I_BAT_E_WITH, (float)energy);
+    info(I_BAT_MAX_CAP, (float)capb); info(I_BAT_DCLOAD_MIN, (float)(P.power_lb_kw / 4));
+    info(I_BAT_DCLOAD_MAX, (float)(P.power_ub_kw / 4));
+
+    // ------------------------------------------------------------------------------------------
+    // Managers advance (utils/managers.py:127-147,285-302,452-474,633-654), observations, info
+    // ------------------------------------------------------------------------------------------
+    const int tn = t + 1;
+    const int step_in_ep = S.step_in_ep[env] + 1;
+    S.t[env] = tn; S.step_in_ep[env] = step_in_ep;
+    const int terminal = step_in_ep >= S.ep_len;
+    build_obs(S, env, tn, ls, soc, obs);
+    const double cmin = S.ci_min[env], crng = S.ci_max[env] - S.ci_min[env];
+    const double nci_next = (L.ci[tn + 1] - cmin) / crng;
+    info(I_OUTSIDE_TEMP, (float)wtemp[wi + 1]); info(I_DAY, (float)(tn / 96)); info(I_HOUR, (float)((tn % 96) * 0.25));
+    info(I_NORM_CI, (float)nci_next);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) info(I_FORECAST0 + i, (float)((L.ci[tn + 1 + i] - cmin) / crng));
+    info(I_ISTERMINAL, terminal ? 1.f : 0.f);
+
+    out.energy = energy; out.nci_next = nci_next;
+    out.ls_penalty = (-0.3 * sqrt((double)over) + 0.3) + (-0.1 * ls.oldest);
+    out.terminal = terminal;
+    out.co2 = co2; out.water = water; out.ite_kw = p_it / 1e3; out.ct_kw = ct / 1e3; out.comp_kw = comp / 1e3;
+    out.hvac_kw = (ct + comp) / 1e3; out.total_kw = total_kw;
+    out.tasks_in_queue = len; out.tasks_dropped = dropped; out.overdue = over;
+    if (err) S.err[env] |= err;
+}
+
+// ---- rolling quartiles: exact order statistics kept in a small sorted bracket -----------------
+// For each quartile j the list qlist[env][j][0..m) holds the order statistics of the window at ranks
+// a .. a+m-1 (rank-contiguous, ties allowed).  One value enters and at most one leaves per step, so a
+// rank moves by at most one list position per step; the list is updated in O(1) here, and a side that
+// runs short (< kWidenMargin ranks beyond the needed pair) is extended by one rank from the full-window
+// scan of the same step (see ScanRequest / apply_widen).  Exactness does not depend on a distribution.
+struct ScanRequest {
+    int n;                  // window length including the new value
+    float lo, hi, shift;    // IQR fences and the centring shift of the moment sums
+    float below[2];         // count x < below[j], track max of those     (-inf: side not requested)
+    float above[2];         // count x > above[j], track min of those     (+inf: side not requested)
+    int widen;              // bit j: below[j] requested, bit 2+j: above[j] requested
+    int degenerate;         // q1 == q3: sigma is exactly 0 (utils/reward_creator.py:43-45 divides by 1)
+    double q1, q3;
+};
+struct ScanResult {
+    float s1, s2;           // sum(c - shift), sum((c - shift)^2) over the clipped window
+    int cnt_below[2], cnt_above[2];
+    float pred[2], succ[2];
+};
+
+#if defined(__CUDA_ARCH__)
+#define SDC_INF_F __int_as_float(0x7f800000)
+#else
+#define SDC_INF_F INFINITY
+#endif
+
+SDC_HD void list_remove(float* lst, int& a, int& m, float o, int& err) {
+    if (m == 0) { err |= SDC_F_BRACKET; return; }
+    if (o < lst[0]) { a -= 1; return; }
+    if (o > lst[m - 1]) return;
+    int i = 0;
+    while (i < m && lst[i] != o) ++i;
+    if (i == m) { err |= SDC_F_BRACKET; return; }
+    for (; i + 1 < m; ++i) lst[i] = lst[i + 1];
+    m -= 1;
+}
+
+// r_target: list index that must stay inside (used to choose the side to drop from on overflow)
+SDC_HD void list_insert(float* lst, int& a, int& m, float e, int n_after, int k_after) {
+    if (m > 0 && e < lst[0] && a > 0) { a += 1; return; }
+    if (m > 0 && e > lst[m - 1] && a + m < n_after - 1) return;     // ranks above the list, list not at the top
+    // e belongs inside the list (or extends a list that reaches the end of the window)
+    int pos = 0;
+    while (pos < m && lst[pos] <= e) ++pos;
+    if (m == kListCap) {
+        // full: drop from the side with more spare ranks around the target k_after
+        const int r = k_after - a;
+        const int margin_lo = r, margin_hi = m - 1 - r;
+        if (margin_lo > margin_hi) {            // drop lst[0]
+            if (pos == 0) { a += 1; return; }   // e itself would be the dropped element
+            for (int i = 0; i + 1 < pos; ++i) lst[i] = lst[i + 1];
+            lst[pos - 1] = e; a += 1; return;
+        } else {                                // drop lst[m-1]
+            if (pos == m) return;
+            for (int i = m - 1; i > pos; --i) lst[i] = lst[i - 1];
+            lst[pos] = e; return;
+        }
+    }
+    for (int i = m; i > pos; --i) lst[i] = lst[i - 1];
+    lst[pos] = e;
+    m += 1;
+}
+
+// Appends `energy` to the env's reward window (fp32 ring), updates both quartile brackets and returns
+// what the full-window scan must compute.  utils/reward_creator.py:16-45.
+SDC_HDN void reward_prepare(const State& S, int env, double energy, ScanRequest& rq) {
+    int err = 0;
+    float e = (float)energy;
+    if (!(fabs(energy) <= 3.0e38)) { err |= SDC_F_NONFINITE; e = 0.f; }
+    const int cap = S.hist_cap;
+    int len = S.hist_len[env], head = S.hist_head[env];
+    float* h = S.hist + (size_t)env * cap;
+    float o = 0.f; bool evict = false;
+    if (len == cap) { o = h[head]; evict = true; } else { len += 1; }
+    h[head] = e;
+    head += 1; if (head == cap) head = 0;
+    S.hist_len[env] = len; S.hist_head[env] = head;
+    const int n = len;
+    rq.n = n; rq.widen = 0; rq.degenerate = 0;
+    rq.below[0] = rq.below[1] = -SDC_INF_F; rq.above[0] = rq.above[1] = SDC_INF_F;
+    double qv[2] = {0.0, 0.0};
+    for (int j = 0; j < 2; ++j) {
+        float* lst = S.qlist + ((size_t)env * 2 + j) * kListCap;
+        int a = S.q_a[env * 2 + j], m = S.q_m[env * 2 + j];
+        const int num = (j == 0 ? 1 : 3) * (n - 1);
+        const int k = num / 4;                                   // np.percentile 'linear': idx = (n-1)*p
+        const double frac = (double)(num % 4) * 0.25;
+        if (evict) list_remove(lst, a, m, o, err);
+        if (m == 0) { lst[0] = e; a = 0; m = 1; }                // first value ever
+        else list_insert(lst, a, m, e, n, k);
+        if (n >= 2) {
+            const int r = k - a;
+            if (r < 0 || r + 1 >= m) {
+                err |= SDC_F_BRACKET;
+            } else {
+                const double lo_v = lst[r], hi_v = lst[r + 1];
+                const double d = hi_v - lo_v;                    // numpy _lerp
+                qv[j] = (frac >= 0.5) ? hi_v - d * (1.0 - frac) : lo_v + d * frac;
+                if (a > 0 && r < kWidenMargin) { rq.widen |= 1 << j; rq.below[j] = lst[0]; }
+                if (a + m < n && (m - 2 - r) < kWidenMargin) { rq.widen |= 4 << j; rq.above[j] = lst[m - 1]; }
+            }
+        }
+        S.q_a[env * 2 + j] = a; S.q_m[env * 2 + j] = m;
+    }
+    const double iqr = qv[1] - qv[0];
+    rq.q1 = qv[0]; rq.q3 = qv[1];
+    rq.lo = (float)(qv[0] - 1.5 * iqr); rq.hi = (float)(qv[1] + 1.5 * iqr);
+    rq.shift = (float)(0.5 * (qv[0] + qv[1]));
+    rq.degenerate = (qv[0] == qv[1]);
+    if (err) S.err[env] |= err;
+}
+
+// Extends the brackets with the ranks found by the scan and turns the moments into the three rewards.
+SDC_HDN void reward_finish(const State& S, int env, const ScanRequest& rq, const ScanResult& rs, const StepResult& st,
+                           float* rew3) {
+    int err = 0;
+    const int n = rq.n;
+    for (int j = 0; j < 2; ++j) {
+        float* lst = S.qlist + ((size_t)env * 2 + j) * kListCap;
+        int a = S.q_a[env * 2 + j], m = S.q_m[env * 2 + j];
+        if (rq.widen & (1 << j)) {                               // rank a-1
+            const int c = rs.cnt_below[j];
+            if (c > a) err |= SDC_F_BRACKET;
+            const float v = (a > c) ? lst[0] : rs.pred[j];       // a tie copy of lst[0] sits below the list
+            if (m == kListCap) m -= 1;                           // drop the top (far side)
+            for (int i = m; i > 0; --i) lst[i] = lst[i - 1];
+            lst[0] = v; a -= 1; m += 1;
+        }
+        if (rq.widen & (4 << j)) {                               // rank a+m
+            const int c = rs.cnt_above[j];
+            const int above = n - a - m;
+            if (c > above) err |= SDC_F_BRACKET;
+            const float v = (above > c) ? lst[m - 1] : rs.succ[j];
+            if (m == kListCap) { for (int i = 0; i + 1 < m; ++i) lst[i] = lst[i + 1]; m -= 1; a += 1; }
+            lst[m] = v; m += 1;
+        }
+        S.q_a[env * 2 + j] = a; S.q_m[env * 2 + j] = m;
+    }
+    double z = 0.0;
+    if (n >= 2) {
+        const double md = (double)rs.s1 / n;
+        double var = (double)rs.s2 / n - md * md;
+        double sd = (var > 0.0 && !rq.degenerate) ? sqrt(var) : 0.0;
+        const double mean = rq.degenerate ? rq.q1 : (double)rq.shift + md;
+        z = (st.energy - mean) / (sd > 0.0 ? sd : 1.0);
+    }
+    const double foot = -1.0 * (st.nci_next * z / 0.50);         // reward_creator.py:67-72
+    double r_ls = foot + st.ls_penalty;
+    r_ls = fmin(fmax(r_ls, -10.0), 10.0);                        // :82
+    rew3[0] = (float)r_ls; rew3[1] = (float)foot; rew3[2] = (float)foot;
+    if (err) S.err[env] |= err;
+}
+
+// ---- counter-based RNG for on-device episode starts and weather noise ---------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Replaces the reference's global `random` / legacy
+// `np.random` draws at reset (sustaindc_env.py:454-455, utils/managers.py:35-48,596-603) in
+// generated mode; replay mode injects the reference's realised values instead (sdc_stage_episode).
+struct U4 { uint32_t x, y, z, w; };
+SDC_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+SDC_HD U4 philox4x32(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        U4 n;
+        n.x = hi1 ^ c.y ^ k0; n.y = lo1; n.z = hi0 ^ c.w ^ k1; n.w = lo0;
+        c = n;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+enum RngStream { RS_START = 0, RS_NOISE = 1 };
+SDC_HD U4 env_random(uint64_t seed, uint32_t episode, uint32_t stream, uint32_t idx) {
+    U4 c; c.x = idx; c.y = episode; c.z = stream; c.w = 0x5DCB200u;
+    return philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+// Four N(0,1) samples (indices 4*idx4 .. 4*idx4+3 of the env's noise stream), Box-Muller in fp32.
+SDC_HD void noise_normals4(uint64_t seed, uint32_t episode, uint32_t idx4, float* z4) {
+    const U4 r = env_random(seed, episode, RS_NOISE, idx4);
+    const float k = 2.3283064365386963e-10f;             // 2^-32
+    const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = (float)r.y * k;
+    const float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u4 = (float)r.w * k;
+    const float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
+    float s, c;
+    sincosf(6.283185307179586f * u2, &s, &c);
+    z4[0] = ra * c; z4[1] = ra * s;
+    sincosf(6.283185307179586f * u4, &s, &c);
+    z4[2] = rb * c; z4[3] = rb * s;
+}
+// Episode start (day, hour) and weather day-roll: random.randint(lo, hi), random.randint(0, 23),
+// np.random.randint(0, 14).
+SDC_HD void draw_episode_start(uint64_t seed, uint32_t episode, int day_lo, int day_hi, int* day, int* hour, int* roll) {
+    const U4 r = env_random(seed, episode, RS_START, 0);
+    *day = day_lo + (int)(r.x % (uint32_t)(day_hi - day_lo + 1));
+    *hour = (int)(r.y % 24u);
+    *roll = (int)(r.z % 14u);
+}
+constexpr int kNoiseThreads = 256;                        // segments of the year-long random walk
+constexpr int kNoiseSeg = 140;                            // 4-aligned segment length, 256*140 >= 35040
+
+// Buffers and knobs of one step launch (all device pointers; see sdc_step in include/sdc_b200.h).
+struct StepArgs {
+    const int32_t* actions; float* obs; float* share; float* rew; uint8_t* done; float* info; float* term_obs;
+    int32_t* ticket; int32_t* ticket_next;             // dynamic unit counter of this / the next step
+    int32_t* reset_count; int32_t* reset_count_next;   // number of envs that finished their episode in this step
+    int32_t* reset_list; double* metrics;
+    int32_t unit_envs, unroll, prefetch, blocks_per_sm;
+};
+
+// HARL shared observation (harl/envs/sustaindc/harlsustaindc_env.py:78-85): ls[0:26] | dc[11] | dc[13] |
+// last element of the zero-padded battery row (always 0.0).
+SDC_HD void share_from_obs(const float* obs78, float* share29) {
+    for (int i = 0; i < SDC_OBS_DIM; ++i) share29[i] = obs78[i];
+    share29[26] = obs78[SDC_OBS_DIM + 11];
+    share29[27] = obs78[SDC_OBS_DIM + 13];
+    share29[28] = obs78[2 * SDC_OBS_DIM + SDC_OBS_DIM - 1];
+}
+
+// ---- reset of the scalar sub-env state (sustaindc_env.py:436-531) ----------------------------
+// The weather window / norms / t0 must already be in place. Set-point and reward window survive.
+template <class ObsSink>
+SDC_HDN void reset_scalar_state(const State& S, int env, int t0, ObsSink& obs) {
+    const LocTables& L = S.loc[S.loc_id[env]];
+    S.t[env] = t0; S.t0[env] = t0; S.step_in_ep[env] = 0;
+    S.ci_min[env] = L.ci_min30[t0]; S.ci_max[env] = L.ci_max30[t0];
+    S.ls_head[env] = t0; S.ls_len[env] = 0; S.ls_sum[env] = 0;
+    S.ls_bins[env * 4 + 0] = 0; S.ls_bins[env * 4 + 1] = 0; S.ls_bins[env * 4 + 2] = 0; S.ls_bins[env * 4 + 3] = 0;
+    S.dc_run[env] = 0; S.dc_scale[env] = 1; S.dc_last[env] = 2;              // dc_gym.py:114-116
+    S.bat_load[env] = 0.0;                                                    // battery_model.py:90-91
+    if (t0 + S.ep_len + 18 > SDC_YEAR_STEPS) S.err[env] |= SDC_F_TRACE_DOMAIN;
+    LsStats ls;
+    ls.oldest = 0.0; ls.avg = 0.0; ls.norm_q = 0.0;
+    for (int i = 0; i < 5; ++i) ls.hist[i] = 0.0;
+    build_obs(S, env, t0, ls, 0.0, obs);
+}
+
+}  // namespace sdc

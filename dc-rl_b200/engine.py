@@ -1,0 +1,207 @@
+"""Thin object wrapper over the C ABI handle (include/sdc_b200.h): one `Engine` == N batched SustainDC envs
+on one GPU.  Host code stays Python; all per-step arithmetic happens in the CUDA library.
+
+Two call styles, same kernels:
+  * device buffers (torch CUDA tensors, anything with ``data_ptr()``): ``reset_device`` / ``step_device``
+  * host buffers (numpy): ``reset_host`` / ``step_host`` -- H2D, step, D2H through the library's pinned staging,
+    i.e. what a numpy-based runner such as harl's sees.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import INFO_STRIDE, N_AGENTS, N_METRICS, OBS_DIM, SHARE_DIM
+from .dc_config import start_day_range
+from .traces import hour_table
+
+_STATE_DTYPES = {
+    "episode": np.uint32, "t": np.int32, "t0": np.int32, "step_in_ep": np.int32, "ci_min": np.float64, "ci_max": np.float64,
+    "t_min": np.float64, "t_max": np.float64, "weather": np.float64, "ls_head": np.int32, "ls_len": np.int32,
+    "ls_sum": np.int32, "ls_bins": np.uint16, "ls_ring": np.uint8, "setpoint": np.float64, "dc_run": np.int32,
+    "dc_scale": np.int32, "dc_last": np.int8, "bat_load": np.float64, "hist": np.float32, "hist_len": np.int32,
+    "hist_head": np.int32, "qlist": np.float32, "q_a": np.int32, "q_m": np.int32, "err": np.int32,
+}
+
+_default_lib = None
+
+
+def default_lib():
+    global _default_lib
+    if _default_lib is None:
+        _default_lib = _lib.load()
+    return _default_lib
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("buffer must be C-contiguous")
+        return C.c_void_p(x.ctypes.data)
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    raise TypeError("expected a tensor, ndarray or raw address")
+
+
+class SdcError(RuntimeError):
+    pass
+
+
+class Engine:
+    def __init__(self, n_envs, locations, dc_params, loc_id=None, cfg_id=None, months=None, seeds=None,
+                 days_per_episode=7, device=0, hist_cap=_lib.HIST_CAP, unit_envs=0, lib=None):
+        """locations: list of traces.LocationTraces; dc_params: list of _lib.DcParams (one per (dc_config,
+        location) pair); loc_id / cfg_id / months / seeds: per-env arrays (scalars broadcast)."""
+        self.lib = lib or default_lib()
+        self.n_envs = int(n_envs)
+        self.ep_len = int(days_per_episode) * 96
+        self.locations, self.dc_params = list(locations), list(dc_params)
+        cfg = _lib.Config(self.n_envs, int(device), self.ep_len, len(self.locations), len(self.dc_params), int(hist_cap),
+                          int(unit_envs), 0)
+        handle = C.c_void_p()
+        rc = self.lib.sdc_create(C.byref(cfg), C.byref(handle))
+        if rc:
+            raise SdcError("sdc_create: %s" % self.lib.sdc_last_error(None).decode())
+        self._h = handle
+        self.hist_cap = int(hist_cap)
+        for i, loc in enumerate(self.locations):
+            s = _lib.Location(*[loc_arr.ctypes.data for loc_arr in (
+                loc.workload, loc.ns_tasks, loc.sh_tasks, loc.ci, loc.ci_min30, loc.ci_max30, loc.temp_base, loc.wetb_base)])
+            self._check(self.lib.sdc_set_location(self._h, i, C.byref(s)))
+        for i, p in enumerate(self.dc_params):
+            self._check(self.lib.sdc_set_dc_params(self._h, i, C.byref(p)))
+        cos, sin = hour_table()
+        self._check(self.lib.sdc_set_hour_table(self._h, _ptr(cos), _ptr(sin)))
+        n = self.n_envs
+        self.loc_id = np.ascontiguousarray(np.broadcast_to(np.asarray(0 if loc_id is None else loc_id, np.uint8), (n,)))
+        self.cfg_id = np.ascontiguousarray(np.broadcast_to(np.asarray(0 if cfg_id is None else cfg_id, np.uint8), (n,)))
+        months = np.broadcast_to(np.asarray(0 if months is None else months, np.int64), (n,))
+        ranges = np.array([start_day_range(m) for m in range(12)], np.int16)
+        self.day_lo = np.ascontiguousarray(ranges[months, 0])
+        self.day_hi = np.ascontiguousarray(ranges[months, 1])
+        seeds = np.arange(n, dtype=np.uint64) if seeds is None else np.broadcast_to(np.asarray(seeds, np.uint64), (n,))
+        self.seeds = np.ascontiguousarray(seeds)
+        self._check(self.lib.sdc_assign(self._h, _ptr(self.loc_id), _ptr(self.cfg_id), _ptr(self.day_lo), _ptr(self.day_hi),
+                                        _ptr(self.seeds)))
+        self.win_len = self.lib.sdc_window_len(self._h)
+
+    # ---- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc < 0:
+            raise SdcError(self.lib.sdc_last_error(self._h).decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.sdc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_tuning(self, **kw):
+        for k, v in kw.items():
+            self._check(self.lib.sdc_set_tuning(self._h, k.encode(), int(v)))
+
+    # ---- episodes ------------------------------------------------------------------------------
+    def stage_episode(self, env_ids, day, hour, temp_win, wetb_win, t_min30, t_max30):
+        """Replay mode: the next reset of `env_ids` uses these starts / realised weather windows
+        (each window ep_len + 18 long) instead of the device RNG."""
+        env_ids = np.ascontiguousarray(env_ids, np.int32)
+        k = len(env_ids)
+        w = self.ep_len + 18
+        temp = np.ascontiguousarray(np.asarray(temp_win, np.float64).reshape(k, -1)[:, :w])
+        wetb = np.ascontiguousarray(np.asarray(wetb_win, np.float64).reshape(k, -1)[:, :w])
+        if temp.shape[1] != w or wetb.shape[1] != w:
+            raise ValueError("weather windows must hold at least ep_len + 18 = %d samples" % w)
+        day = np.ascontiguousarray(day, np.int32)
+        hour = np.ascontiguousarray(hour, np.int32)
+        t_min30 = np.ascontiguousarray(t_min30, np.float64)
+        t_max30 = np.ascontiguousarray(t_max30, np.float64)
+        if not (len(day) == len(hour) == len(t_min30) == len(t_max30) == k):
+            raise ValueError("stage_episode: per-env arrays must have len(env_ids) entries")
+        self._check(self.lib.sdc_stage_episode(self._h, k, _ptr(env_ids), _ptr(day), _ptr(hour), _ptr(temp), _ptr(wetb),
+                                               _ptr(t_min30), _ptr(t_max30)))
+
+    def reset_device(self, obs, share, mask=None, stream=None):
+        self._check(self.lib.sdc_reset(self._h, _ptr(mask), _ptr(obs), _ptr(share), _ptr(stream)))
+
+    def step_device(self, actions, obs, share, rew, done, info=None, term_obs=None, stream=None):
+        self._check(self.lib.sdc_step(self._h, _ptr(actions), _ptr(obs), _ptr(share), _ptr(rew), _ptr(done), _ptr(info),
+                                      _ptr(term_obs), _ptr(stream)))
+
+    def _host_buffers(self):
+        if not hasattr(self, "_hb"):
+            n = self.n_envs
+            self._hb = dict(obs=np.zeros((n, N_AGENTS, OBS_DIM), np.float32), share=np.zeros((n, SHARE_DIM), np.float32),
+                            rew=np.zeros((n, N_AGENTS), np.float32), done=np.zeros(n, np.uint8),
+                            info=np.zeros((INFO_STRIDE, n), np.float32), term=np.zeros((n, N_AGENTS, OBS_DIM), np.float32))
+        return self._hb
+
+    def reset_host(self, mask=None):
+        b = self._host_buffers()
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        self._check(self.lib.sdc_reset_host(self._h, _ptr(m), _ptr(b["obs"]), _ptr(b["share"])))
+        return b["obs"], b["share"]
+
+    def step_host(self, actions, want_info=True, want_term=True):
+        """actions int32 [N,3] -> (obs[N,3,26], share[N,29], rew[N,3], done[N], info[64,N] | None, term_obs | None).
+        The returned arrays are reused by the next call."""
+        b = self._host_buffers()
+        a = np.ascontiguousarray(np.asarray(actions).reshape(self.n_envs, N_AGENTS), np.int32)
+        self._check(self.lib.sdc_step_host(self._h, _ptr(a), _ptr(b["obs"]), _ptr(b["share"]), _ptr(b["rew"]), _ptr(b["done"]),
+                                           _ptr(b["info"]) if want_info else None, _ptr(b["term"]) if want_term else None))
+        return b["obs"], b["share"], b["rew"], b["done"], (b["info"] if want_info else None), (b["term"] if want_term else None)
+
+    # ---- metrics / state -----------------------------------------------------------------------
+    def metrics(self, clear=False):
+        out = np.zeros(N_METRICS, np.float64)
+        self._check(self.lib.sdc_metrics(self._h, _ptr(out), int(bool(clear))))
+        return out
+
+    def prefill_history(self, values):
+        """values: fp32 [count] (shared by all envs) or [N, count]."""
+        v = np.ascontiguousarray(values, np.float32)
+        per_env = int(v.ndim == 2)
+        count = v.shape[-1]
+        self._check(self.lib.sdc_prefill_history(self._h, _ptr(v), count, per_env))
+
+    def rebuild_brackets(self, stream=None):
+        self._check(self.lib.sdc_rebuild_brackets(self._h, _ptr(stream)))
+
+    def read_state(self, name):
+        dt = np.dtype(_STATE_DTYPES[name])
+        n = self.n_envs
+        per_env = {"weather": 2 * self.win_len, "ls_bins": 4, "hist": self.hist_cap, "qlist": 64, "q_a": 2, "q_m": 2}.get(name, 1)
+        if name == "ls_ring":
+            out = np.zeros(n * 65536, dt)       # upper bound; trimmed below
+        else:
+            out = np.zeros(n * per_env, dt)
+        got = self._check(self.lib.sdc_read_state(self._h, name.encode(), _ptr(out), out.nbytes))
+        out = out[:got // dt.itemsize]
+        return out.reshape(n, -1) if out.size != n else out
+
+    def get_state(self):
+        nbytes = self.lib.sdc_state_bytes(self._h)
+        blob = np.zeros(nbytes, np.uint8)
+        self._check(self.lib.sdc_get_state(self._h, _ptr(blob), nbytes))
+        return blob
+
+    def set_state(self, blob):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        self._check(self.lib.sdc_set_state(self._h, _ptr(blob), blob.nbytes))
+
+    @property
+    def error_flags_ptr(self):
+        return self.lib.sdc_error_flags(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.sdc_launch_count(self._h))

@@ -1,0 +1,189 @@
+// TEST INFRASTRUCTURE ONLY -- serial host build of the device logic.
+//
+// Compiles dc-rl_b200/csrc/sdc_core.h (the scalar per-env functions the CUDA kernels call) and
+// dc-rl_b200/csrc/sdc_api.inc (the C-ABI host layer) with g++ against a trivial in-memory backend, so
+// that the step logic, the rolling-quartile brackets and the reset/auto-reset sequencing can be
+// unit-tested against the oracle on machines without a GPU.  It is built by tests/ into
+// tests/hostsim/_build/libsdc_hostsim.so and is never loaded by the dc-rl_b200 package: the product
+// path is libsdc_b200.so (CUDA) only and fails loudly without it.
+//
+// The "kernels" below are plain loops; the full-window scan is a scalar loop (the CUDA kernel does
+// the same sums warp-parallel, so low-order bits of the fp32 moments differ).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../dc-rl_b200/csrc/sdc_core.h"
+
+namespace backend {
+struct Context { int unused = 0; };
+using StepArgs = sdc::StepArgs;
+static const char* init(Context&, int) { return nullptr; }
+static void shutdown(Context&) {}
+static const char* dev_alloc(Context&, void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? nullptr : "malloc"; }
+static void dev_free(Context&, void* p) { free(p); }
+static const char* dev_zero(Context&, void* p, size_t bytes) { memset(p, 0, bytes); return nullptr; }
+static const char* h2d(Context&, void* d, const void* s, size_t n) { memcpy(d, s, n); return nullptr; }
+static const char* d2h(Context&, void* d, const void* s, size_t n) { memcpy(d, s, n); return nullptr; }
+static const char* h2d_async(Context&, void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return nullptr; }
+static const char* d2h_async(Context&, void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return nullptr; }
+static const char* pinned_alloc(Context&, void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? nullptr : "malloc"; }
+static void pinned_free(Context&, void* p) { free(p); }
+static const char* stream_create(Context&, void** s) { *s = nullptr; return nullptr; }
+static const char* stream_sync(Context&, void*) { return nullptr; }
+static const char* sync(Context&) { return nullptr; }
+
+struct ObsRow {
+    float* row;   // [3][26]
+    void operator()(int agent, int idx, float v) { row[agent * SDC_OBS_DIM + idx] = v; }
+};
+struct InfoCol {
+    float* info; int n, env;
+    void operator()(int col, float v) { if (info) info[(size_t)col * n + env] = v; }
+};
+
+static void scan_window(const sdc::State& S, int env, const sdc::ScanRequest& rq, sdc::ScanResult& rs) {
+    const float* h = S.hist + (size_t)env * S.hist_cap;
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < 2; ++j) { rs.cnt_below[j] = rs.cnt_above[j] = 0; rs.pred[j] = -INFINITY; rs.succ[j] = INFINITY; }
+    for (int i = 0; i < rq.n; ++i) {
+        const float x = h[i];
+        const float c = fminf(fmaxf(x, rq.lo), rq.hi);
+        const float d = c - rq.shift;
+        s1 += d; s2 += d * d;
+        for (int j = 0; j < 2; ++j) {
+            if (x < rq.below[j]) { rs.cnt_below[j]++; rs.pred[j] = fmaxf(rs.pred[j], x); }
+            if (x > rq.above[j]) { rs.cnt_above[j]++; rs.succ[j] = fminf(rs.succ[j], x); }
+        }
+    }
+    rs.s1 = s1; rs.s2 = s2;
+}
+
+static const char* launch_step(Context&, const sdc::State& S, const StepArgs& a, void*) {
+    *a.ticket_next = 0; *a.reset_count_next = 0;
+    const int N = S.n_envs;
+    for (int env = 0; env < N; ++env) {
+        ObsRow obs{a.obs + (size_t)env * 3 * SDC_OBS_DIM};
+        InfoCol info{a.info, N, env};
+        sdc::StepResult st;
+        sdc::physics_step(S, env, a.actions[env * 3 + 0], a.actions[env * 3 + 1], a.actions[env * 3 + 2], obs, info, st);
+        sdc::share_from_obs(obs.row, a.share + (size_t)env * SDC_SHARE_DIM);
+        sdc::ScanRequest rq; sdc::ScanResult rs;
+        sdc::reward_prepare(S, env, st.energy, rq);
+        scan_window(S, env, rq, rs);
+        sdc::reward_finish(S, env, rq, rs, st, a.rew + (size_t)env * 3);
+        a.done[env] = (uint8_t)st.terminal;
+        if (st.terminal) {
+            if (a.term_obs) memcpy(a.term_obs + (size_t)env * 3 * SDC_OBS_DIM, obs.row, 3 * SDC_OBS_DIM * sizeof(float));
+            a.reset_list[(*a.reset_count)++] = env;
+        }
+        double* M = a.metrics;
+        M[sdc::M_ENERGY] += st.energy; M[sdc::M_CO2] += st.co2; M[sdc::M_WATER] += st.water;
+        M[sdc::M_TASKS_IN_QUEUE] += st.tasks_in_queue; M[sdc::M_TASKS_DROPPED] += st.tasks_dropped;
+        M[sdc::M_ITE_KW] += st.ite_kw; M[sdc::M_CT_KW] += st.ct_kw; M[sdc::M_COMP_KW] += st.comp_kw; M[sdc::M_HVAC_KW] += st.hvac_kw;
+        M[sdc::M_STEPS] += 1; M[sdc::M_EPISODES] += st.terminal;
+        const float* r = a.rew + (size_t)env * 3;
+        M[sdc::M_REWARD_SUM] += (double)r[0] + r[1] + r[2]; M[sdc::M_REWARD_LS] += r[0]; M[sdc::M_REWARD_DC] += r[1];
+        M[sdc::M_OVERDUE] += st.overdue; M[sdc::M_TOTAL_KW] += st.total_kw;
+    }
+    return nullptr;
+}
+
+static const char* launch_build_reset_list(Context&, const sdc::State& S, const uint8_t* mask, int32_t* list, int32_t* count, void*) {
+    int c = 0;
+    for (int env = 0; env < S.n_envs; ++env) if (!mask || mask[env]) list[c++] = env;
+    *count = c;
+    return nullptr;
+}
+
+// Weather of one episode from the device RNG -- serial statement of what k_reset does block-parallel
+// (utils/managers.py:35-48,594-613).
+static void generate_weather(const sdc::State& S, int env, int t0, int roll, uint32_t episode) {
+    const sdc::LocTables& L = S.loc[S.loc_id[env]];
+    const int n = SDC_YEAR_STEPS;
+    const uint64_t seed = S.seed[env];
+    std::vector<float> inc(sdc::kNoiseThreads * sdc::kNoiseSeg, 0.f);
+    for (int i4 = 0; i4 < (int)inc.size() / 4; ++i4) {
+        float z[4];
+        sdc::noise_normals4(seed, episode, (uint32_t)i4, z);
+        for (int k = 0; k < 4; ++k) inc[i4 * 4 + k] = 0.02f * z[k];
+    }
+    std::vector<double> walk(n);
+    double acc = 0.0;
+    for (int i = 0; i < sdc::kNoiseThreads; ++i) {          // same segment structure as the kernel
+        double seg = 0.0;
+        for (int j = i * sdc::kNoiseSeg; j < (i + 1) * sdc::kNoiseSeg && j < n; ++j) { seg += (double)inc[j]; walk[j] = acc + seg; }
+        acc += seg;
+    }
+    double sum = 0.0;
+    for (int j = 0; j < n; ++j) sum += walk[j];
+    const double mean = sum / n;
+    double ss = 0.0;
+    for (int j = 0; j < n; ++j) ss += (walk[j] - mean) * (walk[j] - mean);
+    const double scale = 0.75 / std::sqrt(ss / n);
+    double* wt = S.weather + (size_t)env * 2 * S.win_len;
+    double* ww = wt + S.win_len;
+    for (int i = 0; i < S.win_len; ++i) { wt[i] = 0.0; ww[i] = 0.0; }
+    double tmin = INFINITY, tmax = -INFINITY;
+    for (int j = 0; j < n; ++j) {
+        const int t = (j + 96 * roll) % n;
+        if (t < t0) continue;
+        const double noise = walk[j] * scale;
+        const double vt = std::fmin(std::fmax(L.temp_base[j] + noise, 0.0), 45.0);
+        if (t < t0 + 2880) { tmin = std::fmin(tmin, vt); tmax = std::fmax(tmax, vt); }
+        if (t < t0 + S.win_len) {
+            wt[t - t0] = vt;
+            ww[t - t0] = std::fmin(std::fmax(L.wetb_base[j] + noise, 0.0), 45.0);
+        }
+    }
+    S.t_min[env] = tmin; S.t_max[env] = tmax;
+}
+
+static const char* launch_reset(Context&, const sdc::State& S, const int32_t* list, const int32_t* count, float* obs, float* share, void*) {
+    for (int i = 0; i < *count; ++i) {
+        const int env = list[i];
+        int day, hour, roll = 0;
+        if (S.pend_valid && S.pend_valid[env]) {
+            S.pend_valid[env] = 0;
+            day = S.pend_day[env]; hour = S.pend_hour[env];
+            memcpy(S.weather + (size_t)env * 2 * S.win_len, S.pend_weather + (size_t)env * 2 * S.win_len, 2 * S.win_len * sizeof(double));
+            S.t_min[env] = S.pend_tmin[env]; S.t_max[env] = S.pend_tmax[env];
+        } else {
+            const uint32_t ep = S.episode[env];
+            sdc::draw_episode_start(S.seed[env], ep, S.day_lo[env], S.day_hi[env], &day, &hour, &roll);
+            generate_weather(S, env, day * 96 + hour * 4, roll, ep);
+        }
+        S.episode[env] += 1;
+        memset(S.ls_ring + (size_t)env * (S.ls_mask + 1), 0, S.ls_mask + 1);
+        ObsRow o{obs + (size_t)env * 3 * SDC_OBS_DIM};
+        sdc::reset_scalar_state(S, env, day * 96 + hour * 4, o);
+        sdc::share_from_obs(o.row, share + (size_t)env * SDC_SHARE_DIM);
+    }
+    return nullptr;
+}
+
+static const char* launch_rebuild(Context&, const sdc::State& S, void*) {
+    for (int env = 0; env < S.n_envs; ++env) {
+        const int n = S.hist_len[env];
+        std::vector<float> v(S.hist + (size_t)env * S.hist_cap, S.hist + (size_t)env * S.hist_cap + n);
+        std::sort(v.begin(), v.end());
+        for (int j = 0; j < 2; ++j) {
+            float* lst = S.qlist + ((size_t)env * 2 + j) * sdc::kListCap;
+            int a = 0, m = 0;
+            if (n > 0) {
+                const int k = ((j == 0 ? 1 : 3) * (n - 1)) / 4;
+                a = k - (sdc::kListCap / 2 - 1); if (a + sdc::kListCap > n) a = n - sdc::kListCap; if (a < 0) a = 0;
+                m = n - a < sdc::kListCap ? n - a : sdc::kListCap;
+                for (int i = 0; i < m; ++i) lst[i] = v[a + i];
+            }
+            S.q_a[env * 2 + j] = a; S.q_m[env * 2 + j] = m;
+        }
+    }
+    return nullptr;
+}
+}  // namespace backend
+
+#include "../../dc-rl_b200/csrc/sdc_api.inc"
