@@ -64,6 +64,7 @@ _PROTOS = {
     "sdc_prefill_history": (C.c_int, [_P, _P, C.c_int32, C.c_int32]),
     "sdc_rebuild_brackets": (C.c_int, [_P, _P]),
     "sdc_read_state": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64]),
+    "sdc_write_state": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64]),
     "sdc_state_bytes": (C.c_size_t, [_P]),
     "sdc_get_state": (C.c_int, [_P, _P, C.c_size_t]),
     "sdc_set_state": (C.c_int, [_P, _P, C.c_size_t]),

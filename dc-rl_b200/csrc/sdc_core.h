@@ -239,6 +239,9 @@ struct StepResult {
     int tasks_in_queue, tasks_dropped, overdue;
 };
 
+// The part of StepResult that has to survive the window scan (kept small: it lives in registers).
+struct RewardInputs { double energy, nci_next, ls_penalty; };
+
 // One env-step of the three sub-envs + managers + observations + info (everything except the
 // reward normaliser).  InfoSink: void operator()(int col, float v).
 template <class ObsSink, class InfoSink>
@@ -577,7 +580,7 @@ SDC_HDN void reward_prepare(const State& S, int env, double energy, ScanRequest&
 }
 
 // Extends the brackets with the ranks found by the scan and turns the moments into the three rewards.
-SDC_HDN void reward_finish(const State& S, int env, const ScanRequest& rq, const ScanResult& rs, const StepResult& st,
+SDC_HDN void reward_finish(const State& S, int env, const ScanRequest& rq, const ScanResult& rs, const RewardInputs& st,
                            float* rew3) {
     int err = 0;
     const int n = rq.n;

@@ -188,6 +188,10 @@ class Engine:
         out = out[:got // dt.itemsize]
         return out.reshape(n, -1) if out.size != n else out
 
+    def write_state(self, name, values):
+        v = np.ascontiguousarray(values, _STATE_DTYPES[name])
+        self._check(self.lib.sdc_write_state(self._h, name.encode(), _ptr(v), v.nbytes))
+
     def get_state(self):
         nbytes = self.lib.sdc_state_bytes(self._h)
         blob = np.zeros(nbytes, np.uint8)

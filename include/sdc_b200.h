@@ -159,6 +159,9 @@ int sdc_rebuild_brackets(sdc_env* env, void* stream);
  * "setpoint","bat_load","hist_len","hist","ls_len","err","qlist","q_a","q_m"; returns bytes written
  * or a negative code. */
 int64_t sdc_read_state(sdc_env* env, const char* name, void* out, int64_t capacity_bytes);
+/* Overwrites one named per-env state array from host memory (exact size required) -- resume / tests /
+ * de-synchronising episode phases.  Writing "hist" or "hist_len" requires sdc_rebuild_brackets afterwards. */
+int64_t sdc_write_state(sdc_env* env, const char* name, const void* src, int64_t bytes);
 size_t sdc_state_bytes(sdc_env* env);
 int sdc_get_state(sdc_env* env, void* blob, size_t bytes);
 int sdc_set_state(sdc_env* env, const void* blob, size_t bytes);

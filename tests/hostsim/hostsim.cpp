@@ -74,7 +74,8 @@ static const char* launch_step(Context&, const sdc::State& S, const StepArgs& a,
         sdc::ScanRequest rq; sdc::ScanResult rs;
         sdc::reward_prepare(S, env, st.energy, rq);
         scan_window(S, env, rq, rs);
-        sdc::reward_finish(S, env, rq, rs, st, a.rew + (size_t)env * 3);
+        sdc::RewardInputs en{st.energy, st.nci_next, st.ls_penalty};
+        sdc::reward_finish(S, env, rq, rs, en, a.rew + (size_t)env * 3);
         a.done[env] = (uint8_t)st.terminal;
         if (st.terminal) {
             if (a.term_obs) memcpy(a.term_obs + (size_t)env * 3 * SDC_OBS_DIM, obs.row, 3 * SDC_OBS_DIM * sizeof(float));

@@ -29,3 +29,28 @@ def test_long_replay_window_saturates(lib):
     assert w["err_flags"] == 0
     assert w["rew"] <= 1e-4 and w["info"] <= 1e-6, w
     assert int(w["engine"].read_state("hist_len")[0]) == 10000
+
+
+def test_batched_mixed_locations_vs_oracle(lib):
+    import scenarios
+    scenarios.batched_mixed_locations_vs_oracle(lib, cuda=False, N=24)
+
+
+def test_rolling_quartiles_with_ties_and_small_windows(lib):
+    import scenarios
+    scenarios.rolling_quartiles_with_ties_and_small_windows(lib)
+
+
+def test_prefill_and_constant_history_branches(lib):
+    import scenarios
+    scenarios.prefill_and_constant_history_branches(lib)
+
+
+def test_state_blob_roundtrip(lib):
+    import scenarios
+    scenarios.state_blob_roundtrip(lib)
+
+
+def test_generated_resets_cover_the_start_range(lib):
+    import scenarios
+    scenarios.device_generated_resets_match_host_statement(lib)
