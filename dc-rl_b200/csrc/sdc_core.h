@@ -253,9 +253,14 @@ SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat
     const int t = S.t[env];
     const int q = t;                                     // quarter-hour stamp == trace index
     if (t + 18 > SDC_YEAR_STEPS) err |= SDC_F_TRACE_DOMAIN;    // the reference crashes here
-    a_ls = a_ls < 0 ? 0 : (a_ls > 2 ? 2 : a_ls);
-    a_dc = a_dc < 0 ? 0 : (a_dc > 2 ? 2 : a_dc);
-    a_bat = a_bat < 0 ? 0 : (a_bat > 2 ? 2 : a_bat);
+    // Out-of-range action ids saturate to {0, 2}.  All branches below test the RAW ids and the reported
+    // ids are clamped in fp32: nvcc 12.9 ptxas for sm_100a miscompiles `x = clamp(x,0,2); if (x == 0) .. else
+    // if (x == 2) ..` into VIMNMX.RELU with a predicate output that does not mean `x == 2` (reproduced on
+    // B200 with scratch-size kernels, see DESIGN.md "toolchain notes"); build() rejects SASS of that form.
+    const bool ls_defer = a_ls <= 0, ls_process = a_ls >= 2;
+    const bool dc_down = a_dc <= 0, dc_up = a_dc >= 2;
+    const bool bat_charge = a_bat <= 0, bat_discharge = a_bat == 1;
+    const float a_ls_f = fminf(fmaxf((float)a_ls, 0.f), 2.f), a_bat_f = fminf(fmaxf((float)a_bat, 0.f), 2.f);
 
     // ------------------------------------------------------------------------------------------
     // Load shifting (envs/carbon_ls.py:172-324).  The FIFO is a ring of task counts per stamp.
@@ -298,7 +303,7 @@ SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat
     cap = 90 - (ns + sh + otp);
     int dropped = 0, proc = 0;
     double util;
-    if (a_ls == 0) {                                                                  // defer   :231-242
+    if (ls_defer) {                                                                   // defer   :231-242
         int add = kQueueMax - len; add = sh < add ? sh : add;
         dropped = sh - add;
         if (add > 0) {
@@ -307,7 +312,7 @@ SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat
             len += add; sum += add * q; b0 += add;
         }
         util = (double)(otp + (sh - add)) / 100;
-    } else if (a_ls == 2) {                                                           // process :244-264
+    } else if (ls_process) {                                                          // process :244-264
         if (cap >= 1) {
             proc = sh < cap ? sh : cap; proc = proc < len ? proc : len;
             pop_oldest(proc);
@@ -335,7 +340,7 @@ SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat
     S.ls_bins[env * 4 + 0] = (uint16_t)b0; S.ls_bins[env * 4 + 1] = (uint16_t)b1;
     S.ls_bins[env * 4 + 2] = (uint16_t)b2; S.ls_bins[env * 4 + 3] = (uint16_t)b3;
     const double hour_now = (double)(t % 96) * 0.25;
-    info(I_LS_ORIG_WORKLOAD, (float)w); info(I_LS_SHIFTED_WORKLOAD, (float)util); info(I_LS_ACTION, (float)a_ls);
+    info(I_LS_ORIG_WORKLOAD, (float)w); info(I_LS_SHIFTED_WORKLOAD, (float)util); info(I_LS_ACTION, a_ls_f);
     info(I_LS_NORM_LOAD_LEFT, 0.f); info(I_LS_UNASSIGNED, 0.f); info(I_LS_PENALTY_FLAG, 0.f);
     info(I_LS_QUEUE_MAX_LEN, (float)kQueueMax); info(I_LS_TASKS_IN_QUEUE, (float)len);
     info(I_LS_NORM_TASKS_IN_QUEUE, (float)ls.norm_q); info(I_LS_TASKS_DROPPED, (float)dropped);
@@ -349,10 +354,10 @@ SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat
     // Data centre (envs/dc_gym.py:142-237; envs/datacenter.py)
     // ------------------------------------------------------------------------------------------
     if (!(util >= 0.0 && util <= 1.0)) { err |= SDC_F_CPU_LOAD_RANGE; util = clampd(util, 0.0, 1.0); }
-    const int delta = a_dc - 1;                                   // {0:-1, 1:0, 2:+1}  make_envs_pyenv.py:127-131
+    const int delta = dc_down ? -1 : (dc_up ? 1 : 0);             // {0:-1, 1:0, 2:+1}  make_envs_pyenv.py:127-131
     int run = S.dc_run[env], scale = S.dc_scale[env];
     const int last = S.dc_last[env];                              // 2 == None (after reset, dc_gym.py:115)
-    if (delta == last && a_dc != 0) { run += 1; } else { run = 1; scale = 1; }    // dc_gym.py:163-167
+    if (delta == last && !dc_down) { run += 1; } else { run = 1; scale = 1; }    // dc_gym.py:163-167
     if (run > 3) scale += 1;                                                          // :170-171
     double sp = S.setpoint[env] + (double)(delta * scale);
     sp = fmax(fmin(sp, kSpMax), kSpMin);                                              // :173-174
@@ -415,14 +420,14 @@ SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat
     double b = S.bat_load[env];
     const double soc0 = b / capb;
     double energy, co2;
-    if (a_bat == 0) {                                            // charge
+    if (bat_charge) {                                            // charge
         const double t_u = round_dec(0.5 * (1 - sigmoid(10 * (soc0 - 0.5))), 1e4) * 15 / 60;
         const double max_c = fmin(capb * 0.1, (capb - b) / (t_u - (-0.04)));
         const double chg = fmin(max_c, capb) * t_u;
         b = round_dec(b + chg, 1e8);
         energy = dcl * 1e3 * 0.25 + chg * 1e3;
         co2 = energy * ci_now;
-    } else if (a_bat == 1) {                                     // discharge
+    } else if (bat_discharge) {                                  // discharge
         const double t_u = fmax(0.5, 4 * sigmoid(10 * (soc0 - 0.25))) * 15 / 60;
         const double max_d = fmin(fmin(capb, b / (0.01 + t_u)), dcl / 4);
         b = round_dec(b - fmin(max_d, capb) * t_u, 1e8);
@@ -436,7 +441,7 @@ SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat
     }
     S.bat_load[env] = b;
     const double soc = b / capb;
-    info(I_BAT_ACTION, (float)a_bat); info(I_BAT_SOC, (float)soc); info(I_BAT_CO2, (float)co2);
+    info(I_BAT_ACTION, a_bat_f); info(I_BAT_SOC, (float)soc); info(I_BAT_CO2, (float)co2);
     info(I_BAT_AVG_CI, (float)ci_now); info(I_BAT_E_WITHOUT, (float)(dcl * 1e3 * 0.25)); info(I_BAT_E_WITH, (float)energy);
     info(I_BAT_MAX_CAP, (float)capb); info(I_BAT_DCLOAD_MIN, (float)(P.power_lb_kw / 4));
     info(I_BAT_DCLOAD_MAX, (float)(P.power_ub_kw / 4));
