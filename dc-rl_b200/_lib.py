@@ -70,6 +70,7 @@ _PROTOS = {
     "sdc_set_state": (C.c_int, [_P, _P, C.c_size_t]),
     "sdc_error_flags": (_P, [_P]),
     "sdc_launch_count": (C.c_int64, [_P]),
+    "sdc_kernel_times": (C.c_int, [_P, _P]),
     "sdc_set_tuning": (C.c_int, [_P, C.c_char_p, C.c_int32]),
 }
 EXPORTS = tuple(_PROTOS)

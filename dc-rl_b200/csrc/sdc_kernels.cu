@@ -64,6 +64,12 @@ static const char* pinned_alloc(Context&, void** p, size_t bytes) { CU(cudaMallo
 static void pinned_free(Context&, void* p) { cudaFreeHost(p); }
 static const char* stream_create(Context&, void** s) { cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); *s = st; return nullptr; }
 static const char* stream_sync(Context&, void* s) { CU(cudaStreamSynchronize((cudaStream_t)s)); return nullptr; }
+static const char* event_create(Context&, void** ev) { cudaEvent_t e; CU(cudaEventCreate(&e)); *ev = e; return nullptr; }
+static const char* event_record(Context&, void* ev, void* st) { CU(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)st)); return nullptr; }
+static const char* event_elapsed_ms(Context&, void* a, void* b, double* ms) {
+    float f = 0.f; CU(cudaEventElapsedTime(&f, (cudaEvent_t)a, (cudaEvent_t)b)); *ms = f; return nullptr;
+}
+static void event_destroy(Context&, void* ev) { cudaEventDestroy((cudaEvent_t)ev); }
 static const char* sync(Context& c) { CU(cudaSetDevice(c.device)); CU(cudaDeviceSynchronize()); return nullptr; }
 
 // =================================================================================================

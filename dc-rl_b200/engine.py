@@ -202,6 +202,12 @@ class Engine:
         blob = np.ascontiguousarray(blob, np.uint8)
         self._check(self.lib.sdc_set_state(self._h, _ptr(blob), blob.nbytes))
 
+    def kernel_times(self):
+        """(timed steps, sum k_step ms, sum k_reset ms, max k_step ms) since the last call; needs set_tuning(timing=1)."""
+        out = np.zeros(4, np.float64)
+        self._check(self.lib.sdc_kernel_times(self._h, _ptr(out)))
+        return out
+
     @property
     def error_flags_ptr(self):
         return self.lib.sdc_error_flags(self._h)

@@ -35,6 +35,10 @@ static void pinned_free(Context&, void* p) { free(p); }
 static const char* stream_create(Context&, void** s) { *s = nullptr; return nullptr; }
 static const char* stream_sync(Context&, void*) { return nullptr; }
 static const char* sync(Context&) { return nullptr; }
+static const char* event_create(Context&, void** ev) { *ev = nullptr; return nullptr; }
+static const char* event_record(Context&, void*, void*) { return nullptr; }
+static const char* event_elapsed_ms(Context&, void*, void*, double* ms) { *ms = 0.0; return nullptr; }
+static void event_destroy(Context&, void*) {}
 
 struct ObsRow {
     float* row;   // [3][26]
