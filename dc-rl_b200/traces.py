@@ -135,8 +135,13 @@ class LocationTraces:
         slow -= np.linspace(slow[0], slow[-1], HOURS)
         ci = 272.8 + 22 * np.sin(day - 1.0) + 12 * np.sin(year * 2) + np.clip(slow, -60, 60) * 0.4 + 6 * rng.standard_normal(HOURS)
         ci = np.clip(ci, 120, 420)
-        front = np.cumsum(rng.standard_normal(HOURS)) * 0.35
-        front -= np.linspace(front[0], front[-1], HOURS)
+        # synoptic fronts: AR(1) with a ~3-day correlation time, sigma ~3.5 C (never pins a month below freezing)
+        shocks = rng.standard_normal(HOURS) * 3.5 * np.sqrt(1 - 0.986 ** 2)
+        front = np.empty(HOURS)
+        acc = 0.0
+        for i in range(HOURS):
+            acc = 0.986 * acc + shocks[i]
+            front[i] = acc
         dry = mean_t - 11.5 * np.cos(year) + 4.0 * np.sin(day - 2.4) + np.clip(front, -9, 9)
         wet = dry - rng.uniform(1.0, 5.0, HOURS)
         return cls(cpu, ci, dry, wet, "synthetic-" + location)

@@ -1,0 +1,270 @@
+"""`CudaShareVecEnv`: N SustainDC envs on one GPU behind harl's ``ShareVecEnv`` surface.
+
+Replaces ``ShareSubprocVecEnv([HARLSustainDCEnv] * N)`` (reference harl/envs/env_wrappers.py:222-297 over
+harl/envs/sustaindc/harlsustaindc_env.py:10-210): same attributes, same ``reset()`` / ``step(actions)`` return
+shapes and dtypes, same auto-reset contract (when an env finishes, the returned obs / share_obs are the post-reset
+ones and ``infos[i][0]`` carries ``original_obs`` / ``original_state`` / ``original_avail_actions``,
+env_wrappers.py:173-192), so ``harl.runners`` drive it unchanged.  One process, one CUDA library handle, no pipes.
+"""
+import os
+
+import numpy as np
+
+from . import info_layout
+from ._lib import N_AGENTS, OBS_DIM, SHARE_DIM
+from .dc_config import load_dc_config, size_datacenter
+from .engine import Engine
+from .traces import LocationTraces, location_key
+
+AGENTS = ("agent_ls", "agent_dc", "agent_bat")
+OBS_WIDTH = {"agent_ls": 26, "agent_dc": 14, "agent_bat": 13}
+
+
+class Box:
+    """Minimal stand-in for gymnasium.spaces.Box (the runners only read the class name, shape, low, high)."""
+
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        shape = tuple(shape) if shape is not None else np.shape(low)
+        self.shape = shape
+        self.low = np.broadcast_to(np.asarray(low, self.dtype), shape).copy()
+        self.high = np.broadcast_to(np.asarray(high, self.dtype), shape).copy()
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+    def __repr__(self):
+        return "Box(%s, %s, %s, %s)" % (self.low.min(), self.high.max(), self.shape, self.dtype)
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = int(n)
+        self.shape = ()
+        self.dtype = np.dtype(np.int64)
+
+    def sample(self):
+        return int(np.random.randint(self.n))
+
+    def __repr__(self):
+        return "Discrete(%d)" % self.n
+
+
+def make_spaces(nonoverlapping_shared_obs_space=True):
+    """Spaces as the HARL adapter exposes them after supersuit padding (harlsustaindc_env.py:25-34,
+    sustaindc_ptzoo.py:24-44; sub-env boxes: carbon_ls.py:40-45, make_envs_pyenv.py:114-132, bat_env_fwd_view.py:23-27)."""
+    obs = [Box(-2.0, 2.0, (OBS_DIM,)), Box(-5.0e9, 5.0e9, (OBS_DIM,)), Box(-2.0, 2.0, (OBS_DIM,))]
+    if nonoverlapping_shared_obs_space:
+        share = [Box(-2.0, 2.0, (SHARE_DIM,)) for _ in range(N_AGENTS)]
+    else:
+        share = [Box(0.0, 1.0, (OBS_DIM * N_AGENTS,)) for _ in range(N_AGENTS)]
+    act = [Discrete(3) for _ in range(N_AGENTS)]
+    return obs, share, act
+
+
+def resolve_traces(location, workload_file="Alibaba_CPU_Data_Hourly_1.csv", data_root=None, traces=None):
+    """Traces for a location: an explicit LocationTraces, the reference's data/ tree (``data_root`` or
+    $SDC_DATA_ROOT), or -- only when asked for with traces='synthetic' -- the seeded synthetic year."""
+    if isinstance(traces, LocationTraces):
+        return traces
+    if traces == "synthetic":
+        return LocationTraces.synthetic(location_key(location))
+    root = data_root or os.environ.get("SDC_DATA_ROOT")
+    if root and os.path.isdir(root):
+        return LocationTraces.from_reference_data(root, location, workload_file)
+    raise FileNotFoundError(
+        "no trace data for location %r: pass env_args['data_root'] (the reference's data/ directory), set SDC_DATA_ROOT, "
+        "or request env_args['traces']='synthetic'" % location)
+
+
+_UNSUPPORTED_REWARDS = "only the default reward methods (default_{ls,dc,bat}_reward) run on the device"
+
+
+class InfoRow:
+    """Dict-like view of one env's info (the reference merges all sub-env infos into every agent's dict,
+    sustaindc_env.py:676-710).  Supports [], get, in, keys, items, assignment of extra keys."""
+    __slots__ = ("_b", "_i", "_extra")
+
+    def __init__(self, batch, i, extra):
+        self._b, self._i, self._extra = batch, i, extra
+
+    def _lookup(self, key):
+        if key in self._extra:
+            return self._extra[key]
+        b, i = self._b, self._i
+        col = info_layout.COL.get(key)
+        if col is not None:
+            v = float(b.table[col, i])
+            return bool(v) if key == info_layout.INFO_TERMINAL_KEY else v
+        if key == info_layout.INFO_HIST_KEY:
+            return b.table[info_layout.HIST0:info_layout.HIST0 + 5, i].astype(np.float64)
+        if key == info_layout.INFO_FORECAST_KEY:
+            return b.table[info_layout.FORECAST0:info_layout.FORECAST0 + 8, i].astype(np.float64)
+        if key == "bat_a_t":
+            return info_layout.BAT_ACTION_NAMES[int(b.table[info_layout.COL["bat_action"], i])]
+        raise KeyError(key)
+
+    def __getitem__(self, key):
+        return self._lookup(key)
+
+    def __setitem__(self, key, value):
+        self._extra[key] = value
+
+    def get(self, key, default=None):
+        try:
+            return self._lookup(key)
+        except KeyError:
+            return default
+
+    def __contains__(self, key):
+        return key in self._extra or key in info_layout.COL or key in _VECTOR_KEYS
+
+    def keys(self):
+        return list(info_layout.INFO_SCALAR_KEYS) + [info_layout.INFO_HIST_KEY] + list(info_layout.INFO_DC_KEYS) + list(
+            info_layout.INFO_COMMON_KEYS) + [info_layout.INFO_FORECAST_KEY, info_layout.INFO_TERMINAL_KEY, "bat_a_t"] + list(self._extra)
+
+    def items(self):
+        return [(k, self._lookup(k)) for k in self.keys()]
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self.keys())
+
+    def to_dict(self):
+        return dict(self.items())
+
+
+_VECTOR_KEYS = (info_layout.INFO_HIST_KEY, info_layout.INFO_FORECAST_KEY, "bat_a_t")
+
+
+class InfoBatch:
+    """``infos`` of one vec-env step: ``len(infos) == N``, ``infos[i][agent]`` is an InfoRow.  Backed by one
+    [64, N] float table copied from the device; nothing per-env is materialised until it is indexed."""
+
+    def __init__(self, table, extras):
+        self.table = table                      # [INFO_STRIDE, N] float32 (a copy owned by this object)
+        self._extras = extras                   # {env index: dict of extra keys for agent 0}
+        self._rows = {}
+
+    def __len__(self):
+        return self.table.shape[1]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        i = int(i)
+        if i < 0:
+            i += len(self)
+        row = self._rows.get(i)
+        if row is None:
+            extra0 = self._extras.setdefault(i, {})
+            row = [InfoRow(self, i, extra0)] + [InfoRow(self, i, {}) for _ in range(N_AGENTS - 1)]
+            self._rows[i] = row
+        return row
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def column(self, key):
+        """Vectorised access: one info key for all envs (fast path for loggers)."""
+        return self.table[info_layout.COL[key]]
+
+
+class CudaShareVecEnv:
+    """harl ``ShareVecEnv`` surface over one `Engine` (see module docstring)."""
+
+    def __init__(self, env_args, n_envs, seed=0, months=None, seeds=None, device=0, lib=None, first_env_id=0):
+        args = dict(env_args)
+        for key in ("ls_reward", "dc_reward", "bat_reward"):
+            if args.get(key, "default_%s" % key) != "default_%s" % key:
+                raise NotImplementedError(_UNSUPPORTED_REWARDS)
+        self.env_args = args
+        self.num_envs = int(n_envs)
+        self.n_agents = N_AGENTS
+        self.nonoverlapping = bool(args.get("nonoverlapping_shared_obs_space", False))
+        self.observation_space, self.share_observation_space, self.action_space = make_spaces(self.nonoverlapping)
+        location = args.get("location", "ny")
+        traces = resolve_traces(location, args.get("workload_file", "Alibaba_CPU_Data_Hourly_1.csv"), args.get("data_root"),
+                                args.get("traces"))
+        cfg_file = args.get("dc_config_file", "dc_config.json")
+        cfg = cfg_file if isinstance(cfg_file, dict) else _find_dc_config(cfg_file, args.get("data_root"))
+        params, self.derived = size_datacenter(location, cfg, args.get("datacenter_capacity_mw", 1))
+        ids = np.arange(first_env_id, first_env_id + self.num_envs)
+        if months is None:
+            if "month" in args:                                   # harl/utils/envs_tools.py:56-62
+                months = np.full(self.num_envs, int(args["month"]))
+            else:
+                months = np.where(ids < 12, ids % 12, ids % 3 + 5)
+        if seeds is None:
+            seeds = (int(seed) + ids * 1000).astype(np.uint64)   # envs_tools.py:67
+        self.engine = Engine(self.num_envs, [traces], [params], months=months, seeds=seeds,
+                             days_per_episode=int(args.get("days_per_episode", 7)), device=device, lib=lib)
+        self.closed = False
+        self._avail = np.ones((self.num_envs, N_AGENTS, 3), np.float32)
+
+    # ---- ShareVecEnv API -----------------------------------------------------------------------
+    def _share(self, obs, share):
+        if self.nonoverlapping:
+            return np.repeat(share[:, None, :], N_AGENTS, axis=1)
+        flat = obs.reshape(self.num_envs, 1, N_AGENTS * OBS_DIM)
+        return np.repeat(flat, N_AGENTS, axis=1)
+
+    def reset(self):
+        obs, share = self.engine.reset_host()
+        obs = obs.copy()
+        return obs, self._share(obs, share), self._avail.copy()
+
+    def step(self, actions):
+        a = np.asarray(actions).reshape(self.num_envs, N_AGENTS)
+        obs, share, rew, done, info, term = self.engine.step_host(a, want_info=True, want_term=True)
+        obs = obs.copy()
+        share_obs = self._share(obs, share)
+        extras = {}
+        finished = np.nonzero(done)[0]
+        if len(finished):
+            term_share = np.concatenate([term[:, 0, :], term[:, 1, 11:12], term[:, 1, 13:14], term[:, 2, 25:26]], axis=1)
+            for i in finished:
+                o = term[i].copy()
+                s = (np.repeat(term_share[i][None], N_AGENTS, 0) if self.nonoverlapping
+                     else np.repeat(o.reshape(1, -1), N_AGENTS, 0))
+                extras[int(i)] = {"original_obs": o, "original_state": s, "original_avail_actions": self._avail[i].copy()}
+        infos = InfoBatch(info.copy(), extras)
+        dones = np.repeat(done.astype(bool)[:, None], N_AGENTS, axis=1)
+        return obs, share_obs, rew.reshape(self.num_envs, N_AGENTS, 1).copy(), dones, infos, self._avail.copy()
+
+    def step_async(self, actions):
+        self._pending = actions
+
+    def step_wait(self):
+        return self.step(self._pending)
+
+    def close(self):
+        if not self.closed:
+            self.engine.close()
+            self.closed = True
+
+    # ---- extras --------------------------------------------------------------------------------
+    def metrics(self, clear=False):
+        """Device-side running sums of the logger's per-step keys (sustaindc_logger.py:86-101) as a dict."""
+        m = self.engine.metrics(clear)
+        return dict(zip(METRIC_NAMES, m.tolist()))
+
+
+METRIC_NAMES = ("bat_total_energy_with_battery_KWh", "bat_CO2_footprint", "dc_water_usage", "ls_tasks_in_queue", "ls_tasks_dropped",
+                "dc_ITE_total_power_kW", "dc_CT_total_power_kW", "dc_Compressor_total_power_kW", "dc_HVAC_total_power_kW",
+                "env_steps", "reward_sum", "episodes", "reward_ls_sum", "reward_dc_sum", "ls_overdue_penalty", "dc_total_power_kW")
+
+
+def _find_dc_config(name, data_root=None):
+    """'dc_config.json' -> built-in default; other names are looked up next to the data root's utils/."""
+    if name in (None, "dc_config.json"):
+        return None
+    if os.path.isfile(name):
+        return load_dc_config(name)
+    for base in filter(None, (data_root, os.environ.get("SDC_DATA_ROOT"))):
+        for cand in (os.path.join(base, name), os.path.join(os.path.dirname(base.rstrip("/")), "utils", name)):
+            if os.path.isfile(cand):
+                return load_dc_config(cand)
+    raise FileNotFoundError("dc_config_file %r not found" % name)
