@@ -34,6 +34,9 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 B_ALG_STEADY = 4 * 10000 + 1024      # bytes per env-step at H = 10 000
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch at N = 65 536 from the round-1 `ncu --set full`
+# capture (profiles/r01_kstep_ncu_raw.csv); only meaningful for the default --envs
+TRAFFIC_BYTES_PER_LAUNCH = 2.685226e9 + 12.06e6
 METRIC = "env-steps/sec at N=65536 parallel envs, 1/2/4/8xB200; HBM GB/s fraction"
 
 
@@ -154,8 +157,8 @@ def prepare(eng, n_envs, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=1500)
@@ -219,6 +222,8 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    eng.set_tuning(timing=1)
+    eng.kernel_times()
     launches0 = eng.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -234,6 +239,8 @@ def main():
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     launches = eng.launch_count - launches0
+    ktimes = eng.kernel_times()             # CUDA events recorded by the library on the launch stream
+    eng.set_tuning(timing=0)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -260,7 +267,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        k_ms = float(np.median(step_ms))
+        k_ms = float(ktimes[1] / max(ktimes[0], 1))          # mean k_step launch duration over the timed region
         achieved = B_ALG_STEADY * n / (k_ms / 1e3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
@@ -272,7 +279,9 @@ def main():
                     "call": "sdc_step_host (numpy actions in; obs, share_obs, rewards, dones out)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_step (+ k_reset, same event pair)", "launch_ms_median": k_ms,
+                         "traffic": TRAFFIC_BYTES_PER_LAUNCH if n == 65536 else None, "kernel": "k_step", "launch_ms_mean": k_ms,
+                         "launch_ms_max": float(ktimes[3]), "k_reset_ms_mean": float(ktimes[2] / max(ktimes[0], 1)),
+                         "step_ms_median": float(np.median(step_ms)),
                          "bytes_per_launch": B_ALG_STEADY * n, "peak_source": peak_src},
             "clocks": clocks, "env_error_flags": err,
         }
