@@ -23,7 +23,7 @@ namespace sdc {
 
 constexpr int kQueueMax = 1000;       // sustaindc_env.py:148-149
 constexpr int kListCap = 32;          // sorted quartile bracket, one element per lane
-constexpr int kWidenMargin = 4;       // extend a bracket side when fewer ranks than this remain
+constexpr int kWidenMargin = 6;       // extend a bracket side when fewer ranks than this remain
 constexpr double kSpMin = 15.0, kSpMax = 21.6;   // utils/make_envs_pyenv.py:124-126
 
 // ---- info table columns: keep in sync with dc-rl_b200/info_layout.py -------------------------
@@ -93,6 +93,18 @@ struct State {
     double* pend_weather;          // [N][2][win_len]
 };
 
+// Where the shared tables are read from (k_step points these at a shared-memory copy).
+struct Tables { const LocTables* loc; const sdc_dc_params* dc; };
+
+// Error flags are OR-ed atomically on the device: a reset worker and the env's step warp may both flag an env.
+SDC_HD void flag_error(const State& S, int env, int bits) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(S.err + env, bits);
+#else
+    S.err[env] |= bits;
+#endif
+}
+
 SDC_HD double round_dec(double x, double scale) { return rint(x * scale) / scale; }   // np.round(x, d)
 SDC_HD double sigmoid(double x) { return 1.0 / (1.0 + exp(-x)); }
 SDC_HD double clampd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
@@ -141,50 +153,69 @@ SDC_HD void trend_features(double cur, const double* v, double* out5) {
 
 struct LsStats { double oldest, avg, norm_q, hist[5]; };
 
+// Per-episode normalisation constants of an env (CI_Manager / Weather_Manager 30-day min-max).
+struct Norms { double cmin, crng, tmin, trng; int t0; };
+
 // Builds the three observations at trace index t. Sink: void operator()(int agent, int idx, float v).
 // Layouts: SURVEY.md A.6 / sustaindc_env.py:302-433.
+// All trace reads are issued first, in one straight-line batch, so that their memory latencies overlap: under the
+// HBM-saturating window scans of the other warps a dependent global read costs ~2 us (profiles/r01_summary.md).
 template <class Sink>
-SDC_HDN void build_obs(const State& S, int env, int t, const LsStats& ls, double soc, Sink& sink) {
-    const LocTables& L = S.loc[S.loc_id[env]];
-    const double cmin = S.ci_min[env], crng = S.ci_max[env] - S.ci_min[env];
-    const double tmin = S.t_min[env], trng = S.t_max[env] - S.t_min[env];
-    const double* wtemp = S.weather + (size_t)env * 2 * S.win_len;
-    const int wi = t - S.t0[env];
+SDC_HDN void build_obs(const State& S, const Tables& T, int env, int t, const LsStats& ls, double soc, const Norms& nm, Sink& sink) {
+    const LocTables& L = T.loc[S.loc_id[env]];
+    const double* wtemp = S.weather + (size_t)env * 2 * S.win_len + (t - nm.t0);
+    const int tp = t >= 16 ? t - 16 : 0;              // start of the 16-sample past window (empty before t = 16)
+#ifndef SDC_LAZY_OBS_LOADS
+    double ci_raw[25], wt_raw[17];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ci_raw[i] = L.ci[tp + i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ci_raw[16 + i] = L.ci[t + i];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) wt_raw[i] = wtemp[i];
+#else
+    const double* ci_raw = L.ci + tp;        // experiment: read where used
+    const double* wt_raw = wtemp;
+    const int ci_shift = t - tp - 16;        // 0 unless t < 16
+#define SDC_CI_NOW(i) L.ci[t + (i)]
+#endif
+    const double w = L.workload[t], w_next = L.workload[t + 1];
     const int hq = t % 96;
     const double cos_h = S.hour_cos[hq], sin_h = S.hour_sin[hq];
 
     // carbon-intensity features: x[0..8] = cur, fut[8]; past[16]
     double x[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) x[i] = (L.ci[t + i] - cmin) / crng;
+#ifndef SDC_LAZY_OBS_LOADS
+    for (int i = 0; i < 9; ++i) x[i] = (ci_raw[16 + i] - nm.cmin) / nm.crng;
+#else
+    for (int i = 0; i < 9; ++i) x[i] = (SDC_CI_NOW(i) - nm.cmin) / nm.crng;
+    (void)ci_shift;
+#endif
     double f_ci[7];
     {
         double sm[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) sm[i] = (((x[i] + x[i + 1]) + x[i + 2]) + x[i + 3]) / 4;
         f_ci[0] = ols_slope<6>(sm);
-        if (t >= 16) {
-            double p[17];
+        double p[17];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) p[i] = (L.ci[t - 16 + i] - cmin) / crng;
-            p[16] = x[0];
-            double smp[14];
+        for (int i = 0; i < 16; ++i) p[i] = (ci_raw[i] - nm.cmin) / nm.crng;
+        p[16] = x[0];
+        double smp[14];
 #pragma unroll
-            for (int i = 0; i < 14; ++i) smp[i] = (((p[i] + p[i + 1]) + p[i + 2]) + p[i + 3]) / 4;
-            f_ci[1] = ols_slope<14>(smp);
-        } else {
-            f_ci[1] = 0.0;   // empty past window at the start of the year
-        }
+        for (int i = 0; i < 14; ++i) smp[i] = (((p[i] + p[i + 1]) + p[i + 2]) + p[i + 3]) / 4;
+        // empty past window at the start of the year -> zero slope
+        f_ci[1] = t >= 16 ? ols_slope<14>(smp) : 0.0;
         trend_features<8>(x[0], x + 1, f_ci + 2);
     }
     // temperature features: nt[0..16] = normT[t..t+16]
     double nt[17];
 #pragma unroll
-    for (int i = 0; i < 17; ++i) nt[i] = (wtemp[wi + i] - tmin) / trng;
+    for (int i = 0; i < 17; ++i) nt[i] = (wt_raw[i] - nm.tmin) / nm.trng;
     double f_t[6];
     f_t[0] = ols_slope<17>(nt);
     trend_features<16>(nt[0], nt + 1, f_t + 1);
-    const double w = L.workload[t], w_next = L.workload[t + 1];
 
     // agent_ls [26]
     int k = 0;
@@ -237,6 +268,9 @@ struct StepResult {
     // logger metrics of this step
     double co2, water, ite_kw, ct_kw, comp_kw, hvac_kw, total_kw;
     int tasks_in_queue, tasks_dropped, overdue;
+    // reward window cursor and the value the new sample evicts (read early, with the other state)
+    int hist_len, hist_head;
+    float evicted;
 };
 
 // The part of StepResult that has to survive the window scan (kept small: it lives in registers).
@@ -245,13 +279,40 @@ struct RewardInputs { double energy, nci_next, ls_penalty; };
 // One env-step of the three sub-envs + managers + observations + info (everything except the
 // reward normaliser).  InfoSink: void operator()(int col, float v).
 template <class ObsSink, class InfoSink>
-SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat, ObsSink& obs, InfoSink& info,
+SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, int a_dc, int a_bat, ObsSink& obs, InfoSink& info,
                           StepResult& out) {
-    const LocTables& L = S.loc[S.loc_id[env]];
-    const sdc_dc_params& P = S.dc[S.cfg_id[env]];
-    int err = 0;
-    const int t = S.t[env];
+    // ---- level 1: every per-env scalar, issued back to back (no stores in between) ----
+    const int t = S.t[env], t0 = S.t0[env], step0 = S.step_in_ep[env];
+    int head = S.ls_head[env], len = S.ls_len[env], sum = S.ls_sum[env];
+    int b0 = S.ls_bins[env * 4 + 0], b1 = S.ls_bins[env * 4 + 1], b2 = S.ls_bins[env * 4 + 2], b3 = S.ls_bins[env * 4 + 3];
+    const double sp0 = S.setpoint[env];
+    int run = S.dc_run[env], scale = S.dc_scale[env];
+    const int last = S.dc_last[env];                              // 2 == None (after reset, dc_gym.py:115)
+    double b = S.bat_load[env];
+    Norms nm;
+    nm.cmin = S.ci_min[env]; nm.crng = S.ci_max[env] - nm.cmin;
+    nm.tmin = S.t_min[env]; nm.trng = S.t_max[env] - nm.tmin; nm.t0 = t0;
+    const int h_len = S.hist_len[env], h_head = S.hist_head[env];
+    const LocTables& L = T.loc[S.loc_id[env]];
+    const sdc_dc_params& P = T.dc[S.cfg_id[env]];
+    // ---- level 2: reads whose address depends on level 1 ----
     const int q = t;                                     // quarter-hour stamp == trace index
+    const int mask = S.ls_mask;
+    uint8_t* ring = S.ls_ring + (size_t)env * (S.ls_mask + 1);
+    const int m1 = ring[(q - 24) & mask], m2 = ring[(q - 48) & mask], m3 = ring[(q - 72) & mask], m4r = ring[(q - 96) & mask];
+    const double w = L.workload[t];
+    const int ns = L.ns[t], sh = L.sh[t];
+    const double* wtemp = S.weather + (size_t)env * 2 * S.win_len;
+    const double* wwetb = wtemp + S.win_len;
+    const int wi = t - t0;
+    const double ambient = wtemp[wi], wet_bulb = wwetb[wi], outside_next = wtemp[wi + 1];
+    const double ci_now = L.ci[t];
+    double ci_fut[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ci_fut[i] = L.ci[t + 2 + i];
+    out.hist_len = h_len; out.hist_head = h_head;
+    out.evicted = S.hist[(size_t)env * S.hist_cap + h_head];
+    int err = 0;
     if (t + 18 > SDC_YEAR_STEPS) err |= SDC_F_TRACE_DOMAIN;    // the reference crashes here
     // Out-of-range action ids saturate to {0, 2}.  All branches below test the RAW ids and the reported
     // ids are clamped in fp32: nvcc 12.9 ptxas for sm_100a miscompiles `x = clamp(x,0,2); if (x == 0) .. else
@@ -265,18 +326,11 @@ SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat
     // ------------------------------------------------------------------------------------------
     // Load shifting (envs/carbon_ls.py:172-324).  The FIFO is a ring of task counts per stamp.
     // ------------------------------------------------------------------------------------------
-    const double w = L.workload[t];
     if (w < 0.0 || w > 1.0) err |= SDC_F_WORKLOAD_RANGE;
-    const int ns = L.ns[t], sh = L.sh[t];
-    uint8_t* ring = S.ls_ring + (size_t)env * (S.ls_mask + 1);
-    const int mask = S.ls_mask;
-    int head = S.ls_head[env], len = S.ls_len[env], sum = S.ls_sum[env];
-    int b0 = S.ls_bins[env * 4 + 0], b1 = S.ls_bins[env * 4 + 1], b2 = S.ls_bins[env * 4 + 2], b3 = S.ls_bins[env * 4 + 3];
     int m4 = 0;
     if (len > 0) {
         // the clock moved one quarter-hour: tasks reaching an age of exactly 6/12/18/24 h change bin
-        const int m1 = ring[(q - 24) & mask], m2 = ring[(q - 48) & mask], m3 = ring[(q - 72) & mask];
-        m4 = ring[(q - 96) & mask];
+        m4 = m4r;
         b0 -= m1; b1 += m1 - m2; b2 += m2 - m3; b3 += m3 - m4;
     }
     int b4 = len - (b0 + b1 + b2 + b3);
@@ -355,18 +409,11 @@ SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat
     // ------------------------------------------------------------------------------------------
     if (!(util >= 0.0 && util <= 1.0)) { err |= SDC_F_CPU_LOAD_RANGE; util = clampd(util, 0.0, 1.0); }
     const int delta = dc_down ? -1 : (dc_up ? 1 : 0);             // {0:-1, 1:0, 2:+1}  make_envs_pyenv.py:127-131
-    int run = S.dc_run[env], scale = S.dc_scale[env];
-    const int last = S.dc_last[env];                              // 2 == None (after reset, dc_gym.py:115)
     if (delta == last && !dc_down) { run += 1; } else { run = 1; scale = 1; }    // dc_gym.py:163-167
     if (run > 3) scale += 1;                                                          // :170-171
-    double sp = S.setpoint[env] + (double)(delta * scale);
+    double sp = sp0 + (double)(delta * scale);
     sp = fmax(fmin(sp, kSpMax), kSpMin);                                              // :173-174
     S.setpoint[env] = sp; S.dc_run[env] = run; S.dc_scale[env] = scale; S.dc_last[env] = (int8_t)delta;
-    const double* wtemp = S.weather + (size_t)env * 2 * S.win_len;
-    const double* wwetb = wtemp + S.win_len;
-    const int wi = t - S.t0[env];
-    const double ambient = wtemp[wi], wet_bulb = wwetb[wi];
-
     const double load_pct = util * 100;
     double p_it = 0.0, sum_out = 0.0;
     for (int c = 0; c < P.n_classes; ++c) {                      // datacenter.py:157-181,250-317 per rack class
@@ -415,9 +462,7 @@ SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat
     // Battery (envs/bat_env_fwd_view.py:84-126,194-284; envs/battery_model.py:94-139)
     // ------------------------------------------------------------------------------------------
     const double dcl = total_kw / 1e3;                           // MW                 sustaindc_env.py:652
-    const double ci_now = L.ci[t];
     const double capb = P.bat_capacity_mwh;
-    double b = S.bat_load[env];
     const double soc0 = b / capb;
     double energy, co2;
     if (bat_charge) {                                            // charge
@@ -450,16 +495,15 @@ SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat
     // Managers advance (utils/managers.py:127-147,285-302,452-474,633-654), observations, info
     // ------------------------------------------------------------------------------------------
     const int tn = t + 1;
-    const int step_in_ep = S.step_in_ep[env] + 1;
+    const int step_in_ep = step0 + 1;
     S.t[env] = tn; S.step_in_ep[env] = step_in_ep;
     const int terminal = step_in_ep >= S.ep_len;
-    build_obs(S, env, tn, ls, soc, obs);
-    const double cmin = S.ci_min[env], crng = S.ci_max[env] - S.ci_min[env];
-    const double nci_next = (L.ci[tn + 1] - cmin) / crng;
-    info(I_OUTSIDE_TEMP, (float)wtemp[wi + 1]); info(I_DAY, (float)(tn / 96)); info(I_HOUR, (float)((tn % 96) * 0.25));
+    build_obs(S, T, env, tn, ls, soc, nm, obs);
+    const double nci_next = (ci_fut[0] - nm.cmin) / nm.crng;
+    info(I_OUTSIDE_TEMP, (float)outside_next); info(I_DAY, (float)(tn / 96)); info(I_HOUR, (float)((tn % 96) * 0.25));
     info(I_NORM_CI, (float)nci_next);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) info(I_FORECAST0 + i, (float)((L.ci[tn + 1 + i] - cmin) / crng));
+    for (int i = 0; i < 8; ++i) info(I_FORECAST0 + i, (float)((ci_fut[i] - nm.cmin) / nm.crng));
     info(I_ISTERMINAL, terminal ? 1.f : 0.f);
 
     out.energy = energy; out.nci_next = nci_next;
@@ -468,28 +512,33 @@ SDC_HDN void physics_step(const State& S, int env, int a_ls, int a_dc, int a_bat
     out.co2 = co2; out.water = water; out.ite_kw = p_it / 1e3; out.ct_kw = ct / 1e3; out.comp_kw = comp / 1e3;
     out.hvac_kw = (ct + comp) / 1e3; out.total_kw = total_kw;
     out.tasks_in_queue = len; out.tasks_dropped = dropped; out.overdue = over;
-    if (err) S.err[env] |= err;
+    if (err) flag_error(S, env, err);
 }
 
 // ---- rolling quartiles: exact order statistics kept in a small sorted bracket -----------------
-// For each quartile j the list qlist[env][j][0..m) holds the order statistics of the window at ranks
+// For each quartile j the list lst[j][0..m) holds the order statistics of the window at ranks
 // a .. a+m-1 (rank-contiguous, ties allowed).  One value enters and at most one leaves per step, so a
 // rank moves by at most one list position per step; the list is updated in O(1) here, and a side that
 // runs short (< kWidenMargin ranks beyond the needed pair) is extended by one rank from the full-window
-// scan of the same step (see ScanRequest / apply_widen).  Exactness does not depend on a distribution.
+// scan of the same step: at most one side per list per step, which is enough because the two margins of a
+// list cannot both shrink in the same step.  Exactness does not depend on the value distribution.
+struct QView {              // the caller stages the two lists (global rows, or shared memory in k_step)
+    float* lst[2];
+    int a[2], m[2];
+};
+enum ScanDir { SCAN_NONE = 0, SCAN_BELOW = 1, SCAN_ABOVE = 2 };
 struct ScanRequest {
     int n;                  // window length including the new value
     float lo, hi, shift;    // IQR fences and the centring shift of the moment sums
-    float below[2];         // count x < below[j], track max of those     (-inf: side not requested)
-    float above[2];         // count x > above[j], track min of those     (+inf: side not requested)
-    int widen;              // bit j: below[j] requested, bit 2+j: above[j] requested
+    int dir[2];             // per quartile list: SCAN_BELOW -> count x < thr and track their max (rank a-1),
+    float thr[2];           //                    SCAN_ABOVE -> count x > thr and track their min (rank a+m)
     int degenerate;         // q1 == q3: sigma is exactly 0 (utils/reward_creator.py:43-45 divides by 1)
-    double q1, q3;
+    double q1;
 };
 struct ScanResult {
     float s1, s2;           // sum(c - shift), sum((c - shift)^2) over the clipped window
-    int cnt_below[2], cnt_above[2];
-    float pred[2], succ[2];
+    int cnt[2];
+    float ext[2];
 };
 
 #if defined(__CUDA_ARCH__)
@@ -509,7 +558,7 @@ SDC_HD void list_remove(float* lst, int& a, int& m, float o, int& err) {
     m -= 1;
 }
 
-// r_target: list index that must stay inside (used to choose the side to drop from on overflow)
+// k_after: rank that must stay inside the list (chooses the side to drop from when the list is full)
 SDC_HD void list_insert(float* lst, int& a, int& m, float e, int n_after, int k_after) {
     if (m > 0 && e < lst[0] && a > 0) { a += 1; return; }
     if (m > 0 && e > lst[m - 1] && a + m < n_after - 1) return;     // ranks above the list, list not at the top
@@ -535,27 +584,26 @@ SDC_HD void list_insert(float* lst, int& a, int& m, float e, int n_after, int k_
     m += 1;
 }
 
-// Appends `energy` to the env's reward window (fp32 ring), updates both quartile brackets and returns
-// what the full-window scan must compute.  utils/reward_creator.py:16-45.
-SDC_HDN void reward_prepare(const State& S, int env, double energy, ScanRequest& rq) {
+// Appends `energy` to the env's reward window (fp32 ring; `o` = the value it evicts, if any), updates both
+// quartile brackets and returns what the full-window scan must compute.  utils/reward_creator.py:16-45.
+SDC_HDN void reward_prepare(const State& S, int env, double energy, int len, int head, float evicted, QView& Q, ScanRequest& rq) {
     int err = 0;
     float e = (float)energy;
     if (!(fabs(energy) <= 3.0e38)) { err |= SDC_F_NONFINITE; e = 0.f; }
     const int cap = S.hist_cap;
-    int len = S.hist_len[env], head = S.hist_head[env];
     float* h = S.hist + (size_t)env * cap;
     float o = 0.f; bool evict = false;
-    if (len == cap) { o = h[head]; evict = true; } else { len += 1; }
+    if (len == cap) { o = evicted; evict = true; } else { len += 1; }
     h[head] = e;
     head += 1; if (head == cap) head = 0;
     S.hist_len[env] = len; S.hist_head[env] = head;
     const int n = len;
-    rq.n = n; rq.widen = 0; rq.degenerate = 0;
-    rq.below[0] = rq.below[1] = -SDC_INF_F; rq.above[0] = rq.above[1] = SDC_INF_F;
+    rq.n = n; rq.degenerate = 0;
     double qv[2] = {0.0, 0.0};
     for (int j = 0; j < 2; ++j) {
-        float* lst = S.qlist + ((size_t)env * 2 + j) * kListCap;
-        int a = S.q_a[env * 2 + j], m = S.q_m[env * 2 + j];
+        float* lst = Q.lst[j];
+        int a = Q.a[j], m = Q.m[j];
+        rq.dir[j] = SCAN_NONE; rq.thr[j] = 0.f;
         const int num = (j == 0 ? 1 : 3) * (n - 1);
         const int k = num / 4;                                   // np.percentile 'linear': idx = (n-1)*p
         const double frac = (double)(num % 4) * 0.25;
@@ -570,45 +618,44 @@ SDC_HDN void reward_prepare(const State& S, int env, double energy, ScanRequest&
                 const double lo_v = lst[r], hi_v = lst[r + 1];
                 const double d = hi_v - lo_v;                    // numpy _lerp
                 qv[j] = (frac >= 0.5) ? hi_v - d * (1.0 - frac) : lo_v + d * frac;
-                if (a > 0 && r < kWidenMargin) { rq.widen |= 1 << j; rq.below[j] = lst[0]; }
-                if (a + m < n && (m - 2 - r) < kWidenMargin) { rq.widen |= 4 << j; rq.above[j] = lst[m - 1]; }
+                const int margin_lo = (a > 0) ? r : kListCap, margin_hi = (a + m < n) ? m - 2 - r : kListCap;
+                if (margin_lo < kWidenMargin && margin_lo <= margin_hi) { rq.dir[j] = SCAN_BELOW; rq.thr[j] = lst[0]; }
+                else if (margin_hi < kWidenMargin) { rq.dir[j] = SCAN_ABOVE; rq.thr[j] = lst[m - 1]; }
             }
         }
-        S.q_a[env * 2 + j] = a; S.q_m[env * 2 + j] = m;
+        Q.a[j] = a; Q.m[j] = m;
     }
     const double iqr = qv[1] - qv[0];
-    rq.q1 = qv[0]; rq.q3 = qv[1];
+    rq.q1 = qv[0];
     rq.lo = (float)(qv[0] - 1.5 * iqr); rq.hi = (float)(qv[1] + 1.5 * iqr);
     rq.shift = (float)(0.5 * (qv[0] + qv[1]));
     rq.degenerate = (qv[0] == qv[1]);
-    if (err) S.err[env] |= err;
+    if (err) flag_error(S, env, err);
 }
 
 // Extends the brackets with the ranks found by the scan and turns the moments into the three rewards.
 SDC_HDN void reward_finish(const State& S, int env, const ScanRequest& rq, const ScanResult& rs, const RewardInputs& st,
-                           float* rew3) {
+                           QView& Q, float* rew3) {
     int err = 0;
     const int n = rq.n;
     for (int j = 0; j < 2; ++j) {
-        float* lst = S.qlist + ((size_t)env * 2 + j) * kListCap;
-        int a = S.q_a[env * 2 + j], m = S.q_m[env * 2 + j];
-        if (rq.widen & (1 << j)) {                               // rank a-1
-            const int c = rs.cnt_below[j];
+        float* lst = Q.lst[j];
+        int a = Q.a[j], m = Q.m[j];
+        const int c = rs.cnt[j];
+        if (rq.dir[j] == SCAN_BELOW) {                           // rank a-1
             if (c > a) err |= SDC_F_BRACKET;
-            const float v = (a > c) ? lst[0] : rs.pred[j];       // a tie copy of lst[0] sits below the list
+            const float v = (a > c) ? lst[0] : rs.ext[j];        // a tie copy of lst[0] sits below the list
             if (m == kListCap) m -= 1;                           // drop the top (far side)
             for (int i = m; i > 0; --i) lst[i] = lst[i - 1];
             lst[0] = v; a -= 1; m += 1;
-        }
-        if (rq.widen & (4 << j)) {                               // rank a+m
-            const int c = rs.cnt_above[j];
+        } else if (rq.dir[j] == SCAN_ABOVE) {                    // rank a+m
             const int above = n - a - m;
             if (c > above) err |= SDC_F_BRACKET;
-            const float v = (above > c) ? lst[m - 1] : rs.succ[j];
+            const float v = (above > c) ? lst[m - 1] : rs.ext[j];
             if (m == kListCap) { for (int i = 0; i + 1 < m; ++i) lst[i] = lst[i + 1]; m -= 1; a += 1; }
             lst[m] = v; m += 1;
         }
-        S.q_a[env * 2 + j] = a; S.q_m[env * 2 + j] = m;
+        Q.a[j] = a; Q.m[j] = m;
     }
     double z = 0.0;
     if (n >= 2) {
@@ -622,7 +669,7 @@ SDC_HDN void reward_finish(const State& S, int env, const ScanRequest& rq, const
     double r_ls = foot + st.ls_penalty;
     r_ls = fmin(fmax(r_ls, -10.0), 10.0);                        // :82
     rew3[0] = (float)r_ls; rew3[1] = (float)foot; rew3[2] = (float)foot;
-    if (err) S.err[env] |= err;
+    if (err) flag_error(S, env, err);
 }
 
 // ---- counter-based RNG for on-device episode starts and weather noise ---------------------------
@@ -675,9 +722,12 @@ constexpr int kNoiseSeg = 140;                            // 4-aligned segment l
 // Buffers and knobs of one step launch (all device pointers; see sdc_step in include/sdc_b200.h).
 struct StepArgs {
     const int32_t* actions; float* obs; float* share; float* rew; uint8_t* done; float* info; float* term_obs;
-    int32_t* ticket; int32_t* ticket_next;             // dynamic unit counter of this / the next step
-    int32_t* reset_count; int32_t* reset_count_next;   // number of envs that finished their episode in this step
-    int32_t* reset_list; double* metrics;
+    int32_t* ctr;          // this step's counters: [0] unit tickets, [1] finished envs appended to reset_list,
+    int32_t* ctr_next;     //                       [2] units past phase A, [3] reset_list slots claimed by workers
+    int32_t* reset_list;   // [N + slack], -1 = empty slot
+    float* reset_scratch;  // per-CTA scratch of the in-kernel reset workers
+    double* metrics;
+    unsigned long long* phase_clocks;   // optional [8]: summed per-warp clock64 deltas of the k_step phases (diagnostics)
     int32_t unit_envs, unroll, prefetch, blocks_per_sm;
 };
 
@@ -701,11 +751,15 @@ SDC_HDN void reset_scalar_state(const State& S, int env, int t0, ObsSink& obs) {
     S.ls_bins[env * 4 + 0] = 0; S.ls_bins[env * 4 + 1] = 0; S.ls_bins[env * 4 + 2] = 0; S.ls_bins[env * 4 + 3] = 0;
     S.dc_run[env] = 0; S.dc_scale[env] = 1; S.dc_last[env] = 2;              // dc_gym.py:114-116
     S.bat_load[env] = 0.0;                                                    // battery_model.py:90-91
-    if (t0 + S.ep_len + 18 > SDC_YEAR_STEPS) S.err[env] |= SDC_F_TRACE_DOMAIN;
+    if (t0 + S.ep_len + 18 > SDC_YEAR_STEPS) flag_error(S, env, SDC_F_TRACE_DOMAIN);
     LsStats ls;
     ls.oldest = 0.0; ls.avg = 0.0; ls.norm_q = 0.0;
     for (int i = 0; i < 5; ++i) ls.hist[i] = 0.0;
-    build_obs(S, env, t0, ls, 0.0, obs);
+    const Tables T{S.loc, S.dc};
+    Norms nm;
+    nm.cmin = S.ci_min[env]; nm.crng = S.ci_max[env] - nm.cmin;
+    nm.tmin = S.t_min[env]; nm.trng = S.t_max[env] - nm.tmin; nm.t0 = t0;
+    build_obs(S, T, env, t0, ls, 0.0, nm, obs);
 }
 
 }  // namespace sdc

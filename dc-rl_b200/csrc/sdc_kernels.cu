@@ -70,6 +70,8 @@ static const char* event_elapsed_ms(Context&, void* a, void* b, double* ms) {
     float f = 0.f; CU(cudaEventElapsedTime(&f, (cudaEvent_t)a, (cudaEvent_t)b)); *ms = f; return nullptr;
 }
 static void event_destroy(Context&, void* ev) { cudaEventDestroy((cudaEvent_t)ev); }
+static size_t reset_scratch_floats(Context& c) { return (size_t)c.sm_count * 4 * sdc::kNoiseThreads * sdc::kNoiseSeg; }
+static const char* dev_fill_bytes(Context&, void* p, int v, size_t bytes) { CU(cudaMemset(p, v, bytes)); return nullptr; }
 static const char* sync(Context& c) { CU(cudaSetDevice(c.device)); CU(cudaDeviceSynchronize()); return nullptr; }
 
 // =================================================================================================
@@ -79,6 +81,10 @@ constexpr int kStepThreads = 256;
 constexpr int kWarpsPerBlock = kStepThreads / 32;
 constexpr int kObsRow = 3 * SDC_OBS_DIM;          // 78 floats per env
 constexpr int kObsRowPad = kObsRow + 1;           // odd stride: conflict-free one-lane-per-row writes
+constexpr int kListRow = kObsRowPad;              // both quartile lists of an env (64 floats) + a 15-word mailbox, odd stride
+// mailbox words of an env's scratch row: scan parameters written by its lane, results written by the scanning warp
+enum { MB_N = 64, MB_LO, MB_HI, MB_SHIFT, MB_DIRS, MB_THR0, MB_THR1, MB_S1, MB_S2, MB_CNT0, MB_CNT1, MB_EXT0, MB_EXT1 };
+constexpr int kTableBytes = 8192;                 // shared-memory copy of the location / dc parameter tables
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -110,6 +116,23 @@ __device__ __forceinline__ float warp_min(float v) {
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Issues, up front and all at once, the second-level (address-dependent) reads of one env-step so that their
+// DRAM latencies overlap instead of being paid one after another inside the scalar phase.
+__device__ __forceinline__ void prefetch_env(const sdc::State& S, const sdc::Tables& T, int env) {
+    const int t = S.t[env], t0 = S.t0[env], head = S.ls_head[env], hh = S.hist_head[env];
+    const sdc::LocTables& L = T.loc[S.loc_id[env]];
+    const double* wt = S.weather + (size_t)env * 2 * S.win_len + (t - t0);
+    prefetch_line(wt); prefetch_line(wt + 16); prefetch_line(wt + S.win_len);
+    const uint8_t* ring = S.ls_ring + (size_t)env * (S.ls_mask + 1);
+    prefetch_line(ring + ((t - 24) & S.ls_mask)); prefetch_line(ring + ((t - 48) & S.ls_mask));
+    prefetch_line(ring + ((t - 72) & S.ls_mask)); prefetch_line(ring + ((t - 96) & S.ls_mask));
+    prefetch_line(ring + (t & S.ls_mask)); prefetch_line(ring + (head & S.ls_mask));
+    prefetch_line(S.hist + (size_t)env * S.hist_cap + hh);
+    prefetch_line(L.ci + t - 16); prefetch_line(L.ci + t); prefetch_line(L.ci + t + 9);
+    prefetch_line(L.workload + t); prefetch_line(L.ns + t); prefetch_line(L.sh + t);
+}
 
 struct SmemObsSink {
     float* row;
@@ -121,214 +144,92 @@ struct GlobalInfoSink {
 };
 
 // ---- phase B: one warp streams one env's window -------------------------------------------------
-struct Acc {
-    float s1[4], s2[4];
-    int cb[2], ca[2];
-    float pred[2], succ[2];
-};
-
-template <bool WIDEN>
-__device__ __forceinline__ void acc_one(Acc& A, int k, float x, float lo, float hi, float shift, const float* below, const float* above) {
-    const float c = fminf(fmaxf(x, lo), hi);
-    const float d = c - shift;
-    A.s1[k] += d;
-    A.s2[k] = fmaf(d, d, A.s2[k]);
-    if (WIDEN) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const bool b = x < below[j];
-            A.cb[j] += b;
-            A.pred[j] = fmaxf(A.pred[j], b ? x : -SDC_INF_F);
-            const bool u = x > above[j];
-            A.ca[j] += u;
-            A.succ[j] = fminf(A.succ[j], u ? x : SDC_INF_F);
-        }
-    }
+template <int D>
+__device__ __forceinline__ void track(int& cnt, float& ext, float x, float thr) {
+    if (D == sdc::SCAN_BELOW) { const bool b = x < thr; cnt += b; ext = fmaxf(ext, b ? x : -SDC_INF_F); }
+    if (D == sdc::SCAN_ABOVE) { const bool b = x > thr; cnt += b; ext = fminf(ext, b ? x : SDC_INF_F); }
 }
 
-template <bool WIDEN, int UNROLL>
-__device__ __forceinline__ void scan_window(const float* __restrict__ h, int n, float lo, float hi, float shift, const float* below,
-                                            const float* above, int lane, sdc::ScanResult& rs) {
-    Acc A;
+template <int D0, int D1>
+struct Acc {
+    float s1[4], s2[4];
+    int cnt[2];
+    float ext[2];
+    float lo, hi, shift, thr0, thr1;
+    __device__ __forceinline__ void one(int k, float x) {
+        const float c = fminf(fmaxf(x, lo), hi);
+        const float d = c - shift;
+        s1[k] += d;
+        s2[k] = fmaf(d, d, s2[k]);
+        track<D0>(cnt[0], ext[0], x, thr0);
+        track<D1>(cnt[1], ext[1], x, thr1);
+    }
+    __device__ __forceinline__ void four(const float4& v) { one(0, v.x); one(1, v.y); one(2, v.z); one(3, v.w); }
+};
+
+template <int D0, int D1, int UNROLL>
+__device__ __forceinline__ void scan_window(const float* h, int n, float lo, float hi, float shift, float thr0, float thr1,
+                                            int lane, sdc::ScanResult& rs) {
+    Acc<D0, D1> A;
 #pragma unroll
     for (int k = 0; k < 4; ++k) { A.s1[k] = 0.f; A.s2[k] = 0.f; }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) { A.cb[j] = 0; A.ca[j] = 0; A.pred[j] = -SDC_INF_F; A.succ[j] = SDC_INF_F; }
+    A.cnt[0] = A.cnt[1] = 0;
+    A.ext[0] = D0 == sdc::SCAN_ABOVE ? SDC_INF_F : -SDC_INF_F;
+    A.ext[1] = D1 == sdc::SCAN_ABOVE ? SDC_INF_F : -SDC_INF_F;
+    A.lo = lo; A.hi = hi; A.shift = shift; A.thr0 = thr0; A.thr1 = thr1;
     const float4* p = reinterpret_cast<const float4*>(h);
     const int n4 = n >> 2;
+    // Full batches of UNROLL rows (UNROLL x 512 B per warp in flight).  Deeper per-warp queues (double buffering,
+    // UNROLL 16, bulk L2 prefetch) were measured SLOWER on B200: with ~2 400 independent 40 KB streams more
+    // outstanding requests only add DRAM row conflicts (profiles/r01_summary.md).
     int c = lane;
     for (; c + (UNROLL - 1) * 32 < n4; c += UNROLL * 32) {
         float4 v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) v[u] = __ldcs(p + c + u * 32);
+        for (int u = 0; u < UNROLL; ++u) v[u] = __ldcg(p + c + u * 32);
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            acc_one<WIDEN>(A, 0, v[u].x, lo, hi, shift, below, above);
-            acc_one<WIDEN>(A, 1, v[u].y, lo, hi, shift, below, above);
-            acc_one<WIDEN>(A, 2, v[u].z, lo, hi, shift, below, above);
-            acc_one<WIDEN>(A, 3, v[u].w, lo, hi, shift, below, above);
-        }
+        for (int u = 0; u < UNROLL; ++u) A.four(v[u]);
     }
-    for (; c < n4; c += 32) {
-        const float4 v = __ldcs(p + c);
-        acc_one<WIDEN>(A, 0, v.x, lo, hi, shift, below, above);
-        acc_one<WIDEN>(A, 1, v.y, lo, hi, shift, below, above);
-        acc_one<WIDEN>(A, 2, v.z, lo, hi, shift, below, above);
-        acc_one<WIDEN>(A, 3, v.w, lo, hi, shift, below, above);
+    for (; c + 3 * 32 < n4; c += 4 * 32) {           // tail: groups of four rows, then single rows
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcg(p + c + u * 32);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) A.four(v[u]);
     }
+    for (; c < n4; c += 32) A.four(__ldcg(p + c));
     const int rem = n & 3;
-    if (lane < rem) acc_one<WIDEN>(A, 0, __ldcs(h + (n4 << 2) + lane), lo, hi, shift, below, above);
+    if (lane < rem) A.one(0, __ldcg(h + (n4 << 2) + lane));
     rs.s1 = warp_sum((A.s1[0] + A.s1[1]) + (A.s1[2] + A.s1[3]));
     rs.s2 = warp_sum((A.s2[0] + A.s2[1]) + (A.s2[2] + A.s2[3]));
-    if (WIDEN) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            rs.cnt_below[j] = warp_sum(A.cb[j]); rs.cnt_above[j] = warp_sum(A.ca[j]);
-            rs.pred[j] = warp_max(A.pred[j]); rs.succ[j] = warp_min(A.succ[j]);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) { rs.cnt_below[j] = 0; rs.cnt_above[j] = 0; rs.pred[j] = -SDC_INF_F; rs.succ[j] = SDC_INF_F; }
-    }
+    rs.cnt[0] = D0 ? warp_sum(A.cnt[0]) : 0;
+    rs.cnt[1] = D1 ? warp_sum(A.cnt[1]) : 0;
+    rs.ext[0] = D0 == sdc::SCAN_BELOW ? warp_max(A.ext[0]) : (D0 == sdc::SCAN_ABOVE ? warp_min(A.ext[0]) : 0.f);
+    rs.ext[1] = D1 == sdc::SCAN_BELOW ? warp_max(A.ext[1]) : (D1 == sdc::SCAN_ABOVE ? warp_min(A.ext[1]) : 0.f);
 }
 
-// =================================================================================================
-// k_step
-// =================================================================================================
 template <int UNROLL>
-__global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, const StepArgs a) {
-    extern __shared__ float smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int U = a.unit_envs;
-    float* tile = smem + (size_t)warp * U * kObsRowPad;          // this warp's [U][79] observation tile
-    const int N = S.n_envs;
-    const int n_units = (N + U - 1) / U;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *a.ticket_next = 0; *a.reset_count_next = 0; }
-
-    for (;;) {
-        int unit = 0;
-        if (lane == 0) unit = atomicAdd(a.ticket, 1);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit >= n_units) break;
-        const int env0 = unit * U;
-        const int env = env0 + lane;
-        const bool active = lane < U && env < N;
-        const int n_here = min(U, N - env0);
-
-        // ---------------- phase A: one lane per env ----------------
-        sdc::RewardInputs en;                                       // what phase C needs from phase A
-        sdc::ScanRequest rq;
-        rq.n = 0; rq.widen = 0; rq.lo = rq.hi = rq.shift = 0.f; rq.degenerate = 0; rq.q1 = rq.q3 = 0.0;
-        rq.below[0] = rq.below[1] = -SDC_INF_F; rq.above[0] = rq.above[1] = SDC_INF_F;
-        en.energy = 0.0; en.nci_next = 0.0; en.ls_penalty = 0.0;
-        {
-            double m[13];
-#pragma unroll
-            for (int k = 0; k < 13; ++k) m[k] = 0.0;
-            if (active) {
-                if (a.prefetch) {
-                    // start pulling this env's window towards L2 while the scalar physics runs
-                    const int len = S.hist_len[env];
-                    if (len >= 4 && lane < 2) l2_prefetch_bulk(S.hist + (size_t)env * S.hist_cap, (unsigned)((len * 4) & ~15));
-                }
-                const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
-                SmemObsSink obs{tile + lane * kObsRowPad};
-                GlobalInfoSink info{a.info, N, env};
-                sdc::StepResult st;
-                sdc::physics_step(S, env, a_ls, a_dc, a_bat, obs, info, st);
-                sdc::reward_prepare(S, env, st.energy, rq);
-                en.energy = st.energy; en.nci_next = st.nci_next; en.ls_penalty = st.ls_penalty;
-                a.done[env] = (uint8_t)st.terminal;
-                if (st.terminal) {
-                    a.reset_list[atomicAdd(a.reset_count, 1)] = env;
-                    if (a.term_obs) {
-                        float* dst = a.term_obs + (size_t)env * kObsRow;
-                        for (int k = 0; k < kObsRow; ++k) dst[k] = obs.row[k];
-                    }
-                }
-                m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
-                m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
-                m[11] = st.overdue; m[12] = st.total_kw;
-            }
-            // logger sums (harl/envs/sustaindc/sustaindc_logger.py:86-101): warp reduce, one atomic per metric
-            constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
-                                      sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
-                                      sdc::M_OVERDUE, sdc::M_TOTAL_KW};
-#pragma unroll
-            for (int k = 0; k < 13; ++k) {
-                const double v = warp_sum(m[k]);
-                if (lane == 0) atomicAdd(a.metrics + slot[k], v);
-            }
-        }
-        __syncwarp();
-        // observation tile -> global, coalesced (rows of a unit are contiguous in obs[N,3,26])
-        {
-            float2* dst = reinterpret_cast<float2*>(a.obs + (size_t)env0 * kObsRow);
-            const int total2 = n_here * (kObsRow / 2);
-            for (int i = lane; i < total2; i += 32) {
-                const int e = i / (kObsRow / 2), k = (i - e * (kObsRow / 2)) * 2;
-                dst[i] = make_float2(tile[e * kObsRowPad + k], tile[e * kObsRowPad + k + 1]);
-            }
-            float* sh = a.share + (size_t)env0 * SDC_SHARE_DIM;
-            const int total = n_here * SDC_SHARE_DIM;
-            for (int i = lane; i < total; i += 32) {
-                const int e = i / SDC_SHARE_DIM, k = i - e * SDC_SHARE_DIM;
-                // ls[0:26] | dc[11] | dc[13] | padded battery row [25]   (harlsustaindc_env.py:78-85)
-                const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
-                sh[i] = tile[e * kObsRowPad + src];
-            }
-        }
-        __syncwarp();
-
-        // ---------------- phase B: the warp streams each env's reward window ----------------
-        sdc::ScanResult mine;
-        mine.s1 = mine.s2 = 0.f;
-        mine.cnt_below[0] = mine.cnt_below[1] = mine.cnt_above[0] = mine.cnt_above[1] = 0;
-        mine.pred[0] = mine.pred[1] = -SDC_INF_F; mine.succ[0] = mine.succ[1] = SDC_INF_F;
-        for (int l = 0; l < n_here; ++l) {
-            const int n = __shfl_sync(0xffffffffu, rq.n, l);
-            if (a.prefetch && l + 2 < n_here) {
-                const int n2 = __shfl_sync(0xffffffffu, rq.n, l + 2);
-                if (lane == 0 && n2 >= 4) l2_prefetch_bulk(S.hist + (size_t)(env0 + l + 2) * S.hist_cap, (unsigned)((n2 * 4) & ~15));
-            }
-            if (n < 2) continue;                                   // z = 0 (utils/reward_creator.py:26-27)
-            const float lo = __shfl_sync(0xffffffffu, rq.lo, l), hi = __shfl_sync(0xffffffffu, rq.hi, l);
-            const float shift = __shfl_sync(0xffffffffu, rq.shift, l);
-            const int widen = __shfl_sync(0xffffffffu, rq.widen, l);
-            const float* h = S.hist + (size_t)(env0 + l) * S.hist_cap;
-            sdc::ScanResult rs;
-            if (widen) {
-                float below[2], above[2];
-                below[0] = __shfl_sync(0xffffffffu, rq.below[0], l); below[1] = __shfl_sync(0xffffffffu, rq.below[1], l);
-                above[0] = __shfl_sync(0xffffffffu, rq.above[0], l); above[1] = __shfl_sync(0xffffffffu, rq.above[1], l);
-                scan_window<true, 4>(h, n, lo, hi, shift, below, above, lane, rs);
-            } else {
-                scan_window<false, UNROLL>(h, n, lo, hi, shift, nullptr, nullptr, lane, rs);
-            }
-            if (lane == l) mine = rs;
-        }
-
-        // ---------------- phase C: one lane per env ----------------
-        double m_sum = 0.0, m_ls = 0.0, m_dc = 0.0;
-        if (active) {
-            float r3[3];
-            sdc::reward_finish(S, env, rq, mine, en, r3);
-            a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
-            m_sum = (double)r3[0] + r3[1] + r3[2]; m_ls = r3[0]; m_dc = r3[1];
-        }
-        m_sum = warp_sum(m_sum); m_ls = warp_sum(m_ls); m_dc = warp_sum(m_dc);
-        if (lane == 0) {
-            atomicAdd(a.metrics + sdc::M_REWARD_SUM, m_sum); atomicAdd(a.metrics + sdc::M_REWARD_LS, m_ls);
-            atomicAdd(a.metrics + sdc::M_REWARD_DC, m_dc);
-        }
-        __syncwarp();
+// Own register allocation for the hot loop (not inlined into the large step kernel, whose scalar phases would
+// otherwise push spills into it -- measured: +45 % scan time).
+__device__ __noinline__ void scan_dispatch(const float* h, int n, float lo, float hi, float shift, int d0, int d1, float t0, float t1,
+                                           int lane, sdc::ScanResult& rs) {
+    switch (d0 * 3 + d1) {
+        case 0: scan_window<0, 0, UNROLL>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
+        case 1: scan_window<0, 1, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
+        case 2: scan_window<0, 2, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
+        case 3: scan_window<1, 0, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
+        case 4: scan_window<1, 1, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
+        case 5: scan_window<1, 2, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
+        case 6: scan_window<2, 0, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
+        case 7: scan_window<2, 1, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
+        default: scan_window<2, 2, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
     }
 }
 
 // =================================================================================================
-// k_reset
+// episode reset of one env by one CTA (used by k_reset and by the reset workers inside k_step)
 // =================================================================================================
-constexpr int kResetThreads = sdc::kNoiseThreads;   // 256
+constexpr int kResetThreads = sdc::kNoiseThreads;   // 256 == kStepThreads
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
     v = warp_sum(v);
@@ -362,99 +263,383 @@ struct RowSink {
     __device__ __forceinline__ void operator()(int agent, int idx, float v) { row[agent * SDC_OBS_DIM + idx] = v; }
 };
 
+struct ResetShared {
+    double red[kResetThreads / 32];
+    double seg_off[kResetThreads];
+    int start[3];
+    float row[kObsRow];
+};
+
+// `inc` = scratch for the 256*140 random-walk increments of one env (shared memory in k_reset, an L2-resident global
+// buffer for the in-kernel workers).  Must be called by all kResetThreads threads of the CTA.
+__device__ __noinline__ void reset_one_env(const sdc::State& S, int env, float* obs, float* share, float* inc, ResetShared& sh) {
+    const int tid = threadIdx.x;
+    const int n = SDC_YEAR_STEPS;
+    double* wt = S.weather + (size_t)env * 2 * S.win_len;
+    double* ww = wt + S.win_len;
+    const bool staged = S.pend_valid && S.pend_valid[env];
+    __syncthreads();
+    if (staged) {
+        if (tid == 0) { sh.start[0] = S.pend_day[env]; sh.start[1] = S.pend_hour[env]; sh.start[2] = 0; }
+        const double* src = S.pend_weather + (size_t)env * 2 * S.win_len;
+        for (int k = tid; k < 2 * S.win_len; k += kResetThreads) wt[k] = src[k];
+        if (tid == 0) { S.t_min[env] = S.pend_tmin[env]; S.t_max[env] = S.pend_tmax[env]; }
+    } else {
+        const uint32_t ep = S.episode[env];
+        const uint64_t seed = S.seed[env];
+        if (tid == 0) sdc::draw_episode_start(seed, ep, S.day_lo[env], S.day_hi[env], &sh.start[0], &sh.start[1], &sh.start[2]);
+        // pass 1: increments of this thread's segment (utils/managers.py:45-46)
+        double seg = 0.0;
+        for (int q = 0; q < sdc::kNoiseSeg / 4; ++q) {
+            float z[4];
+            const int j0 = tid * sdc::kNoiseSeg + q * 4;
+            sdc::noise_normals4(seed, ep, (uint32_t)(j0 >> 2), z);
+            const float4 v4 = make_float4(0.02f * z[0], 0.02f * z[1], 0.02f * z[2], 0.02f * z[3]);
+            *reinterpret_cast<float4*>(inc + j0) = v4;
+            if (j0 + 0 < n) seg += (double)v4.x;
+            if (j0 + 1 < n) seg += (double)v4.y;
+            if (j0 + 2 < n) seg += (double)v4.z;
+            if (j0 + 3 < n) seg += (double)v4.w;
+        }
+        sh.seg_off[tid] = seg;
+        __syncthreads();
+        if (tid == 0) {                           // serial exclusive prefix, same order as the host statement
+            double acc = 0.0;
+            for (int k = 0; k < kResetThreads; ++k) { const double s = sh.seg_off[k]; sh.seg_off[k] = acc; acc += s; }
+        }
+        __syncthreads();
+        const double off = sh.seg_off[tid];
+        const int j_lo = tid * sdc::kNoiseSeg, j_hi = min(j_lo + sdc::kNoiseSeg, n);
+        // pass 2 / 3: mean and population std of the walk
+        double run = 0.0, sum = 0.0;
+        for (int j = j_lo; j < j_hi; ++j) { run += (double)inc[j]; sum += off + run; }
+        const double mean = block_sum(sum, sh.red) / n;
+        run = 0.0; double ss = 0.0;
+        for (int j = j_lo; j < j_hi; ++j) { run += (double)inc[j]; const double d = (off + run) - mean; ss += d * d; }
+        const double scale = 0.75 / sqrt(block_sum(ss, sh.red) / n);          // managers.py:46-48
+        // pass 4: roll, clip, window, 30-day min/max (managers.py:598-608)
+        const int t0 = sh.start[0] * 96 + sh.start[1] * 4, roll = sh.start[2];
+        for (int k = tid; k < 2 * S.win_len; k += kResetThreads) wt[k] = 0.0;
+        __syncthreads();
+        const sdc::LocTables& L = S.loc[S.loc_id[env]];
+        double tmin = INFINITY, tmax = -INFINITY;
+        run = 0.0;
+        for (int j = j_lo; j < j_hi; ++j) {
+            run += (double)inc[j];
+            int t = j + 96 * roll; if (t >= n) t -= n;
+            if (t < t0) continue;
+            const double noise = (off + run) * scale;
+            const double vt = fmin(fmax(L.temp_base[j] + noise, 0.0), 45.0);
+            if (t < t0 + 2880) { tmin = fmin(tmin, vt); tmax = fmax(tmax, vt); }
+            if (t < t0 + S.win_len) {
+                wt[t - t0] = vt;
+                ww[t - t0] = fmin(fmax(L.wetb_base[j] + noise, 0.0), 45.0);
+            }
+        }
+        tmin = block_minmax(tmin, true, sh.red);
+        tmax = block_minmax(tmax, false, sh.red);
+        if (tid == 0) { S.t_min[env] = tmin; S.t_max[env] = tmax; }
+    }
+    uint8_t* ring = S.ls_ring + (size_t)env * (S.ls_mask + 1);
+    for (int k = tid; k <= S.ls_mask; k += kResetThreads) ring[k] = 0;
+    __syncthreads();                               // weather window + norms visible to thread 0
+    if (tid == 0) {
+        if (staged) S.pend_valid[env] = 0;
+        S.episode[env] += 1;
+        RowSink sink{sh.row};
+        sdc::reset_scalar_state(S, env, sh.start[0] * 96 + sh.start[1] * 4, sink);
+    }
+    __syncthreads();
+    for (int k = tid; k < kObsRow; k += kResetThreads) obs[(size_t)env * kObsRow + k] = sh.row[k];
+    if (tid < SDC_SHARE_DIM) {
+        const int k = tid;
+        const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
+        share[(size_t)env * SDC_SHARE_DIM + k] = sh.row[src];
+    }
+}
+
+// =================================================================================================
+// k_reset: explicit resets (sdc_reset), one CTA per listed env
+// =================================================================================================
 __global__ void __launch_bounds__(kResetThreads) k_reset(const sdc::State S, const int32_t* __restrict__ list,
                                                          const int32_t* __restrict__ count, float* obs, float* share) {
     extern __shared__ float inc[];                  // [256*140] random-walk increments of one env
-    __shared__ double red[kResetThreads / 32];
-    __shared__ double seg_off[kResetThreads];
-    __shared__ int s_start[3];
-    __shared__ float s_row[kObsRow];
-    const int tid = threadIdx.x;
-    const int n = SDC_YEAR_STEPS;
+    __shared__ ResetShared sh;
     const int total = *count;
-    for (int i = blockIdx.x; i < total; i += gridDim.x) {
-        const int env = list[i];
-        double* wt = S.weather + (size_t)env * 2 * S.win_len;
-        double* ww = wt + S.win_len;
-        const bool staged = S.pend_valid && S.pend_valid[env];
+    for (int i = blockIdx.x; i < total; i += gridDim.x) reset_one_env(S, list[i], obs, share, inc, sh);
+}
+
+// =================================================================================================
+// k_step
+// =================================================================================================
+template <int UNROLL>
+__global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, const StepArgs a, const int n_unit_ctas) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int U = a.unit_envs;
+    // location / dc-parameter tables -> shared memory (removes one level of pointer chasing per env)
+    sdc::Tables T{S.loc, S.dc};
+    {
+        const int loc_bytes = S.n_loc * (int)sizeof(sdc::LocTables), dc_bytes = S.n_cfg * (int)sizeof(sdc_dc_params);
+        if (loc_bytes + dc_bytes <= kTableBytes) {
+            int* dst = reinterpret_cast<int*>(smem_raw);
+            const int* src_loc = reinterpret_cast<const int*>(S.loc);
+            const int* src_dc = reinterpret_cast<const int*>(S.dc);
+            for (int i = threadIdx.x; i < loc_bytes / 4; i += kStepThreads) dst[i] = src_loc[i];
+            for (int i = threadIdx.x; i < dc_bytes / 4; i += kStepThreads) dst[loc_bytes / 4 + i] = src_dc[i];
+            T.loc = reinterpret_cast<const sdc::LocTables*>(smem_raw);
+            T.dc = reinterpret_cast<const sdc_dc_params*>(smem_raw + loc_bytes);
+        }
         __syncthreads();
-        if (staged) {
-            if (tid == 0) { s_start[0] = S.pend_day[env]; s_start[1] = S.pend_hour[env]; s_start[2] = 0; }
-            const double* src = S.pend_weather + (size_t)env * 2 * S.win_len;
-            for (int k = tid; k < 2 * S.win_len; k += kResetThreads) wt[k] = src[k];
-            if (tid == 0) { S.t_min[env] = S.pend_tmin[env]; S.t_max[env] = S.pend_tmax[env]; }
-        } else {
-            const uint32_t ep = S.episode[env];
-            const uint64_t seed = S.seed[env];
-            if (tid == 0) sdc::draw_episode_start(seed, ep, S.day_lo[env], S.day_hi[env], &s_start[0], &s_start[1], &s_start[2]);
-            // pass 1: increments of this thread's segment (utils/managers.py:45-46)
-            double seg = 0.0;
-            for (int q = 0; q < sdc::kNoiseSeg / 4; ++q) {
-                float z[4];
-                const int j0 = tid * sdc::kNoiseSeg + q * 4;
-                sdc::noise_normals4(seed, ep, (uint32_t)(j0 >> 2), z);
+    }
+    float* tile = reinterpret_cast<float*>(smem_raw + kTableBytes) + (size_t)warp * U * kObsRowPad;   // this warp's scratch
+    const int N = S.n_envs;
+    const int n_units = (N + U - 1) / U;
+    if (blockIdx.x == 0 && threadIdx.x < 4) a.ctr_next[threadIdx.x] = 0;
+
+    for (; blockIdx.x < n_unit_ctas;) {
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(a.ctr + 0, 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        const int env0 = unit * U;
+        const int env = env0 + lane;
+        const bool active = lane < U && env < N;
+        const int n_here = min(U, N - env0);
+
+        const long long tk0 = clock64();
+        // ---------------- phase A: one lane per env ----------------
+        sdc::RewardInputs en;                                       // what phase C needs from phase A
+        en.energy = 0.0; en.nci_next = 0.0; en.ls_penalty = 0.0;
+        int finished = 0, h_len = 0, h_head = 0;
+        float h_evicted = 0.f;
+        {
+            double m[13];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float v = 0.02f * z[k];
-                    inc[j0 + k] = v;
-                    if (j0 + k < n) seg += (double)v;
+            for (int k = 0; k < 13; ++k) m[k] = 0.0;
+            if (active) {
+                prefetch_env(S, T, env);
+                // the unit's bracket lists (one contiguous block) are needed right after the physics
+                prefetch_line(S.qlist + (size_t)env * 2 * sdc::kListCap); prefetch_line(S.qlist + (size_t)env * 2 * sdc::kListCap + 32);
+                if (a.prefetch & 1) {
+                    const int len = S.hist_len[env];
+                    if (len >= 4 && lane < 2) l2_prefetch_bulk(S.hist + (size_t)env * S.hist_cap, (unsigned)((len * 4) & ~15));
                 }
-            }
-            seg_off[tid] = seg;
-            __syncthreads();
-            if (tid == 0) {                           // serial exclusive prefix, same order as the host statement
-                double acc = 0.0;
-                for (int k = 0; k < kResetThreads; ++k) { const double s = seg_off[k]; seg_off[k] = acc; acc += s; }
-            }
-            __syncthreads();
-            const double off = seg_off[tid];
-            const int j_lo = tid * sdc::kNoiseSeg, j_hi = min(j_lo + sdc::kNoiseSeg, n);
-            // pass 2 / 3: mean and population std of the walk
-            double run = 0.0, sum = 0.0;
-            for (int j = j_lo; j < j_hi; ++j) { run += (double)inc[j]; sum += off + run; }
-            const double mean = block_sum(sum, red) / n;
-            run = 0.0; double ss = 0.0;
-            for (int j = j_lo; j < j_hi; ++j) { run += (double)inc[j]; const double d = (off + run) - mean; ss += d * d; }
-            const double scale = 0.75 / sqrt(block_sum(ss, red) / n);          // managers.py:46-48
-            // pass 4: roll, clip, window, 30-day min/max (managers.py:598-608)
-            const int t0 = s_start[0] * 96 + s_start[1] * 4, roll = s_start[2];
-            for (int k = tid; k < 2 * S.win_len; k += kResetThreads) wt[k] = 0.0;
-            __syncthreads();
-            const sdc::LocTables& L = S.loc[S.loc_id[env]];
-            double tmin = INFINITY, tmax = -INFINITY;
-            run = 0.0;
-            for (int j = j_lo; j < j_hi; ++j) {
-                run += (double)inc[j];
-                int t = j + 96 * roll; if (t >= n) t -= n;
-                if (t < t0) continue;
-                const double noise = (off + run) * scale;
-                const double vt = fmin(fmax(L.temp_base[j] + noise, 0.0), 45.0);
-                if (t < t0 + 2880) { tmin = fmin(tmin, vt); tmax = fmax(tmax, vt); }
-                if (t < t0 + S.win_len) {
-                    wt[t - t0] = vt;
-                    ww[t - t0] = fmin(fmax(L.wetb_base[j] + noise, 0.0), 45.0);
+                const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
+                SmemObsSink obs{tile + lane * kObsRowPad};
+                GlobalInfoSink info{a.info, N, env};
+                sdc::StepResult st;
+                sdc::physics_step(S, T, env, a_ls, a_dc, a_bat, obs, info, st);
+                en.energy = st.energy; en.nci_next = st.nci_next; en.ls_penalty = st.ls_penalty;
+                h_len = st.hist_len; h_head = st.hist_head; h_evicted = st.evicted;
+                a.done[env] = (uint8_t)st.terminal;
+                finished = st.terminal;
+                if (st.terminal) {
+                    if (a.term_obs) {
+                        float* dst = a.term_obs + (size_t)env * kObsRow;
+                        for (int k = 0; k < kObsRow; ++k) dst[k] = obs.row[k];
+                    }
                 }
+                m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
+                m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
+                m[11] = st.overdue; m[12] = st.total_kw;
             }
-            tmin = block_minmax(tmin, true, red);
-            tmax = block_minmax(tmax, false, red);
-            if (tid == 0) { S.t_min[env] = tmin; S.t_max[env] = tmax; }
+            // logger sums (harl/envs/sustaindc/sustaindc_logger.py:86-101): warp reduce, one atomic per metric
+            constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
+                                      sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
+                                      sdc::M_OVERDUE, sdc::M_TOTAL_KW};
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {
+                const double v = warp_sum(m[k]);
+                if (lane == 0) atomicAdd(a.metrics + slot[k], v);
+            }
         }
-        uint8_t* ring = S.ls_ring + (size_t)env * (S.ls_mask + 1);
-        for (int k = tid; k <= S.ls_mask; k += kResetThreads) ring[k] = 0;
-        __syncthreads();                               // weather window + norms visible to thread 0
-        if (tid == 0) {
-            if (staged) S.pend_valid[env] = 0;
-            S.episode[env] += 1;
-            RowSink sink{s_row};
-            sdc::reset_scalar_state(S, env, s_start[0] * 96 + s_start[1] * 4, sink);
+        __syncwarp();
+        const long long tk1 = clock64();
+        // observation tile -> global, coalesced (rows of a unit are contiguous in obs[N,3,26])
+        {
+            float2* dst = reinterpret_cast<float2*>(a.obs + (size_t)env0 * kObsRow);
+            const int total2 = n_here * (kObsRow / 2);
+            for (int i = lane; i < total2; i += 32) {
+                const int e = i / (kObsRow / 2), k = (i - e * (kObsRow / 2)) * 2;
+                dst[i] = make_float2(tile[e * kObsRowPad + k], tile[e * kObsRowPad + k + 1]);
+            }
+            float* sh = a.share + (size_t)env0 * SDC_SHARE_DIM;
+            const int total = n_here * SDC_SHARE_DIM;
+            for (int i = lane; i < total; i += 32) {
+                const int e = i / SDC_SHARE_DIM, k = i - e * SDC_SHARE_DIM;
+                // ls[0:26] | dc[11] | dc[13] | padded battery row [25]   (harlsustaindc_env.py:78-85)
+                const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
+                sh[i] = tile[e * kObsRowPad + src];
+            }
+        }
+        __syncwarp();
+        const long long tkA = clock64();
+        // Finished envs go to the reset workers (other CTAs of this launch).  Order matters: the terminal observation is
+        // in global memory before the env is published, because the worker overwrites obs/share with the reset ones.
+        // (The fences are only paid by the ~5 % of units that contain a finished env: a gpu-scope fence waits for all of
+        // the warp's outstanding stores and costs tens of microseconds while the other warps saturate HBM.)
+        if (__any_sync(0xffffffffu, finished)) {
+            __threadfence();
+            if (finished) a.reset_list[atomicAdd(a.ctr + 1, 1)] = env;
+            __threadfence();
+            __syncwarp();
+        }
+        if (lane == 0) atomicAdd(a.ctr + 2, 1);
+        const long long tkB = clock64();
+        // the unit's quartile brackets -> the same scratch (coalesced), updated in place, written back after phase C
+        int2 qa = make_int2(0, 0), qm = make_int2(0, 0);
+        if (active) { qa = reinterpret_cast<const int2*>(S.q_a)[env]; qm = reinterpret_cast<const int2*>(S.q_m)[env]; }
+        {
+            const float4* src = reinterpret_cast<const float4*>(S.qlist + (size_t)env0 * 2 * sdc::kListCap);
+            const int total4 = n_here * (2 * sdc::kListCap / 4);
+#ifdef SDC_BATCHED_LIST_STAGING   // measured slower overall on B200 (scan phase +50 %), kept for reference
+            float4 v[16];                                  // all 16 loads in flight before the first store
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const int i = lane + 32 * j; if (i < total4) v[j] = __ldcg(src + i); }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int i = lane + 32 * j;
+                if (i < total4) {
+                    const int e = i >> 4, k = (i & 15) * 4;
+                    float* d = tile + e * kListRow + k;
+                    d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
+                }
+            }
+#else
+            for (int i = lane; i < total4; i += 32) {
+                const float4 v = src[i];
+                const int e = i >> 4, k = (i & 15) * 4;
+                float* d = tile + e * kListRow + k;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+#endif
+        }
+        __syncwarp();
+        const long long tkC = clock64();
+        // Per-env scan parameters and results live in the env's shared-memory row, not in registers: anything that
+        // spills to local memory inside the per-env loop costs a ~2 us DRAM round trip while HBM is saturated.
+        sdc::QView Q;
+        Q.lst[0] = tile + lane * kListRow; Q.lst[1] = Q.lst[0] + sdc::kListCap;
+        Q.a[0] = Q.a[1] = Q.m[0] = Q.m[1] = 0;
+        int rq_degenerate = 0;
+        double rq_q1 = 0.0;
+        if (lane < U) {                                            // rows exist for the unit's U lanes only
+            float* mb = tile + lane * kListRow;
+            int* mbi = reinterpret_cast<int*>(mb);
+            mbi[MB_N] = 0;
+            if (active) {
+                sdc::ScanRequest rq;
+                Q.a[0] = qa.x; Q.a[1] = qa.y; Q.m[0] = qm.x; Q.m[1] = qm.y;
+                sdc::reward_prepare(S, env, en.energy, h_len, h_head, h_evicted, Q, rq);
+                mbi[MB_N] = rq.n; mb[MB_LO] = rq.lo; mb[MB_HI] = rq.hi; mb[MB_SHIFT] = rq.shift;
+                mbi[MB_DIRS] = rq.dir[0] | (rq.dir[1] << 2); mb[MB_THR0] = rq.thr[0]; mb[MB_THR1] = rq.thr[1];
+                rq_degenerate = rq.degenerate; rq_q1 = rq.q1;
+            }
+            mb[MB_S1] = 0.f; mb[MB_S2] = 0.f; mbi[MB_CNT0] = 0; mbi[MB_CNT1] = 0; mb[MB_EXT0] = 0.f; mb[MB_EXT1] = 0.f;
+        }
+        __syncwarp();
+
+        const long long tk2 = clock64();
+        // ---------------- phase B: the warp streams each env's reward window ----------------
+        for (int l = 0; l < n_here; ++l) {
+            float* mb = tile + l * kListRow;
+            int* mbi = reinterpret_cast<int*>(mb);
+            const int n = mbi[MB_N];
+            if ((a.prefetch & 2) && l + 1 < n_here) {              // warm L2 with the head of the next env's window
+                const float* nxt = S.hist + (size_t)(env0 + l + 1) * S.hist_cap + lane * 32;
+                prefetch_line(nxt); prefetch_line(nxt + 1024);
+            }
+            if (n < 2) continue;                                   // z = 0 (utils/reward_creator.py:26-27)
+            const int dirs = mbi[MB_DIRS];
+            sdc::ScanResult rs;
+            scan_dispatch<UNROLL>(S.hist + (size_t)(env0 + l) * S.hist_cap, n, mb[MB_LO], mb[MB_HI], mb[MB_SHIFT], dirs & 3, dirs >> 2,
+                                  mb[MB_THR0], mb[MB_THR1], lane, rs);
+            if (lane == 0) {
+                mb[MB_S1] = rs.s1; mb[MB_S2] = rs.s2; mbi[MB_CNT0] = rs.cnt[0]; mbi[MB_CNT1] = rs.cnt[1];
+                mb[MB_EXT0] = rs.ext[0]; mb[MB_EXT1] = rs.ext[1];
+            }
+        }
+        __syncwarp();
+
+        const long long tk3 = clock64();
+        // ---------------- phase C: one lane per env ----------------
+        double m_sum = 0.0, m_ls = 0.0, m_dc = 0.0;
+        if (active) {
+            const float* mb = tile + lane * kListRow;
+            const int* mbi = reinterpret_cast<const int*>(mb);
+            sdc::ScanRequest rq;
+            rq.n = mbi[MB_N]; rq.lo = mb[MB_LO]; rq.hi = mb[MB_HI]; rq.shift = mb[MB_SHIFT];
+            rq.dir[0] = mbi[MB_DIRS] & 3; rq.dir[1] = mbi[MB_DIRS] >> 2; rq.thr[0] = mb[MB_THR0]; rq.thr[1] = mb[MB_THR1];
+            rq.degenerate = rq_degenerate; rq.q1 = rq_q1;
+            sdc::ScanResult mine;
+            mine.s1 = mb[MB_S1]; mine.s2 = mb[MB_S2]; mine.cnt[0] = mbi[MB_CNT0]; mine.cnt[1] = mbi[MB_CNT1];
+            mine.ext[0] = mb[MB_EXT0]; mine.ext[1] = mb[MB_EXT1];
+            float r3[3];
+            sdc::reward_finish(S, env, rq, mine, en, Q, r3);
+            reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
+            reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
+            a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
+            m_sum = (double)r3[0] + r3[1] + r3[2]; m_ls = r3[0]; m_dc = r3[1];
+        }
+        m_sum = warp_sum(m_sum); m_ls = warp_sum(m_ls); m_dc = warp_sum(m_dc);
+        if (lane == 0) {
+            atomicAdd(a.metrics + sdc::M_REWARD_SUM, m_sum); atomicAdd(a.metrics + sdc::M_REWARD_LS, m_ls);
+            atomicAdd(a.metrics + sdc::M_REWARD_DC, m_dc);
+        }
+        __syncwarp();
+        {
+            float4* dst = reinterpret_cast<float4*>(S.qlist + (size_t)env0 * 2 * sdc::kListCap);
+            const int total4 = n_here * (2 * sdc::kListCap / 4);
+            for (int i = lane; i < total4; i += 32) {
+                const int e = i >> 4, k = (i & 15) * 4;
+                const float* d = tile + e * kListRow + k;
+                dst[i] = make_float4(d[0], d[1], d[2], d[3]);
+            }
+        }
+        __syncwarp();
+        if (a.phase_clocks && lane == 0) {
+            const long long tk4 = clock64();
+            atomicAdd(a.phase_clocks + 0, (unsigned long long)(tk1 - tk0));   // physics + info + metrics
+            atomicAdd(a.phase_clocks + 1, (unsigned long long)(tk2 - tk1));   // obs flush, list staging, bracket update
+            atomicAdd(a.phase_clocks + 2, (unsigned long long)(tk3 - tk2));   // window scans
+            atomicAdd(a.phase_clocks + 3, (unsigned long long)(tk4 - tk3));   // rewards, list write-back
+            atomicAdd(a.phase_clocks + 4, 1ull);                              // units
+            atomicAdd(a.phase_clocks + 5, (unsigned long long)(tkA - tk1));   // stage: obs/share tile flush
+            atomicAdd(a.phase_clocks + 6, (unsigned long long)(tkC - tkB));   // stage: bracket lists -> smem
+            atomicAdd(a.phase_clocks + 7, (unsigned long long)(tk2 - tkC));   // stage: window append + bracket update
+        }
+    }
+
+    // ---------------- episode resets: every CTA turns into a reset worker once it has no unit left ----------------
+    // CTAs beyond n_unit_ctas start here immediately, so resets of envs that finished in this step overlap with the
+    // window scans of the other CTAs.  A worker claims the next slot of reset_list and waits until it is filled or
+    // until every unit is past phase A (then no further env can be appended).
+    __shared__ ResetShared rsh;
+    __shared__ int s_env;
+    __syncthreads();
+    float* inc = a.reset_scratch + (size_t)blockIdx.x * (sdc::kNoiseThreads * sdc::kNoiseSeg);
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const int my = atomicAdd(a.ctr + 3, 1);
+            volatile int32_t* list = a.reset_list;
+            volatile int32_t* units_done = a.ctr + 2;
+            int env = -1;
+            for (;;) {
+                env = list[my];
+                if (env >= 0) break;
+                if (*units_done >= n_units) { __threadfence(); env = list[my]; break; }
+                __nanosleep(200);
+            }
+            if (env >= 0) list[my] = -1;
+            s_env = env;
         }
         __syncthreads();
-        for (int k = tid; k < kObsRow; k += kResetThreads) obs[(size_t)env * kObsRow + k] = s_row[k];
-        if (tid < SDC_SHARE_DIM) {
-            const int k = tid;
-            const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
-            share[(size_t)env * SDC_SHARE_DIM + k] = s_row[src];
-        }
+        const int env = s_env;
+        if (env < 0) break;
+        __threadfence();
+        reset_one_env(S, env, a.obs, a.share, inc, rsh);
+        __syncthreads();
     }
 }
 
@@ -512,18 +697,27 @@ __global__ void __launch_bounds__(kSortThreads) k_rebuild(const sdc::State S) {
 // =================================================================================================
 static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& a, void* stream) {
     const int U = a.unit_envs;
-    const size_t smem = (size_t)kWarpsPerBlock * U * kObsRowPad * sizeof(float);
+    const size_t smem = kTableBytes + (size_t)kWarpsPerBlock * U * kObsRowPad * sizeof(float);
     const int n_units = (S.n_envs + U - 1) / U;
     const int bps = a.blocks_per_sm > 0 ? a.blocks_per_sm : c.step_blocks_per_sm;
-    int blocks = c.sm_count * bps;
+    // All CTAs must be co-resident (reset workers wait for unit CTAs): never more than the resident capacity.
+    const int capacity = c.sm_count * (bps < 2 ? bps : 2);
     const int need = (n_units + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (blocks > need) blocks = need;
-    if (blocks < 1) blocks = 1;
+    int reserve = capacity / 8;                       // CTAs that only do resets (they overlap with the scans)
+    if (reserve < 1) reserve = 1;
+    int n_unit_ctas = need < capacity - reserve ? need : capacity - reserve;
+    if (n_unit_ctas < 1) n_unit_ctas = 1;
+    int blocks = n_unit_ctas + reserve;
+    if (need < capacity - reserve && blocks < capacity) {
+        // small batches: spare CTAs cost nothing; cap so that a handful of envs does not launch a whole grid
+        const int want = n_unit_ctas + (S.n_envs < 4096 ? 4 : reserve);
+        blocks = want < capacity ? want : capacity;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(c.device));
-    if (a.unroll == 4) k_step<4><<<blocks, kStepThreads, smem, st>>>(S, a);
-    else if (a.unroll == 16) k_step<16><<<blocks, kStepThreads, smem, st>>>(S, a);
-    else k_step<8><<<blocks, kStepThreads, smem, st>>>(S, a);
+    if (a.unroll == 4) k_step<4><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas);
+    else if (a.unroll == 16) k_step<16><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas);
+    else k_step<8><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas);
     CU(cudaGetLastError());
     return nullptr;
 }
@@ -556,9 +750,9 @@ static const char* launch_rebuild(Context&, const sdc::State& S, void* stream) {
 }
 
 static const char* set_kernel_attributes() {
-    CU(cudaFuncSetAttribute(k_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU(cudaFuncSetAttribute(k_step<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU(cudaFuncSetAttribute(k_step<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_step<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_step<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(sdc::kNoiseThreads * sdc::kNoiseSeg * sizeof(float))));
     CU(cudaFuncSetAttribute(k_rebuild, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));

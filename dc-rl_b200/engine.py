@@ -20,7 +20,7 @@ _STATE_DTYPES = {
     "t_min": np.float64, "t_max": np.float64, "weather": np.float64, "ls_head": np.int32, "ls_len": np.int32,
     "ls_sum": np.int32, "ls_bins": np.uint16, "ls_ring": np.uint8, "setpoint": np.float64, "dc_run": np.int32,
     "dc_scale": np.int32, "dc_last": np.int8, "bat_load": np.float64, "hist": np.float32, "hist_len": np.int32,
-    "hist_head": np.int32, "qlist": np.float32, "q_a": np.int32, "q_m": np.int32, "err": np.int32,
+    "hist_head": np.int32, "phase_clocks": np.uint64, "qlist": np.float32, "q_a": np.int32, "q_m": np.int32, "err": np.int32,
 }
 
 _default_lib = None
@@ -179,13 +179,17 @@ class Engine:
     def read_state(self, name):
         dt = np.dtype(_STATE_DTYPES[name])
         n = self.n_envs
-        per_env = {"weather": 2 * self.win_len, "ls_bins": 4, "hist": self.hist_cap, "qlist": 64, "q_a": 2, "q_m": 2}.get(name, 1)
-        if name == "ls_ring":
+        per_env = {"phase_clocks": 0, "weather": 2 * self.win_len, "ls_bins": 4, "hist": self.hist_cap, "qlist": 64, "q_a": 2, "q_m": 2}.get(name, 1)
+        if name == "phase_clocks":
+            out = np.zeros(8, dt)
+        elif name == "ls_ring":
             out = np.zeros(n * 65536, dt)       # upper bound; trimmed below
         else:
             out = np.zeros(n * per_env, dt)
         got = self._check(self.lib.sdc_read_state(self._h, name.encode(), _ptr(out), out.nbytes))
         out = out[:got // dt.itemsize]
+        if name == "phase_clocks":
+            return out
         return out.reshape(n, -1) if out.size != n else out
 
     def write_state(self, name, values):

@@ -169,10 +169,10 @@ int sdc_set_state(sdc_env* env, const void* blob, size_t bytes);
 const int32_t* sdc_error_flags(sdc_env* env);
 /* number of kernels this handle has launched (bench gpu_launches) */
 int64_t sdc_launch_count(sdc_env* env);
-/* Per-kernel device timing: after sdc_set_tuning(env, "timing", 1) every sdc_step brackets k_step and k_reset
+/* Per-kernel device timing: after sdc_set_tuning(env, "timing", 1) every sdc_step brackets its k_step launch
  * with CUDA events recorded on the launch stream.  sdc_kernel_times synchronises, writes
- * out[0] = number of timed steps, out[1] = sum of k_step ms, out[2] = sum of k_reset ms, out[3] = max k_step ms,
- * and clears the accumulators. */
+ * out[0] = number of timed steps, out[1] = sum of k_step ms, out[2] = 0 (episode resets run inside k_step),
+ * out[3] = max k_step ms, and clears the accumulators. */
 int sdc_kernel_times(sdc_env* env, double* out4);
 /* tuning knob for experiments: "unit_envs", "unroll", "prefetch", "blocks_per_sm", "timing" */
 int sdc_set_tuning(sdc_env* env, const char* key, int32_t value);

@@ -35,6 +35,8 @@ static void pinned_free(Context&, void* p) { free(p); }
 static const char* stream_create(Context&, void** s) { *s = nullptr; return nullptr; }
 static const char* stream_sync(Context&, void*) { return nullptr; }
 static const char* sync(Context&) { return nullptr; }
+static size_t reset_scratch_floats(Context&) { return 4; }
+static const char* dev_fill_bytes(Context&, void* p, int v, size_t bytes) { memset(p, v, bytes); return nullptr; }
 static const char* event_create(Context&, void** ev) { *ev = nullptr; return nullptr; }
 static const char* event_record(Context&, void*, void*) { return nullptr; }
 static const char* event_elapsed_ms(Context&, void*, void*, double* ms) { *ms = 0.0; return nullptr; }
@@ -52,38 +54,46 @@ struct InfoCol {
 static void scan_window(const sdc::State& S, int env, const sdc::ScanRequest& rq, sdc::ScanResult& rs) {
     const float* h = S.hist + (size_t)env * S.hist_cap;
     float s1 = 0.f, s2 = 0.f;
-    for (int j = 0; j < 2; ++j) { rs.cnt_below[j] = rs.cnt_above[j] = 0; rs.pred[j] = -INFINITY; rs.succ[j] = INFINITY; }
+    for (int j = 0; j < 2; ++j) { rs.cnt[j] = 0; rs.ext[j] = rq.dir[j] == sdc::SCAN_ABOVE ? INFINITY : -INFINITY; }
     for (int i = 0; i < rq.n; ++i) {
         const float x = h[i];
         const float c = fminf(fmaxf(x, rq.lo), rq.hi);
         const float d = c - rq.shift;
         s1 += d; s2 += d * d;
         for (int j = 0; j < 2; ++j) {
-            if (x < rq.below[j]) { rs.cnt_below[j]++; rs.pred[j] = fmaxf(rs.pred[j], x); }
-            if (x > rq.above[j]) { rs.cnt_above[j]++; rs.succ[j] = fminf(rs.succ[j], x); }
+            if (rq.dir[j] == sdc::SCAN_BELOW && x < rq.thr[j]) { rs.cnt[j]++; rs.ext[j] = fmaxf(rs.ext[j], x); }
+            if (rq.dir[j] == sdc::SCAN_ABOVE && x > rq.thr[j]) { rs.cnt[j]++; rs.ext[j] = fminf(rs.ext[j], x); }
         }
     }
     rs.s1 = s1; rs.s2 = s2;
 }
 
-static const char* launch_step(Context&, const sdc::State& S, const StepArgs& a, void*) {
-    *a.ticket_next = 0; *a.reset_count_next = 0;
+static const char* launch_reset(Context&, const sdc::State& S, const int32_t* list, const int32_t* count, float* obs, float* share, void*);
+
+static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs& a, void*) {
+    for (int k = 0; k < 4; ++k) a.ctr_next[k] = 0;
     const int N = S.n_envs;
     for (int env = 0; env < N; ++env) {
         ObsRow obs{a.obs + (size_t)env * 3 * SDC_OBS_DIM};
         InfoCol info{a.info, N, env};
         sdc::StepResult st;
-        sdc::physics_step(S, env, a.actions[env * 3 + 0], a.actions[env * 3 + 1], a.actions[env * 3 + 2], obs, info, st);
+        const sdc::Tables T{S.loc, S.dc};
+        sdc::physics_step(S, T, env, a.actions[env * 3 + 0], a.actions[env * 3 + 1], a.actions[env * 3 + 2], obs, info, st);
         sdc::share_from_obs(obs.row, a.share + (size_t)env * SDC_SHARE_DIM);
         sdc::ScanRequest rq; sdc::ScanResult rs;
-        sdc::reward_prepare(S, env, st.energy, rq);
+        sdc::QView Q;
+        for (int j = 0; j < 2; ++j) {
+            Q.lst[j] = S.qlist + ((size_t)env * 2 + j) * sdc::kListCap; Q.a[j] = S.q_a[env * 2 + j]; Q.m[j] = S.q_m[env * 2 + j];
+        }
+        sdc::reward_prepare(S, env, st.energy, st.hist_len, st.hist_head, st.evicted, Q, rq);
         scan_window(S, env, rq, rs);
         sdc::RewardInputs en{st.energy, st.nci_next, st.ls_penalty};
-        sdc::reward_finish(S, env, rq, rs, en, a.rew + (size_t)env * 3);
+        sdc::reward_finish(S, env, rq, rs, en, Q, a.rew + (size_t)env * 3);
+        for (int j = 0; j < 2; ++j) { S.q_a[env * 2 + j] = Q.a[j]; S.q_m[env * 2 + j] = Q.m[j]; }
         a.done[env] = (uint8_t)st.terminal;
         if (st.terminal) {
             if (a.term_obs) memcpy(a.term_obs + (size_t)env * 3 * SDC_OBS_DIM, obs.row, 3 * SDC_OBS_DIM * sizeof(float));
-            a.reset_list[(*a.reset_count)++] = env;
+            a.reset_list[a.ctr[1]++] = env;
         }
         double* M = a.metrics;
         M[sdc::M_ENERGY] += st.energy; M[sdc::M_CO2] += st.co2; M[sdc::M_WATER] += st.water;
@@ -94,6 +104,8 @@ static const char* launch_step(Context&, const sdc::State& S, const StepArgs& a,
         M[sdc::M_REWARD_SUM] += (double)r[0] + r[1] + r[2]; M[sdc::M_REWARD_LS] += r[0]; M[sdc::M_REWARD_DC] += r[1];
         M[sdc::M_OVERDUE] += st.overdue; M[sdc::M_TOTAL_KW] += st.total_kw;
     }
+    launch_reset(cx, S, a.reset_list, a.ctr + 1, a.obs, a.share, nullptr);     // the CUDA kernel does this with worker CTAs
+    for (int i = 0; i < a.ctr[1]; ++i) a.reset_list[i] = -1;
     return nullptr;
 }
 
