@@ -19,6 +19,10 @@
 #define SDC_HDN inline
 #endif
 
+#if !defined(__CUDACC__)
+struct uint2 { unsigned int x, y; };      // host builds (tests/hostsim) only need the layout
+#endif
+
 namespace sdc {
 
 constexpr int kQueueMax = 1000;       // sustaindc_env.py:148-149
@@ -722,13 +726,20 @@ constexpr int kNoiseSeg = 140;                            // 4-aligned segment l
 // Buffers and knobs of one step launch (all device pointers; see sdc_step in include/sdc_b200.h).
 struct StepArgs {
     const int32_t* actions; float* obs; float* share; float* rew; uint8_t* done; float* info; float* term_obs;
-    int32_t* ctr;          // this step's counters: [0] unit tickets, [1] finished envs appended to reset_list,
-    int32_t* ctr_next;     //                       [2] units past phase A, [3] reset_list slots claimed by workers
+    // this step's counters (ctr) and the next step's (ctr_next, zeroed by this launch):
+    //   [0] unit tickets  [1] finished envs appended to reset_list  [2] units past the scalar phase
+    //   [3] reset_list slots claimed by workers  [4] scan jobs published  [5] scan jobs claimed
+    int32_t* ctr;
+    int32_t* ctr_next;
     int32_t* reset_list;   // [N + slack], -1 = empty slot
     float* reset_scratch;  // per-CTA scratch of the in-kernel reset workers
+    uint2* job_queue;      // [N][8]  (word, step tag): global queue of window-scan job records (env + parameters)
+    uint2* job_results;    // [N][8]  (word, step tag): scan results per env
     double* metrics;
     unsigned long long* phase_clocks;   // optional [8]: summed per-warp clock64 deltas of the k_step phases (diagnostics)
+    int32_t seq;           // step tag (never 0)
     int32_t unit_envs, unroll, prefetch, blocks_per_sm;
+    int32_t local_jobs;    // envs of a unit scanned by the producing warp itself; the rest go to the global queue
 };
 
 // HARL shared observation (harl/envs/sustaindc/harlsustaindc_env.py:78-85): ls[0:26] | dc[11] | dc[13] |

@@ -116,6 +116,7 @@ __device__ __forceinline__ float warp_min(float v) {
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Issues, up front and all at once, the second-level (address-dependent) reads of one env-step so that their
@@ -372,6 +373,20 @@ __global__ void __launch_bounds__(kResetThreads) k_reset(const sdc::State S, con
 // =================================================================================================
 // k_step
 // =================================================================================================
+// Flag-tagged 8-byte words (value, step tag) for the lock-free hand-offs between warps: an aligned 8-byte store is
+// atomic, so a reader that sees the current step's tag also sees the value -- no fences (a gpu-scope fence costs
+// microseconds while HBM is saturated).
+__device__ __forceinline__ void st_pair(uint2* p, uint32_t val, uint32_t tag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(val), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_pair(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    return r;
+}
+enum { JP_ENV = 0, JP_N, JP_LO, JP_HI, JP_SHIFT, JP_DIRS, JP_THR0, JP_THR1, JP_WORDS = 8 };  // words of one queue record
+enum { JR_S1 = 0, JR_S2, JR_EXT0, JR_EXT1, JR_CNTS, JR_WORDS = 8 };                     // job result words per env
+
 template <int UNROLL>
 __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, const StepArgs a, const int n_unit_ctas) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -395,21 +410,48 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
     float* tile = reinterpret_cast<float*>(smem_raw + kTableBytes) + (size_t)warp * U * kObsRowPad;   // this warp's scratch
     const int N = S.n_envs;
     const int n_units = (N + U - 1) / U;
-    if (blockIdx.x == 0 && threadIdx.x < 4) a.ctr_next[threadIdx.x] = 0;
+    const uint32_t seq = (uint32_t)a.seq;
+    const int total_jobs = (N / U) * max(U - a.local_jobs, 0) + max(N % U - a.local_jobs, 0);       // records the queue will hold
+    if (blockIdx.x == 0 && threadIdx.x < 8) a.ctr_next[threadIdx.x] = 0;
 
-    for (; blockIdx.x < n_unit_ctas;) {
-        int unit = 0;
-        if (lane == 0) unit = atomicAdd(a.ctr + 0, 1);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit >= n_units) break;
-        const int env0 = unit * U;
-        const int env = env0 + lane;
-        const bool active = lane < U && env < N;
-        const int n_here = min(U, N - env0);
+    // ------------------------------------------------------------------------------------------------------------
+    // Every warp of a unit CTA runs this small state machine until no unit and no scan job is left:
+    //   produce  take a unit of U envs: scalar phase (one lane per env), then publish one window-scan job per env
+    //   consume  take any published job (global queue, any env of any warp) and stream that env's window
+    //   finish   once all jobs of the own unit have results: rewards, bracket write-back
+    // Jobs are balanced over all warps of the chip; a warp never blocks on a single condition, so there is no
+    // hold-and-wait cycle whatever the number of units per warp.
+    // ------------------------------------------------------------------------------------------------------------
+    if (a.phase_clocks && threadIdx.x == 0) atomicMin(a.phase_clocks + 8, gtime_ns());
+    bool have_unit = false, units_left = blockIdx.x < n_unit_ctas, jobs_left = blockIdx.x < n_unit_ctas;
+    int pending = -1;                                              // claimed job ticket not yet consumed
+    int env0 = 0, n_here = 0;
+    sdc::RewardInputs en;
+    en.energy = 0.0; en.nci_next = 0.0; en.ls_penalty = 0.0;
+    sdc::QView Q;
+    Q.lst[0] = tile + lane * kListRow; Q.lst[1] = Q.lst[0] + sdc::kListCap;
+    Q.a[0] = Q.a[1] = Q.m[0] = Q.m[1] = 0;
+    sdc::ScanRequest rq;                                           // the own env's request (phase C needs n, dirs, shift, q1)
+    rq.n = 0; rq.lo = rq.hi = rq.shift = 0.f; rq.dir[0] = rq.dir[1] = 0; rq.thr[0] = rq.thr[1] = 0.f; rq.degenerate = 0; rq.q1 = 0.0;
+    sdc::ScanResult mine;                                          // results of the locally scanned envs (lane l <-> env l)
+    mine.s1 = mine.s2 = 0.f; mine.cnt[0] = mine.cnt[1] = 0; mine.ext[0] = mine.ext[1] = 0.f;
+    int unit_n_local = 0;
+    long long clk_scan = 0, clk_idle = 0;
+    int n_jobs_done = 0;
 
+    while (have_unit || units_left || jobs_left || pending >= 0) {
+        // ---------------- produce ----------------
+        if (!have_unit && units_left) {
+            int unit = 0;
+            if (lane == 0) unit = atomicAdd(a.ctr + 0, 1);
+            unit = __shfl_sync(0xffffffffu, unit, 0);
+            if (unit >= n_units) { units_left = false; continue; }
+            env0 = unit * U;
+            const int env = env0 + lane;
+            const bool active = lane < U && env < N;
+            n_here = min(U, N - env0);
         const long long tk0 = clock64();
         // ---------------- phase A: one lane per env ----------------
-        sdc::RewardInputs en;                                       // what phase C needs from phase A
         en.energy = 0.0; en.nci_next = 0.0; en.ls_penalty = 0.0;
         int finished = 0, h_len = 0, h_head = 0;
         float h_evicted = 0.f;
@@ -517,98 +559,150 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         }
         __syncwarp();
         const long long tkC = clock64();
-        // Per-env scan parameters and results live in the env's shared-memory row, not in registers: anything that
-        // spills to local memory inside the per-env loop costs a ~2 us DRAM round trip while HBM is saturated.
-        sdc::QView Q;
-        Q.lst[0] = tile + lane * kListRow; Q.lst[1] = Q.lst[0] + sdc::kListCap;
         Q.a[0] = Q.a[1] = Q.m[0] = Q.m[1] = 0;
-        int rq_degenerate = 0;
-        double rq_q1 = 0.0;
-        if (lane < U) {                                            // rows exist for the unit's U lanes only
-            float* mb = tile + lane * kListRow;
-            int* mbi = reinterpret_cast<int*>(mb);
-            mbi[MB_N] = 0;
-            if (active) {
-                sdc::ScanRequest rq;
-                Q.a[0] = qa.x; Q.a[1] = qa.y; Q.m[0] = qm.x; Q.m[1] = qm.y;
-                sdc::reward_prepare(S, env, en.energy, h_len, h_head, h_evicted, Q, rq);
-                mbi[MB_N] = rq.n; mb[MB_LO] = rq.lo; mb[MB_HI] = rq.hi; mb[MB_SHIFT] = rq.shift;
-                mbi[MB_DIRS] = rq.dir[0] | (rq.dir[1] << 2); mb[MB_THR0] = rq.thr[0]; mb[MB_THR1] = rq.thr[1];
-                rq_degenerate = rq.degenerate; rq_q1 = rq.q1;
-            }
-            mb[MB_S1] = 0.f; mb[MB_S2] = 0.f; mbi[MB_CNT0] = 0; mbi[MB_CNT1] = 0; mb[MB_EXT0] = 0.f; mb[MB_EXT1] = 0.f;
-        }
-        __syncwarp();
-
-        const long long tk2 = clock64();
-        // ---------------- phase B: the warp streams each env's reward window ----------------
-        for (int l = 0; l < n_here; ++l) {
-            float* mb = tile + l * kListRow;
-            int* mbi = reinterpret_cast<int*>(mb);
-            const int n = mbi[MB_N];
-            if ((a.prefetch & 2) && l + 1 < n_here) {              // warm L2 with the head of the next env's window
-                const float* nxt = S.hist + (size_t)(env0 + l + 1) * S.hist_cap + lane * 32;
-                prefetch_line(nxt); prefetch_line(nxt + 1024);
-            }
-            if (n < 2) continue;                                   // z = 0 (utils/reward_creator.py:26-27)
-            const int dirs = mbi[MB_DIRS];
-            sdc::ScanResult rs;
-            scan_dispatch<UNROLL>(S.hist + (size_t)(env0 + l) * S.hist_cap, n, mb[MB_LO], mb[MB_HI], mb[MB_SHIFT], dirs & 3, dirs >> 2,
-                                  mb[MB_THR0], mb[MB_THR1], lane, rs);
-            if (lane == 0) {
-                mb[MB_S1] = rs.s1; mb[MB_S2] = rs.s2; mbi[MB_CNT0] = rs.cnt[0]; mbi[MB_CNT1] = rs.cnt[1];
-                mb[MB_EXT0] = rs.ext[0]; mb[MB_EXT1] = rs.ext[1];
-            }
-        }
-        __syncwarp();
-
-        const long long tk3 = clock64();
-        // ---------------- phase C: one lane per env ----------------
-        double m_sum = 0.0, m_ls = 0.0, m_dc = 0.0;
+        rq.n = 0; rq.dir[0] = rq.dir[1] = 0; rq.degenerate = 0; rq.q1 = 0.0; rq.shift = 0.f;
         if (active) {
-            const float* mb = tile + lane * kListRow;
-            const int* mbi = reinterpret_cast<const int*>(mb);
-            sdc::ScanRequest rq;
-            rq.n = mbi[MB_N]; rq.lo = mb[MB_LO]; rq.hi = mb[MB_HI]; rq.shift = mb[MB_SHIFT];
-            rq.dir[0] = mbi[MB_DIRS] & 3; rq.dir[1] = mbi[MB_DIRS] >> 2; rq.thr[0] = mb[MB_THR0]; rq.thr[1] = mb[MB_THR1];
-            rq.degenerate = rq_degenerate; rq.q1 = rq_q1;
-            sdc::ScanResult mine;
-            mine.s1 = mb[MB_S1]; mine.s2 = mb[MB_S2]; mine.cnt[0] = mbi[MB_CNT0]; mine.cnt[1] = mbi[MB_CNT1];
-            mine.ext[0] = mb[MB_EXT0]; mine.ext[1] = mb[MB_EXT1];
-            float r3[3];
-            sdc::reward_finish(S, env, rq, mine, en, Q, r3);
-            reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
-            reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
-            a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
-            m_sum = (double)r3[0] + r3[1] + r3[2]; m_ls = r3[0]; m_dc = r3[1];
+            Q.a[0] = qa.x; Q.a[1] = qa.y; Q.m[0] = qm.x; Q.m[1] = qm.y;
+            sdc::reward_prepare(S, env, en.energy, h_len, h_head, h_evicted, Q, rq);
         }
-        m_sum = warp_sum(m_sum); m_ls = warp_sum(m_ls); m_dc = warp_sum(m_dc);
-        if (lane == 0) {
-            atomicAdd(a.metrics + sdc::M_REWARD_SUM, m_sum); atomicAdd(a.metrics + sdc::M_REWARD_LS, m_ls);
-            atomicAdd(a.metrics + sdc::M_REWARD_DC, m_dc);
-        }
-        __syncwarp();
+        // The first `local_jobs` envs of the unit are scanned by this warp right away (parameters stay in registers);
+        // the others become records of the global job queue, which any warp of the chip consumes (load balance).
+        const int n_local = min(a.local_jobs, n_here);
+        unit_n_local = n_local;
+        mine.s1 = mine.s2 = 0.f; mine.cnt[0] = mine.cnt[1] = 0; mine.ext[0] = mine.ext[1] = 0.f;
         {
-            float4* dst = reinterpret_cast<float4*>(S.qlist + (size_t)env0 * 2 * sdc::kListCap);
-            const int total4 = n_here * (2 * sdc::kListCap / 4);
-            for (int i = lane; i < total4; i += 32) {
-                const int e = i >> 4, k = (i & 15) * 4;
-                const float* d = tile + e * kListRow + k;
-                dst[i] = make_float4(d[0], d[1], d[2], d[3]);
+            const bool queued = active && lane >= n_local;
+            const unsigned act = __ballot_sync(0xffffffffu, queued);
+            int base = 0;
+            if (lane == 0 && act) base = atomicAdd(a.ctr + 4, __popc(act));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (queued) {
+                uint2* jp = a.job_queue + (size_t)(base + __popc(act & ((1u << lane) - 1u))) * JP_WORDS;
+                st_pair(jp + JP_ENV, (uint32_t)env, seq); st_pair(jp + JP_N, (uint32_t)rq.n, seq);
+                st_pair(jp + JP_LO, __float_as_uint(rq.lo), seq); st_pair(jp + JP_HI, __float_as_uint(rq.hi), seq);
+                st_pair(jp + JP_SHIFT, __float_as_uint(rq.shift), seq); st_pair(jp + JP_DIRS, (uint32_t)(rq.dir[0] | (rq.dir[1] << 2)), seq);
+                st_pair(jp + JP_THR0, __float_as_uint(rq.thr[0]), seq); st_pair(jp + JP_THR1, __float_as_uint(rq.thr[1]), seq);
             }
         }
         __syncwarp();
-        if (a.phase_clocks && lane == 0) {
-            const long long tk4 = clock64();
-            atomicAdd(a.phase_clocks + 0, (unsigned long long)(tk1 - tk0));   // physics + info + metrics
-            atomicAdd(a.phase_clocks + 1, (unsigned long long)(tk2 - tk1));   // obs flush, list staging, bracket update
-            atomicAdd(a.phase_clocks + 2, (unsigned long long)(tk3 - tk2));   // window scans
-            atomicAdd(a.phase_clocks + 3, (unsigned long long)(tk4 - tk3));   // rewards, list write-back
-            atomicAdd(a.phase_clocks + 4, 1ull);                              // units
-            atomicAdd(a.phase_clocks + 5, (unsigned long long)(tkA - tk1));   // stage: obs/share tile flush
-            atomicAdd(a.phase_clocks + 6, (unsigned long long)(tkC - tkB));   // stage: bracket lists -> smem
-            atomicAdd(a.phase_clocks + 7, (unsigned long long)(tk2 - tkC));   // stage: window append + bracket update
+        const long long tl0 = clock64();
+        for (int l = 0; l < n_local; ++l) {
+            const int n = __shfl_sync(0xffffffffu, rq.n, l);
+            if (n < 2) continue;                                   // z = 0 (utils/reward_creator.py:26-27)
+            const int dirs = __shfl_sync(0xffffffffu, rq.dir[0] | (rq.dir[1] << 2), l);
+            sdc::ScanResult rs;
+            scan_dispatch<UNROLL>(S.hist + (size_t)(env0 + l) * S.hist_cap, n, __shfl_sync(0xffffffffu, rq.lo, l),
+                                  __shfl_sync(0xffffffffu, rq.hi, l), __shfl_sync(0xffffffffu, rq.shift, l), dirs & 3, dirs >> 2,
+                                  __shfl_sync(0xffffffffu, rq.thr[0], l), __shfl_sync(0xffffffffu, rq.thr[1], l), lane, rs);
+            if (lane == l) mine = rs;
+            n_jobs_done += 1;
         }
+        clk_scan += clock64() - tl0;
+        __syncwarp();
+        have_unit = true;
+        if (a.phase_clocks && lane == 0) {
+            const long long tk2 = clock64();
+            atomicAdd(a.phase_clocks + 0, (unsigned long long)(tk1 - tk0));   // physics + info + metrics
+            atomicAdd(a.phase_clocks + 1, (unsigned long long)(tk2 - tk1));   // obs flush, list staging, bracket update, publish
+            atomicAdd(a.phase_clocks + 4, 1ull);                              // units
+            atomicMax(a.phase_clocks + 9, gtime_ns());
+        }
+        continue;
+        }
+
+        // ---------------- consume ----------------
+        if (pending < 0 && jobs_left) {
+            int j = 0;
+            if (lane == 0) j = atomicAdd(a.ctr + 5, 1);
+            j = __shfl_sync(0xffffffffu, j, 0);
+            if (j >= total_jobs) jobs_left = false; else pending = j;
+        }
+        if (pending >= 0) {
+            uint2 w = make_uint2(0u, seq);
+            if (lane < JP_WORDS) w = ld_pair(a.job_queue + (size_t)pending * JP_WORDS + lane);       // one round trip: whole record
+            if (__all_sync(0xffffffffu, w.y == seq)) {
+                const long long tc0 = clock64();
+                const int jenv = (int)__shfl_sync(0xffffffffu, w.x, JP_ENV);
+                const int n = (int)__shfl_sync(0xffffffffu, w.x, JP_N);
+                sdc::ScanResult rs;
+                rs.s1 = rs.s2 = 0.f; rs.cnt[0] = rs.cnt[1] = 0; rs.ext[0] = rs.ext[1] = 0.f;
+                if (n >= 2) {                                      // n < 2: z = 0 (utils/reward_creator.py:26-27)
+                    const int dirs = (int)__shfl_sync(0xffffffffu, w.x, JP_DIRS);
+                    scan_dispatch<UNROLL>(S.hist + (size_t)jenv * S.hist_cap, n, __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_LO)),
+                                          __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_HI)),
+                                          __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_SHIFT)), dirs & 3, dirs >> 2,
+                                          __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_THR0)),
+                                          __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_THR1)), lane, rs);
+                }
+                if (lane < 5) {
+                    const uint32_t v = lane == JR_S1 ? __float_as_uint(rs.s1) : lane == JR_S2 ? __float_as_uint(rs.s2)
+                                     : lane == JR_EXT0 ? __float_as_uint(rs.ext[0]) : lane == JR_EXT1 ? __float_as_uint(rs.ext[1])
+                                     : (uint32_t)(rs.cnt[0] | (rs.cnt[1] << 16));
+                    st_pair(a.job_results + (size_t)jenv * JR_WORDS + lane, v, seq);
+                }
+                pending = -1;
+                clk_scan += clock64() - tc0; n_jobs_done += 1;
+                if (a.phase_clocks && lane == 0) atomicMax(a.phase_clocks + 10, gtime_ns());
+                continue;
+            }
+        }
+
+        // ---------------- finish ----------------
+        if (have_unit) {
+            const int env = env0 + lane;
+            const bool active = lane < U && env < N;
+            uint2 r[5];
+            bool ok = true;
+            const bool remote = active && lane >= unit_n_local;
+            if (remote) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { r[k] = ld_pair(a.job_results + (size_t)env * JR_WORDS + k); ok = ok && r[k].y == seq; }
+            }
+            if (__all_sync(0xffffffffu, ok)) {
+                const long long tk3 = clock64();
+                double m_sum = 0.0, m_ls = 0.0, m_dc = 0.0;
+                if (active) {
+                    if (remote) {
+                        mine.s1 = __uint_as_float(r[JR_S1].x); mine.s2 = __uint_as_float(r[JR_S2].x);
+                        mine.ext[0] = __uint_as_float(r[JR_EXT0].x); mine.ext[1] = __uint_as_float(r[JR_EXT1].x);
+                        mine.cnt[0] = (int)(r[JR_CNTS].x & 0xffffu); mine.cnt[1] = (int)(r[JR_CNTS].x >> 16);
+                    }
+                    float r3[3];
+                    sdc::reward_finish(S, env, rq, mine, en, Q, r3);
+                    reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
+                    reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
+                    a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
+                    m_sum = (double)r3[0] + r3[1] + r3[2]; m_ls = r3[0]; m_dc = r3[1];
+                }
+                m_sum = warp_sum(m_sum); m_ls = warp_sum(m_ls); m_dc = warp_sum(m_dc);
+                if (lane == 0) {
+                    atomicAdd(a.metrics + sdc::M_REWARD_SUM, m_sum); atomicAdd(a.metrics + sdc::M_REWARD_LS, m_ls);
+                    atomicAdd(a.metrics + sdc::M_REWARD_DC, m_dc);
+                }
+                __syncwarp();
+                {
+                    float4* dst = reinterpret_cast<float4*>(S.qlist + (size_t)env0 * 2 * sdc::kListCap);
+                    const int total4 = n_here * (2 * sdc::kListCap / 4);
+                    for (int i = lane; i < total4; i += 32) {
+                        const int e = i >> 4, k = (i & 15) * 4;
+                        const float* d = tile + e * kListRow + k;
+                        dst[i] = make_float4(d[0], d[1], d[2], d[3]);
+                    }
+                }
+                __syncwarp();
+                have_unit = false;
+                if (a.phase_clocks && lane == 0) { atomicAdd(a.phase_clocks + 3, (unsigned long long)(clock64() - tk3)); atomicMax(a.phase_clocks + 11, gtime_ns()); }
+                continue;
+            }
+        }
+        // nothing to do right now: the claimed job is not published yet and the own unit is still being scanned elsewhere
+        { const long long ti = clock64(); __nanosleep(100); clk_idle += clock64() - ti; }
+    }
+    if (a.phase_clocks && lane == 0) {
+        atomicAdd(a.phase_clocks + 2, (unsigned long long)clk_scan);      // window scans (all jobs this warp consumed)
+        atomicAdd(a.phase_clocks + 5, (unsigned long long)clk_idle);      // waiting
+        atomicAdd(a.phase_clocks + 6, (unsigned long long)n_jobs_done);
+        atomicAdd(a.phase_clocks + 7, 1ull);                              // warps
     }
 
     // ---------------- episode resets: every CTA turns into a reset worker once it has no unit left ----------------
@@ -641,6 +735,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         reset_one_env(S, env, a.obs, a.share, inc, rsh);
         __syncthreads();
     }
+    if (a.phase_clocks && threadIdx.x == 0) atomicMax(a.phase_clocks + 12, gtime_ns());
 }
 
 __global__ void k_build_reset_list(int n_envs, const uint8_t* __restrict__ mask, int32_t* list, int32_t* count) {

@@ -181,7 +181,7 @@ class Engine:
         n = self.n_envs
         per_env = {"phase_clocks": 0, "weather": 2 * self.win_len, "ls_bins": 4, "hist": self.hist_cap, "qlist": 64, "q_a": 2, "q_m": 2}.get(name, 1)
         if name == "phase_clocks":
-            out = np.zeros(8, dt)
+            out = np.zeros(16, dt)
         elif name == "ls_ring":
             out = np.zeros(n * 65536, dt)       # upper bound; trimmed below
         else:

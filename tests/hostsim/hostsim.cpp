@@ -71,7 +71,7 @@ static void scan_window(const sdc::State& S, int env, const sdc::ScanRequest& rq
 static const char* launch_reset(Context&, const sdc::State& S, const int32_t* list, const int32_t* count, float* obs, float* share, void*);
 
 static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs& a, void*) {
-    for (int k = 0; k < 4; ++k) a.ctr_next[k] = 0;
+    for (int k = 0; k < 8; ++k) a.ctr_next[k] = 0;
     const int N = S.n_envs;
     for (int env = 0; env < N; ++env) {
         ObsRow obs{a.obs + (size_t)env * 3 * SDC_OBS_DIM};
