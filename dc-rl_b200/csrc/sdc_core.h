@@ -277,14 +277,18 @@ struct StepResult {
     float evicted;
 };
 
+// What the observation builder needs from the scalar phase: k_step publishes the env's window-scan job first and
+// builds the observations afterwards, off the critical path of the scan queue.
+struct ObsDeferred { LsStats ls; double soc; Norms nm; int tn; };
+
 // The part of StepResult that has to survive the window scan (kept small: it lives in registers).
 struct RewardInputs { double energy, nci_next, ls_penalty; };
 
 // One env-step of the three sub-envs + managers + observations + info (everything except the
 // reward normaliser).  InfoSink: void operator()(int col, float v).
-template <class ObsSink, class InfoSink>
-SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, int a_dc, int a_bat, ObsSink& obs, InfoSink& info,
-                          StepResult& out) {
+template <class InfoSink>
+SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, int a_dc, int a_bat, InfoSink& info,
+                          StepResult& out, ObsDeferred& od) {
     // ---- level 1: every per-env scalar, issued back to back (no stores in between) ----
     const int t = S.t[env], t0 = S.t0[env], step0 = S.step_in_ep[env];
     int head = S.ls_head[env], len = S.ls_len[env], sum = S.ls_sum[env];
@@ -502,7 +506,7 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
     const int step_in_ep = step0 + 1;
     S.t[env] = tn; S.step_in_ep[env] = step_in_ep;
     const int terminal = step_in_ep >= S.ep_len;
-    build_obs(S, T, env, tn, ls, soc, nm, obs);
+    od.ls = ls; od.soc = soc; od.nm = nm; od.tn = tn;
     const double nci_next = (ci_fut[0] - nm.cmin) / nm.crng;
     info(I_OUTSIDE_TEMP, (float)outside_next); info(I_DAY, (float)(tn / 96)); info(I_HOUR, (float)((tn % 96) * 0.25));
     info(I_NORM_CI, (float)nci_next);
@@ -517,6 +521,12 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
     out.hvac_kw = (ct + comp) / 1e3; out.total_kw = total_kw;
     out.tasks_in_queue = len; out.tasks_dropped = dropped; out.overdue = over;
     if (err) flag_error(S, env, err);
+}
+
+// Observations of the step (sustaindc_env.py:578-582), from what physics_step left in `od`.
+template <class ObsSink>
+SDC_HDN void emit_obs(const State& S, const Tables& T, int env, const ObsDeferred& od, ObsSink& obs) {
+    build_obs(S, T, env, od.tn, od.ls, od.soc, od.nm, obs);
 }
 
 // ---- rolling quartiles: exact order statistics kept in a small sorted bracket -----------------

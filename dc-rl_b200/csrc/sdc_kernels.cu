@@ -70,7 +70,7 @@ static const char* event_elapsed_ms(Context&, void* a, void* b, double* ms) {
     float f = 0.f; CU(cudaEventElapsedTime(&f, (cudaEvent_t)a, (cudaEvent_t)b)); *ms = f; return nullptr;
 }
 static void event_destroy(Context&, void* ev) { cudaEventDestroy((cudaEvent_t)ev); }
-static size_t reset_scratch_floats(Context& c) { return (size_t)c.sm_count * 4 * sdc::kNoiseThreads * sdc::kNoiseSeg; }
+static size_t reset_scratch_floats(Context&) { return 4; }      // the reset workers need no global scratch any more
 static const char* dev_fill_bytes(Context&, void* p, int v, size_t bytes) { CU(cudaMemset(p, v, bytes)); return nullptr; }
 static const char* sync(Context& c) { CU(cudaSetDevice(c.device)); CU(cudaDeviceSynchronize()); return nullptr; }
 
@@ -80,10 +80,7 @@ static const char* sync(Context& c) { CU(cudaSetDevice(c.device)); CU(cudaDevice
 constexpr int kStepThreads = 256;
 constexpr int kWarpsPerBlock = kStepThreads / 32;
 constexpr int kObsRow = 3 * SDC_OBS_DIM;          // 78 floats per env
-constexpr int kObsRowPad = kObsRow + 1;           // odd stride: conflict-free one-lane-per-row writes
-constexpr int kListRow = kObsRowPad;              // both quartile lists of an env (64 floats) + a 15-word mailbox, odd stride
-// mailbox words of an env's scratch row: scan parameters written by its lane, results written by the scanning warp
-enum { MB_N = 64, MB_LO, MB_HI, MB_SHIFT, MB_DIRS, MB_THR0, MB_THR1, MB_S1, MB_S2, MB_CNT0, MB_CNT1, MB_EXT0, MB_EXT1 };
+constexpr int kListRow = 2 * sdc::kListCap + 4;   // both quartile lists of an env; 16-byte aligned rows for cp.async
 constexpr int kTableBytes = 8192;                 // shared-memory copy of the location / dc parameter tables
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -135,14 +132,43 @@ __device__ __forceinline__ void prefetch_env(const sdc::State& S, const sdc::Tab
     prefetch_line(L.workload + t); prefetch_line(L.ns + t); prefetch_line(L.sh + t);
 }
 
-struct SmemObsSink {
-    float* row;
-    __device__ __forceinline__ void operator()(int agent, int idx, float v) { row[agent * SDC_OBS_DIM + idx] = v; }
+// Observation rows written straight to the output tensors: obs[env][3][26], the HARL shared observation
+// (ls[0:26] | dc[11] | dc[13] | padded battery row [25], harlsustaindc_env.py:78-85) and, for finished envs, term_obs.
+struct GlobalObsSink {
+    float* obs; float* share; float* term;
+    __device__ __forceinline__ void operator()(int agent, int idx, float v) {
+#ifdef SDC_EXPERIMENT_NO_OBS_STORES
+        if (v == 123.456f) obs[0] = v;
+        return;
+#endif
+        obs[agent * SDC_OBS_DIM + idx] = v;
+        if (term) term[agent * SDC_OBS_DIM + idx] = v;
+        if (agent == 0) share[idx] = v;
+        else if (agent == 1 && idx == 11) share[26] = v;
+        else if (agent == 1 && idx == 13) share[27] = v;
+        else if (agent == 2 && idx == 25) share[28] = v;
+    }
 };
 struct GlobalInfoSink {
     float* info; int n, env;
     __device__ __forceinline__ void operator()(int col, float v) { if (info) info[(size_t)col * n + env] = v; }
 };
+
+// Streaming 128-bit load of the reward window.  Deliberately a WEAK load (no `volatile`, evict-first hint): the
+// CUDA intrinsics (__ldcg/__ldcs) are `asm volatile` and ld.global.cg compiles to LDG...STRONG.GPU, which ptxas
+// keeps in order and interleaves with the arithmetic -- only ~3 loads in flight when the warp first stalls.  Weak
+// loads let it issue the whole batch up front.  Coherence: a window line is read once per launch, after its new
+// sample was stored (ordering via the tagged queue words), and L1 is invalidated at kernel boundaries.
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 
 // ---- phase B: one warp streams one env's window -------------------------------------------------
 template <int D>
@@ -187,20 +213,21 @@ __device__ __forceinline__ void scan_window(const float* h, int n, float lo, flo
     for (; c + (UNROLL - 1) * 32 < n4; c += UNROLL * 32) {
         float4 v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) v[u] = __ldcg(p + c + u * 32);
+        for (int u = 0; u < UNROLL; ++u) v[u] = ld_stream(p + c + u * 32);
+        __syncwarp();            // scheduling fence: ptxas must issue the whole batch before the first use (see scan_job)
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) A.four(v[u]);
     }
     for (; c + 3 * 32 < n4; c += 4 * 32) {           // tail: groups of four rows, then single rows
         float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldcg(p + c + u * 32);
+        for (int u = 0; u < 4; ++u) v[u] = ld_stream(p + c + u * 32);
 #pragma unroll
         for (int u = 0; u < 4; ++u) A.four(v[u]);
     }
-    for (; c < n4; c += 32) A.four(__ldcg(p + c));
+    for (; c < n4; c += 32) A.four(ld_stream(p + c));
     const int rem = n & 3;
-    if (lane < rem) A.one(0, __ldcg(h + (n4 << 2) + lane));
+    if (lane < rem) A.one(0, ld_stream(h + (n4 << 2) + lane));
     rs.s1 = warp_sum((A.s1[0] + A.s1[1]) + (A.s1[2] + A.s1[3]));
     rs.s2 = warp_sum((A.s2[0] + A.s2[1]) + (A.s2[2] + A.s2[3]));
     rs.cnt[0] = D0 ? warp_sum(A.cnt[0]) : 0;
@@ -210,9 +237,10 @@ __device__ __forceinline__ void scan_window(const float* h, int n, float lo, flo
 }
 
 template <int UNROLL>
-// Own register allocation for the hot loop (not inlined into the large step kernel, whose scalar phases would
-// otherwise push spills into it -- measured: +45 % scan time).
-__device__ __noinline__ void scan_dispatch(const float* h, int n, float lo, float hi, float shift, int d0, int d1, float t0, float t1,
+// Inlined on purpose: results and parameters stay in registers.  Anything that goes through local memory in the
+// per-job path (a by-reference result struct, a State copy made for a non-inlined callee) misses the small L1 most of
+// the time and then costs a ~1.5 us round trip while HBM is saturated -- measured: +50 % per window scan.
+__device__ __forceinline__ void scan_dispatch(const float* h, int n, float lo, float hi, float shift, int d0, int d1, float t0, float t1,
                                            int lane, sdc::ScanResult& rs) {
     switch (d0 * 3 + d1) {
         case 0: scan_window<0, 0, UNROLL>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
@@ -271,9 +299,15 @@ struct ResetShared {
     float row[kObsRow];
 };
 
-// `inc` = scratch for the 256*140 random-walk increments of one env (shared memory in k_reset, an L2-resident global
-// buffer for the in-kernel workers).  Must be called by all kResetThreads threads of the CTA.
-__device__ __noinline__ void reset_one_env(const sdc::State& S, int env, float* obs, float* share, float* inc, ResetShared& sh) {
+constexpr int kNormWindow = 2880;                 // 30 days of quarter-hours (utils/managers.py:435,606)
+
+// Episode reset of one env by one CTA.  `runbuf` = kNormWindow doubles of shared memory.
+// Weather noise (utils/managers.py:35-48,596-613): the year-long random walk is generated ONCE (Philox, 140 samples per
+// thread); its mean / variance come from per-thread partial sums combined with the segment offsets, and only the walk
+// values that land in the 30-day window after the start are kept (in shared memory).  The emit pass then runs over
+// window positions, so its trace reads are coalesced and independent.  No global scratch: a dependent global access
+// costs ~2 us while the other CTAs saturate HBM with window scans.
+__device__ __forceinline__ void reset_one_env(const sdc::State& S, int env, float* obs, float* share, double* runbuf, ResetShared& sh) {
     const int tid = threadIdx.x;
     const int n = SDC_YEAR_STEPS;
     double* wt = S.weather + (size_t)env * 2 * S.win_len;
@@ -289,20 +323,29 @@ __device__ __noinline__ void reset_one_env(const sdc::State& S, int env, float* 
         const uint32_t ep = S.episode[env];
         const uint64_t seed = S.seed[env];
         if (tid == 0) sdc::draw_episode_start(seed, ep, S.day_lo[env], S.day_hi[env], &sh.start[0], &sh.start[1], &sh.start[2]);
-        // pass 1: increments of this thread's segment (utils/managers.py:45-46)
-        double seg = 0.0;
+        __syncthreads();
+        const int t0 = sh.start[0] * 96 + sh.start[1] * 4, roll = sh.start[2];
+        const int k_max = min(kNormWindow, n - t0);            // the reference's slice is truncated at the year end
+        // pass 1: this thread's segment of the walk (utils/managers.py:45-46)
+        double run = 0.0, sum_run = 0.0, sum_run2 = 0.0;
+        int cnt = 0;
         for (int q = 0; q < sdc::kNoiseSeg / 4; ++q) {
             float z[4];
             const int j0 = tid * sdc::kNoiseSeg + q * 4;
             sdc::noise_normals4(seed, ep, (uint32_t)(j0 >> 2), z);
-            const float4 v4 = make_float4(0.02f * z[0], 0.02f * z[1], 0.02f * z[2], 0.02f * z[3]);
-            *reinterpret_cast<float4*>(inc + j0) = v4;
-            if (j0 + 0 < n) seg += (double)v4.x;
-            if (j0 + 1 < n) seg += (double)v4.y;
-            if (j0 + 2 < n) seg += (double)v4.z;
-            if (j0 + 3 < n) seg += (double)v4.w;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                if (j < n) {
+                    run += (double)(0.02f * z[u]);
+                    sum_run += run; sum_run2 += run * run; cnt += 1;
+                    int t = j + 96 * roll; if (t >= n) t -= n;
+                    const int k = t - t0;
+                    if (k >= 0 && k < k_max) runbuf[k] = run;
+                }
+            }
         }
-        sh.seg_off[tid] = seg;
+        sh.seg_off[tid] = run;
         __syncthreads();
         if (tid == 0) {                           // serial exclusive prefix, same order as the host statement
             double acc = 0.0;
@@ -310,31 +353,23 @@ __device__ __noinline__ void reset_one_env(const sdc::State& S, int env, float* 
         }
         __syncthreads();
         const double off = sh.seg_off[tid];
-        const int j_lo = tid * sdc::kNoiseSeg, j_hi = min(j_lo + sdc::kNoiseSeg, n);
-        // pass 2 / 3: mean and population std of the walk
-        double run = 0.0, sum = 0.0;
-        for (int j = j_lo; j < j_hi; ++j) { run += (double)inc[j]; sum += off + run; }
-        const double mean = block_sum(sum, sh.red) / n;
-        run = 0.0; double ss = 0.0;
-        for (int j = j_lo; j < j_hi; ++j) { run += (double)inc[j]; const double d = (off + run) - mean; ss += d * d; }
-        const double scale = 0.75 / sqrt(block_sum(ss, sh.red) / n);          // managers.py:46-48
-        // pass 4: roll, clip, window, 30-day min/max (managers.py:598-608)
-        const int t0 = sh.start[0] * 96 + sh.start[1] * 4, roll = sh.start[2];
-        for (int k = tid; k < 2 * S.win_len; k += kResetThreads) wt[k] = 0.0;
-        __syncthreads();
+        // walk_j = off + run_j  ->  sums of w and w^2 from the partial sums
+        const double sw = block_sum(cnt * off + sum_run, sh.red);
+        const double sw2 = block_sum(cnt * off * off + 2.0 * off * sum_run + sum_run2, sh.red);
+        const double mean = sw / n;
+        const double scale = 0.75 / sqrt(sw2 / n - mean * mean);              // managers.py:46-48
+        // emit: roll, clip, window, 30-day min/max (managers.py:598-608), one window position per thread and trip
         const sdc::LocTables& L = S.loc[S.loc_id[env]];
         double tmin = INFINITY, tmax = -INFINITY;
-        run = 0.0;
-        for (int j = j_lo; j < j_hi; ++j) {
-            run += (double)inc[j];
-            int t = j + 96 * roll; if (t >= n) t -= n;
-            if (t < t0) continue;
-            const double noise = (off + run) * scale;
-            const double vt = fmin(fmax(L.temp_base[j] + noise, 0.0), 45.0);
-            if (t < t0 + 2880) { tmin = fmin(tmin, vt); tmax = fmax(tmax, vt); }
-            if (t < t0 + S.win_len) {
-                wt[t - t0] = vt;
-                ww[t - t0] = fmin(fmax(L.wetb_base[j] + noise, 0.0), 45.0);
+        for (int k = tid; k < max(k_max, S.win_len); k += kResetThreads) {
+            if (k < k_max) {
+                int j = t0 + k - 96 * roll; if (j < 0) j += n;
+                const double noise = (sh.seg_off[j / sdc::kNoiseSeg] + runbuf[k]) * scale;
+                const double vt = fmin(fmax(L.temp_base[j] + noise, 0.0), 45.0);
+                tmin = fmin(tmin, vt); tmax = fmax(tmax, vt);
+                if (k < S.win_len) { wt[k] = vt; ww[k] = fmin(fmax(L.wetb_base[j] + noise, 0.0), 45.0); }
+            } else if (k < S.win_len) {
+                wt[k] = 0.0; ww[k] = 0.0;                                      // beyond the year end (flagged domain)
             }
         }
         tmin = block_minmax(tmin, true, sh.red);
@@ -364,15 +399,33 @@ __device__ __noinline__ void reset_one_env(const sdc::State& S, int env, float* 
 // =================================================================================================
 __global__ void __launch_bounds__(kResetThreads) k_reset(const sdc::State S, const int32_t* __restrict__ list,
                                                          const int32_t* __restrict__ count, float* obs, float* share) {
-    extern __shared__ float inc[];                  // [256*140] random-walk increments of one env
+    extern __shared__ double runbuf[];              // [kNormWindow] walk values inside the 30-day window
     __shared__ ResetShared sh;
     const int total = *count;
-    for (int i = blockIdx.x; i < total; i += gridDim.x) reset_one_env(S, list[i], obs, share, inc, sh);
+    for (int i = blockIdx.x; i < total; i += gridDim.x) reset_one_env(S, list[i], obs, share, runbuf, sh);
 }
 
 // =================================================================================================
 // k_step
 // =================================================================================================
+// The window scan as a separate (non-inlined) function: with its own register allocation ptxas keeps all UNROLL
+// 128-bit loads of a batch in flight before the first use; inlined into the large kernel it sinks the loads next to
+// their uses to save registers and the scan runs ~45 % slower.  Results go through SHARED memory (8 words per warp):
+// a by-reference struct would live in local memory, which misses the small L1 and then costs a DRAM-latency round
+// trip per access while HBM is saturated.
+template <int UNROLL>
+__device__ __noinline__ void scan_job(const float* h, int n, float lo, float hi, float shift, int dirs, float t0, float t1,
+                                      float* out) {
+    const int lane = threadIdx.x & 31;
+    sdc::ScanResult rs;
+    scan_dispatch<UNROLL>(h, n, lo, hi, shift, dirs & 3, dirs >> 2, t0, t1, lane, rs);
+    if (lane == 0) {
+        out[0] = rs.s1; out[1] = rs.s2; out[2] = rs.ext[0]; out[3] = rs.ext[1];
+        reinterpret_cast<int*>(out)[4] = rs.cnt[0] | (rs.cnt[1] << 16);
+    }
+    __syncwarp();
+}
+
 // Flag-tagged 8-byte words (value, step tag) for the lock-free hand-offs between warps: an aligned 8-byte store is
 // atomic, so a reader that sees the current step's tag also sees the value -- no fences (a gpu-scope fence costs
 // microseconds while HBM is saturated).
@@ -407,7 +460,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         }
         __syncthreads();
     }
-    float* tile = reinterpret_cast<float*>(smem_raw + kTableBytes) + (size_t)warp * U * kObsRowPad;   // this warp's scratch
+    __shared__ float scan_out[kWarpsPerBlock * 8];
+    float* tile = reinterpret_cast<float*>(smem_raw + kTableBytes) + (size_t)warp * U * kListRow;     // this warp's bracket lists
     const int N = S.n_envs;
     const int n_units = (N + U - 1) / U;
     const uint32_t seq = (uint32_t)a.seq;
@@ -451,119 +505,67 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
             const bool active = lane < U && env < N;
             n_here = min(U, N - env0);
         const long long tk0 = clock64();
-        // ---------------- phase A: one lane per env ----------------
-        en.energy = 0.0; en.nci_next = 0.0; en.ls_penalty = 0.0;
-        int finished = 0, h_len = 0, h_head = 0;
-        float h_evicted = 0.f;
-        {
-            double m[13];
-#pragma unroll
-            for (int k = 0; k < 13; ++k) m[k] = 0.0;
-            if (active) {
-                prefetch_env(S, T, env);
-                // the unit's bracket lists (one contiguous block) are needed right after the physics
-                prefetch_line(S.qlist + (size_t)env * 2 * sdc::kListCap); prefetch_line(S.qlist + (size_t)env * 2 * sdc::kListCap + 32);
-                if (a.prefetch & 1) {
-                    const int len = S.hist_len[env];
-                    if (len >= 4 && lane < 2) l2_prefetch_bulk(S.hist + (size_t)env * S.hist_cap, (unsigned)((len * 4) & ~15));
-                }
-                const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
-                SmemObsSink obs{tile + lane * kObsRowPad};
-                GlobalInfoSink info{a.info, N, env};
-                sdc::StepResult st;
-                sdc::physics_step(S, T, env, a_ls, a_dc, a_bat, obs, info, st);
-                en.energy = st.energy; en.nci_next = st.nci_next; en.ls_penalty = st.ls_penalty;
-                h_len = st.hist_len; h_head = st.hist_head; h_evicted = st.evicted;
-                a.done[env] = (uint8_t)st.terminal;
-                finished = st.terminal;
-                if (st.terminal) {
-                    if (a.term_obs) {
-                        float* dst = a.term_obs + (size_t)env * kObsRow;
-                        for (int k = 0; k < kObsRow; ++k) dst[k] = obs.row[k];
-                    }
-                }
-                m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
-                m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
-                m[11] = st.overdue; m[12] = st.total_kw;
-            }
-            // logger sums (harl/envs/sustaindc/sustaindc_logger.py:86-101): warp reduce, one atomic per metric
-            constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
-                                      sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
-                                      sdc::M_OVERDUE, sdc::M_TOTAL_KW};
-#pragma unroll
-            for (int k = 0; k < 13; ++k) {
-                const double v = warp_sum(m[k]);
-                if (lane == 0) atomicAdd(a.metrics + slot[k], v);
-            }
-        }
-        __syncwarp();
-        const long long tk1 = clock64();
-        // observation tile -> global, coalesced (rows of a unit are contiguous in obs[N,3,26])
-        {
-            float2* dst = reinterpret_cast<float2*>(a.obs + (size_t)env0 * kObsRow);
-            const int total2 = n_here * (kObsRow / 2);
-            for (int i = lane; i < total2; i += 32) {
-                const int e = i / (kObsRow / 2), k = (i - e * (kObsRow / 2)) * 2;
-                dst[i] = make_float2(tile[e * kObsRowPad + k], tile[e * kObsRowPad + k + 1]);
-            }
-            float* sh = a.share + (size_t)env0 * SDC_SHARE_DIM;
-            const int total = n_here * SDC_SHARE_DIM;
-            for (int i = lane; i < total; i += 32) {
-                const int e = i / SDC_SHARE_DIM, k = i - e * SDC_SHARE_DIM;
-                // ls[0:26] | dc[11] | dc[13] | padded battery row [25]   (harlsustaindc_env.py:78-85)
-                const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
-                sh[i] = tile[e * kObsRowPad + src];
-            }
-        }
-        __syncwarp();
-        const long long tkA = clock64();
-        // Finished envs go to the reset workers (other CTAs of this launch).  Order matters: the terminal observation is
-        // in global memory before the env is published, because the worker overwrites obs/share with the reset ones.
-        // (The fences are only paid by the ~5 % of units that contain a finished env: a gpu-scope fence waits for all of
-        // the warp's outstanding stores and costs tens of microseconds while the other warps saturate HBM.)
-        if (__any_sync(0xffffffffu, finished)) {
-            __threadfence();
-            if (finished) a.reset_list[atomicAdd(a.ctr + 1, 1)] = env;
-            __threadfence();
-            __syncwarp();
-        }
-        if (lane == 0) atomicAdd(a.ctr + 2, 1);
-        const long long tkB = clock64();
-        // the unit's quartile brackets -> the same scratch (coalesced), updated in place, written back after phase C
-        int2 qa = make_int2(0, 0), qm = make_int2(0, 0);
-        if (active) { qa = reinterpret_cast<const int2*>(S.q_a)[env]; qm = reinterpret_cast<const int2*>(S.q_m)[env]; }
+        // ---------------- scalar phase, one lane per env ----------------
+        // (1) the unit's quartile brackets (one contiguous 8 KB block) start moving into shared memory asynchronously
         {
             const float4* src = reinterpret_cast<const float4*>(S.qlist + (size_t)env0 * 2 * sdc::kListCap);
             const int total4 = n_here * (2 * sdc::kListCap / 4);
-#ifdef SDC_BATCHED_LIST_STAGING   // measured slower overall on B200 (scan phase +50 %), kept for reference
-            float4 v[16];                                  // all 16 loads in flight before the first store
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { const int i = lane + 32 * j; if (i < total4) v[j] = __ldcg(src + i); }
+#if defined(SDC_LIST_STAGING_SERIAL)
+            for (int i = lane; i < total4; i += 32) {
+                const float4 v = src[i];
+                float* d = tile + (i >> 4) * kListRow + (i & 15) * 4;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+#elif defined(SDC_LIST_STAGING_CA)
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int i = lane + 32 * j;
                 if (i < total4) {
-                    const int e = i >> 4, k = (i & 15) * 4;
-                    float* d = tile + e * kListRow + k;
-                    d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + (i >> 4) * kListRow + (i & 15) * 4);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + i) : "memory");
                 }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
 #else
-            for (int i = lane; i < total4; i += 32) {
-                const float4 v = src[i];
-                const int e = i >> 4, k = (i & 15) * 4;
-                float* d = tile + e * kListRow + k;
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int i = lane + 32 * j;
+                if (i < total4) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + (i >> 4) * kListRow + (i & 15) * 4);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + i) : "memory");
+                }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
         }
+        int2 qa = make_int2(0, 0), qm = make_int2(0, 0);
+        if (active) { qa = reinterpret_cast<const int2*>(S.q_a)[env]; qm = reinterpret_cast<const int2*>(S.q_m)[env]; }
+        // (2) load shifting, data centre, battery -> the step's energy
+        en.energy = 0.0; en.nci_next = 0.0; en.ls_penalty = 0.0;
+        sdc::StepResult st;
+        sdc::ObsDeferred od;
+        st.terminal = 0;
+        if (active) {
+            prefetch_env(S, T, env);
+            if (a.prefetch & 1) {
+                const int len = S.hist_len[env];
+                if (len >= 4 && lane < 2) l2_prefetch_bulk(S.hist + (size_t)env * S.hist_cap, (unsigned)((len * 4) & ~15));
+            }
+            const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
+            GlobalInfoSink info{a.info, N, env};
+            sdc::physics_step(S, T, env, a_ls, a_dc, a_bat, info, st, od);
+            en.energy = st.energy; en.nci_next = st.nci_next; en.ls_penalty = st.ls_penalty;
+        }
+        const long long tk1 = clock64();
+        if (a.prefetch & 8) { const long long td = clock64(); while (clock64() - td < 100000) __nanosleep(500); }   // experiment: +50 us
+        // (3) append the energy to the reward window, update the brackets, publish the window-scan jobs
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        const long long tkC = clock64();
         Q.a[0] = Q.a[1] = Q.m[0] = Q.m[1] = 0;
         rq.n = 0; rq.dir[0] = rq.dir[1] = 0; rq.degenerate = 0; rq.q1 = 0.0; rq.shift = 0.f;
         if (active) {
             Q.a[0] = qa.x; Q.a[1] = qa.y; Q.m[0] = qm.x; Q.m[1] = qm.y;
-            sdc::reward_prepare(S, env, en.energy, h_len, h_head, h_evicted, Q, rq);
+            sdc::reward_prepare(S, env, en.energy, st.hist_len, st.hist_head, st.evicted, Q, rq);
         }
         // The first `local_jobs` envs of the unit are scanned by this warp right away (parameters stay in registers);
         // the others become records of the global job queue, which any warp of the chip consumes (load balance).
@@ -590,20 +592,63 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
             const int n = __shfl_sync(0xffffffffu, rq.n, l);
             if (n < 2) continue;                                   // z = 0 (utils/reward_creator.py:26-27)
             const int dirs = __shfl_sync(0xffffffffu, rq.dir[0] | (rq.dir[1] << 2), l);
-            sdc::ScanResult rs;
-            scan_dispatch<UNROLL>(S.hist + (size_t)(env0 + l) * S.hist_cap, n, __shfl_sync(0xffffffffu, rq.lo, l),
-                                  __shfl_sync(0xffffffffu, rq.hi, l), __shfl_sync(0xffffffffu, rq.shift, l), dirs & 3, dirs >> 2,
-                                  __shfl_sync(0xffffffffu, rq.thr[0], l), __shfl_sync(0xffffffffu, rq.thr[1], l), lane, rs);
-            if (lane == l) mine = rs;
+            float* rs_slot = scan_out + warp * 8;
+            scan_job<UNROLL>(S.hist + (size_t)(env0 + l) * S.hist_cap, n, __shfl_sync(0xffffffffu, rq.lo, l),
+                             __shfl_sync(0xffffffffu, rq.hi, l), __shfl_sync(0xffffffffu, rq.shift, l), dirs,
+                             __shfl_sync(0xffffffffu, rq.thr[0], l), __shfl_sync(0xffffffffu, rq.thr[1], l), rs_slot);
+            if (lane == l) {
+                mine.s1 = rs_slot[0]; mine.s2 = rs_slot[1]; mine.ext[0] = rs_slot[2]; mine.ext[1] = rs_slot[3];
+                const int c = reinterpret_cast<const int*>(rs_slot)[4];
+                mine.cnt[0] = c & 0xffff; mine.cnt[1] = c >> 16;
+            }
+            __syncwarp();
             n_jobs_done += 1;
         }
         clk_scan += clock64() - tl0;
         __syncwarp();
         have_unit = true;
+        const long long tk2 = clock64();
+        // (4) off the queue's critical path: observations (written straight to obs / share / term_obs; the L2 merges the
+        //     per-lane 4-byte stores into full sectors), logger sums, hand-over of finished envs to the reset workers
+        {
+            double m[13];
+#pragma unroll
+            for (int k = 0; k < 13; ++k) m[k] = 0.0;
+            const int finished = st.terminal;
+            if (active) {
+                GlobalObsSink obs{a.obs + (size_t)env * kObsRow, a.share + (size_t)env * SDC_SHARE_DIM,
+                                  (finished && a.term_obs) ? a.term_obs + (size_t)env * kObsRow : nullptr};
+                sdc::emit_obs(S, T, env, od, obs);
+                a.done[env] = (uint8_t)finished;
+                m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
+                m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
+                m[11] = st.overdue; m[12] = st.total_kw;
+            }
+            // logger sums (harl/envs/sustaindc/sustaindc_logger.py:86-101): warp reduce, one atomic per metric
+            constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
+                                      sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
+                                      sdc::M_OVERDUE, sdc::M_TOTAL_KW};
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {
+                const double v = warp_sum(m[k]);
+                if (lane == 0) atomicAdd(a.metrics + slot[k], v);
+            }
+            // Finished envs go to the reset workers (other CTAs of this launch).  Order matters: the terminal observation
+            // is in global memory before the env is published, because the worker overwrites obs/share with the reset
+            // ones.  Only the ~5 % of units that contain a finished env pay the gpu-scope fences.
+            if (__any_sync(0xffffffffu, finished)) {
+                __threadfence();
+                if (finished) a.reset_list[atomicAdd(a.ctr + 1, 1)] = env;
+                __threadfence();
+                __syncwarp();
+            }
+            if (lane == 0) atomicAdd(a.ctr + 2, 1);
+        }
         if (a.phase_clocks && lane == 0) {
-            const long long tk2 = clock64();
-            atomicAdd(a.phase_clocks + 0, (unsigned long long)(tk1 - tk0));   // physics + info + metrics
-            atomicAdd(a.phase_clocks + 1, (unsigned long long)(tk2 - tk1));   // obs flush, list staging, bracket update, publish
+            const long long tk2b = clock64();
+            atomicAdd(a.phase_clocks + 0, (unsigned long long)(tk1 - tk0));   // load shifting + data centre + battery
+            atomicAdd(a.phase_clocks + 1, (unsigned long long)(tk2 - tk1));   // window append, bracket update, publish (+ local scans)
+            atomicAdd(a.phase_clocks + 13, (unsigned long long)(tk2b - tk2)); // deferred observations + metrics
             atomicAdd(a.phase_clocks + 4, 1ull);                              // units
             atomicMax(a.phase_clocks + 9, gtime_ns());
         }
@@ -624,22 +669,19 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                 const long long tc0 = clock64();
                 const int jenv = (int)__shfl_sync(0xffffffffu, w.x, JP_ENV);
                 const int n = (int)__shfl_sync(0xffffffffu, w.x, JP_N);
-                sdc::ScanResult rs;
-                rs.s1 = rs.s2 = 0.f; rs.cnt[0] = rs.cnt[1] = 0; rs.ext[0] = rs.ext[1] = 0.f;
+                float* rs_slot = scan_out + warp * 8;
                 if (n >= 2) {                                      // n < 2: z = 0 (utils/reward_creator.py:26-27)
-                    const int dirs = (int)__shfl_sync(0xffffffffu, w.x, JP_DIRS);
-                    scan_dispatch<UNROLL>(S.hist + (size_t)jenv * S.hist_cap, n, __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_LO)),
-                                          __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_HI)),
-                                          __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_SHIFT)), dirs & 3, dirs >> 2,
-                                          __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_THR0)),
-                                          __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_THR1)), lane, rs);
+                    scan_job<UNROLL>(S.hist + (size_t)jenv * S.hist_cap, n, __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_LO)),
+                                     __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_HI)),
+                                     __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_SHIFT)), (int)__shfl_sync(0xffffffffu, w.x, JP_DIRS),
+                                     __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_THR0)),
+                                     __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_THR1)), rs_slot);
+                } else {
+                    if (lane < 5) rs_slot[lane] = 0.f;
+                    __syncwarp();
                 }
-                if (lane < 5) {
-                    const uint32_t v = lane == JR_S1 ? __float_as_uint(rs.s1) : lane == JR_S2 ? __float_as_uint(rs.s2)
-                                     : lane == JR_EXT0 ? __float_as_uint(rs.ext[0]) : lane == JR_EXT1 ? __float_as_uint(rs.ext[1])
-                                     : (uint32_t)(rs.cnt[0] | (rs.cnt[1] << 16));
-                    st_pair(a.job_results + (size_t)jenv * JR_WORDS + lane, v, seq);
-                }
+                if (lane < 5) st_pair(a.job_results + (size_t)jenv * JR_WORDS + lane, __float_as_uint(rs_slot[lane]), seq);
+                __syncwarp();
                 pending = -1;
                 clk_scan += clock64() - tc0; n_jobs_done += 1;
                 if (a.phase_clocks && lane == 0) atomicMax(a.phase_clocks + 10, gtime_ns());
@@ -712,7 +754,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
     __shared__ ResetShared rsh;
     __shared__ int s_env;
     __syncthreads();
-    float* inc = a.reset_scratch + (size_t)blockIdx.x * (sdc::kNoiseThreads * sdc::kNoiseSeg);
+    double* runbuf = reinterpret_cast<double*>(smem_raw + kTableBytes);   // the warps' scratch tiles are free by now
     for (;;) {
         if (threadIdx.x == 0) {
             const int my = atomicAdd(a.ctr + 3, 1);
@@ -732,7 +774,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         const int env = s_env;
         if (env < 0) break;
         __threadfence();
-        reset_one_env(S, env, a.obs, a.share, inc, rsh);
+        reset_one_env(S, env, a.obs, a.share, runbuf, rsh);
         __syncthreads();
     }
     if (a.phase_clocks && threadIdx.x == 0) atomicMax(a.phase_clocks + 12, gtime_ns());
@@ -792,7 +834,9 @@ __global__ void __launch_bounds__(kSortThreads) k_rebuild(const sdc::State S) {
 // =================================================================================================
 static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& a, void* stream) {
     const int U = a.unit_envs;
-    const size_t smem = kTableBytes + (size_t)kWarpsPerBlock * U * kObsRowPad * sizeof(float);
+    size_t smem = (size_t)kWarpsPerBlock * U * kListRow * sizeof(float);
+    if (smem < kNormWindow * sizeof(double)) smem = kNormWindow * sizeof(double);      // reset workers reuse the tile region
+    smem += kTableBytes + (size_t)(a.prefetch >> 8) * 1024;     // (experiment: pad)
     const int n_units = (S.n_envs + U - 1) / U;
     const int bps = a.blocks_per_sm > 0 ? a.blocks_per_sm : c.step_blocks_per_sm;
     // All CTAs must be co-resident (reset workers wait for unit CTAs): never more than the resident capacity.
@@ -819,7 +863,7 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
 
 static const char* launch_reset(Context& c, const sdc::State& S, const int32_t* list, const int32_t* count, float* obs, float* share,
                                 void* stream) {
-    const size_t smem = (size_t)sdc::kNoiseThreads * sdc::kNoiseSeg * sizeof(float);
+    const size_t smem = kNormWindow * sizeof(double);
     CU(cudaSetDevice(c.device));
     int blocks = c.sm_count;
     if (blocks > S.n_envs) blocks = S.n_envs;
@@ -848,8 +892,6 @@ static const char* set_kernel_attributes() {
     CU(cudaFuncSetAttribute(k_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_step<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_step<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(sdc::kNoiseThreads * sdc::kNoiseSeg * sizeof(float))));
     CU(cudaFuncSetAttribute(k_rebuild, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     return nullptr;
 }

@@ -22,23 +22,23 @@ def run(eng, steps, label):
     torch.cuda.synchronize()
     kt = eng.kernel_times(); ph = eng.read_state("phase_clocks").astype(np.float64)
     units = max(ph[4], 1); ghz = 1.965e3; warps = max(ph[7], 1); jobs = max(ph[6], 1)
-    print("%-40s k_step %.3f ms | per unit us: physics %.1f stage+publish %.1f finish %.1f | per warp us: scanning %.1f idle %.1f | per job us %.2f (jobs/warp %.1f)" % (
-        label, kt[1] / kt[0], ph[0] / units / ghz, ph[1] / units / ghz, ph[3] / units / ghz, ph[2] / warps / ghz, ph[5] / warps / ghz,
+    print("%-40s k_step %.3f ms | per unit us: core %.1f publish %.1f obs(deferred) %.1f finish %.1f | per warp us: scanning %.1f idle %.1f | per job us %.2f (jobs/warp %.1f)" % (
+        label, kt[1] / kt[0], ph[0] / units / ghz, ph[1] / units / ghz, ph[13] / units / ghz, ph[3] / units / ghz, ph[2] / warps / ghz, ph[5] / warps / ghz,
         ph[2] / jobs / ghz, jobs / warps), flush=True)
 eng, _ = bench.build_engine(n, 0)
 eng.set_tuning(timing=1)
 bench.prepare(eng, n, 0)
-for lj in (0, 8, 16, 24, 32):
+for lj in (0, 8):
     eng.set_tuning(unroll=8, prefetch=0, local_jobs=lj)
     run(eng, 30, "fresh unroll=8 local_jobs=%d" % lj)
-eng.set_tuning(local_jobs=16)
+eng.set_tuning(local_jobs=0)
 blob = eng.get_state()
 eng.write_state("step_in_ep", np.zeros(n, np.int32)); eng.write_state("t", eng.read_state("t0").astype(np.int32))
 eng.set_tuning(unroll=8, prefetch=0)
 run(eng, 30, "NO RESETS (synced episodes) unroll=8")
 eng.set_state(blob); eng.set_tuning(timing=1)
 for i in range(500): eng.step_device(acts[i % 8], obs, share, rew, done, None, None, st)
-for lj in (8, 16, 24):
+for lj in (0, 8):
   for unroll in (4, 8):
     eng.set_tuning(unroll=unroll, prefetch=0, local_jobs=lj)
     run(eng, 30, "sustained unroll=%d local_jobs=%d" % (unroll, lj))

@@ -32,13 +32,9 @@ def run2(eng, steps, label):
     print("%-34s k_step %.3f ms | per-unit us: physics %.1f stage %.1f scans %.1f finish %.1f | flush %.1f lists %.1f prepare %.1f" % (
         label, kt[1] / kt[0], ph[0] / units / ghz, ph[1] / units / ghz, ph[2] / units / ghz, ph[3] / units / ghz,
         ph[5] / units / ghz, ph[6] / units / ghz, ph[7] / units / ghz), flush=True)
-for name, path in (("A batched staging", "/root/repo/scratch/libsdc_A.so"), ("C serial staging", "/root/repo/scratch/libsdc_C.so")):
-    lib = _lib.load(path)
-    E._default_lib = lib
-    eng, _ = B.build_engine(n, 0)
-    eng.set_tuning(timing=1)
-    B.prepare(eng, n, 0)
-    for unroll in (4, 8):
-        eng.set_tuning(unroll=unroll)
-        run2(eng, 30, name + " unroll=%d" % unroll)
-    eng.close()
+eng, _ = B.build_engine(n, 0)
+eng.set_tuning(timing=1)
+B.prepare(eng, n, 0)
+for label, pf in (("baseline", 0), ("delay publish 50us", 8), ("smem +11KB", 11 << 8), ("smem +20KB", 20 << 8), ("both", 8 | (11 << 8))):
+    eng.set_tuning(unroll=8, prefetch=pf)
+    run(eng, 30, label)

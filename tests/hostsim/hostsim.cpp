@@ -78,7 +78,9 @@ static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs&
         InfoCol info{a.info, N, env};
         sdc::StepResult st;
         const sdc::Tables T{S.loc, S.dc};
-        sdc::physics_step(S, T, env, a.actions[env * 3 + 0], a.actions[env * 3 + 1], a.actions[env * 3 + 2], obs, info, st);
+        sdc::ObsDeferred od;
+        sdc::physics_step(S, T, env, a.actions[env * 3 + 0], a.actions[env * 3 + 1], a.actions[env * 3 + 2], info, st, od);
+        sdc::emit_obs(S, T, env, od, obs);
         sdc::share_from_obs(obs.row, a.share + (size_t)env * SDC_SHARE_DIM);
         sdc::ScanRequest rq; sdc::ScanResult rs;
         sdc::QView Q;
