@@ -210,7 +210,8 @@ __device__ __forceinline__ void scan_window(const float* h, int n, float lo, flo
     // UNROLL 16, bulk L2 prefetch) were measured SLOWER on B200: with ~2 400 independent 40 KB streams more
     // outstanding requests only add DRAM row conflicts (profiles/r01_summary.md).
     int c = lane;
-    for (; c + (UNROLL - 1) * 32 < n4; c += UNROLL * 32) {
+    const int nb = n4 / (UNROLL * 32);               // warp-uniform trip count (the fence below is a warp barrier)
+    for (int b = 0; b < nb; ++b, c += UNROLL * 32) {
         float4 v[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) v[u] = ld_stream(p + c + u * 32);
@@ -557,7 +558,6 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
             en.energy = st.energy; en.nci_next = st.nci_next; en.ls_penalty = st.ls_penalty;
         }
         const long long tk1 = clock64();
-        if (a.prefetch & 8) { const long long td = clock64(); while (clock64() - td < 100000) __nanosleep(500); }   // experiment: +50 us
         // (3) append the energy to the reward window, update the brackets, publish the window-scan jobs
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
@@ -836,7 +836,7 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     const int U = a.unit_envs;
     size_t smem = (size_t)kWarpsPerBlock * U * kListRow * sizeof(float);
     if (smem < kNormWindow * sizeof(double)) smem = kNormWindow * sizeof(double);      // reset workers reuse the tile region
-    smem += kTableBytes + (size_t)(a.prefetch >> 8) * 1024;     // (experiment: pad)
+    smem += kTableBytes;
     const int n_units = (S.n_envs + U - 1) / U;
     const int bps = a.blocks_per_sm > 0 ? a.blocks_per_sm : c.step_blocks_per_sm;
     // All CTAs must be co-resident (reset workers wait for unit CTAs): never more than the resident capacity.
