@@ -60,6 +60,7 @@ _PROTOS = {
     "sdc_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sdc_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "sdc_reset_host": (C.c_int, [_P, _P, _P, _P]),
+    "sdc_host_buffers": (C.c_int, [_P] + [C.POINTER(_P)] * 7),
     "sdc_metrics": (C.c_int, [_P, _P, C.c_int32]),
     "sdc_prefill_history": (C.c_int, [_P, _P, C.c_int32, C.c_int32]),
     "sdc_rebuild_brackets": (C.c_int, [_P, _P]),

@@ -97,6 +97,7 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None):
+            self.__dict__.pop("_hb", None)        # views into the handle's pinned buffers die with it
             self.lib.sdc_destroy(self._h)
             self._h = None
 
@@ -138,11 +139,22 @@ class Engine:
                                       _ptr(term_obs), _ptr(stream)))
 
     def _host_buffers(self):
+        """numpy views of the handle's page-locked I/O buffers (sdc_host_buffers): the host-side calls then move
+        data straight between these and the device, with no staging copy."""
         if not hasattr(self, "_hb"):
             n = self.n_envs
-            self._hb = dict(obs=np.zeros((n, N_AGENTS, OBS_DIM), np.float32), share=np.zeros((n, SHARE_DIM), np.float32),
-                            rew=np.zeros((n, N_AGENTS), np.float32), done=np.zeros(n, np.uint8),
-                            info=np.zeros((INFO_STRIDE, n), np.float32), term=np.zeros((n, N_AGENTS, OBS_DIM), np.float32))
+            p = [C.c_void_p() for _ in range(7)]
+            self._check(self.lib.sdc_host_buffers(self._h, *[C.byref(x) for x in p]))
+
+            def view(ptr, shape, ctype, dtype):
+                count = int(np.prod(shape))
+                return np.frombuffer((ctype * count).from_address(ptr.value), dtype=dtype).reshape(shape)
+            self._hb = dict(actions=view(p[0], (n, N_AGENTS), C.c_int32, np.int32),
+                            obs=view(p[1], (n, N_AGENTS, OBS_DIM), C.c_float, np.float32),
+                            share=view(p[2], (n, SHARE_DIM), C.c_float, np.float32),
+                            rew=view(p[3], (n, N_AGENTS), C.c_float, np.float32), done=view(p[4], (n,), C.c_uint8, np.uint8),
+                            info=view(p[5], (INFO_STRIDE, n), C.c_float, np.float32),
+                            term=view(p[6], (n, N_AGENTS, OBS_DIM), C.c_float, np.float32))
         return self._hb
 
     def reset_host(self, mask=None):
@@ -155,7 +167,8 @@ class Engine:
         """actions int32 [N,3] -> (obs[N,3,26], share[N,29], rew[N,3], done[N], info[64,N] | None, term_obs | None).
         The returned arrays are reused by the next call."""
         b = self._host_buffers()
-        a = np.ascontiguousarray(np.asarray(actions).reshape(self.n_envs, N_AGENTS), np.int32)
+        a = b["actions"]
+        a[...] = np.asarray(actions).reshape(self.n_envs, N_AGENTS)       # the one host copy: caller's actions -> pinned
         self._check(self.lib.sdc_step_host(self._h, _ptr(a), _ptr(b["obs"]), _ptr(b["share"]), _ptr(b["rew"]), _ptr(b["done"]),
                                            _ptr(b["info"]) if want_info else None, _ptr(b["term"]) if want_term else None))
         return b["obs"], b["share"], b["rew"], b["done"], (b["info"] if want_info else None), (b["term"] if want_term else None)

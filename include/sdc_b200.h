@@ -145,6 +145,13 @@ int sdc_step(sdc_env* env, const int32_t* actions_dev, float* obs_dev, float* sh
 int sdc_step_host(sdc_env* env, const int32_t* actions, float* obs, float* share, float* rew,
                   uint8_t* done, float* info, float* term_obs);
 int sdc_reset_host(sdc_env* env, const uint8_t* mask, float* obs, float* share);
+/* The handle's own page-locked HOST buffers, laid out like the sdc_step_host arguments (actions[N,3] int32,
+ * obs[N,3,26], share[N,29], rew[N,3], done[N], info[SDC_INFO_STRIDE][N], term_obs[N,3,26]); valid until
+ * sdc_destroy.  Passing these same pointers to sdc_step_host / sdc_reset_host makes the transfers go
+ * straight between them and the device (no staging copy on the host): this is how the Python vec-env hands
+ * numpy views to the runner.  Any of the out-pointers may be NULL. */
+int sdc_host_buffers(sdc_env* env, int32_t** actions, float** obs, float** share, float** rew, uint8_t** done,
+                     float** info, float** term_obs);
 
 /* ---- metrics / state ----------------------------------------------------------------------- */
 /* Running sums since the last call with clear!=0 (SustainDCLogger.per_step,
