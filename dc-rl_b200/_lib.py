@@ -10,6 +10,7 @@ import os
 MAX_RACK_CLASSES = 32
 N_AGENTS, OBS_DIM, SHARE_DIM, INFO_STRIDE = 3, 26, 29, 64
 YEAR_STEPS, TRACE_PAD, HIST_CAP, N_METRICS = 35040, 64, 10000, 16
+LIST_CAP, TAIL_CAP = 128, 128          # sdc_core.h kListCap / kTailCap (state inspection only)
 ABI_VERSION = 1
 
 F_WORKLOAD_RANGE, F_CPU_LOAD_RANGE, F_OUTLET_DELTA, F_TRACE_DOMAIN, F_BRACKET, F_NONFINITE, F_BATTERY = (

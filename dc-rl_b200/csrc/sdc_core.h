@@ -26,8 +26,17 @@ struct uint2 { unsigned int x, y; };      // host builds (tests/hostsim) only ne
 namespace sdc {
 
 constexpr int kQueueMax = 1000;       // sustaindc_env.py:148-149
-constexpr int kListCap = 32;          // sorted quartile bracket, one element per lane
-constexpr int kWidenMargin = 6;       // extend a bracket side when fewer ranks than this remain
+constexpr int kListCap = 128;         // sorted quartile bracket (order statistics around a quartile rank)
+constexpr int kWidenMargin = 4;       // safety net: extend a bracket side by one exact rank when fewer ranks than this remain
+constexpr int kRecentreMargin = 10;   // ask the refresh pass to re-centre a bracket when fewer ranks than this remain
+constexpr int kRecentreOk = 16;       // a re-centred bracket must have at least this many ranks on both sides
+constexpr int kCollectAim = 110;      // half-width of the re-centring interval in average bracket gaps
+constexpr int kCollectCap = 512;      // values a refresh can collect per bracket
+constexpr int kWexpMax = 6;           // |log2| range of the adaptive interval width
+constexpr int kTailCap = 128;         // values per tail band
+constexpr int kBandTarget = 40;       // a refresh narrows the bands when one holds more values than this
+constexpr int kAlphaOff = 12;         // narrowest tail band: alpha = 0.5 / 2^12 of the IQR
+constexpr int kTailRetry = 200;       // steps of plain scans before another attempt at tail sets that did not fit
 constexpr double kSpMin = 15.0, kSpMax = 21.6;   // utils/make_envs_pyenv.py:124-126
 
 // ---- info table columns: keep in sync with dc-rl_b200/info_layout.py -------------------------
@@ -91,6 +100,13 @@ struct State {
     float* qlist;                  // [N][2][kListCap] sorted order statistics around the quartile ranks
     int32_t* q_a;                  // [N][2] rank of qlist[.][0]
     int32_t* q_m;                  // [N][2] elements in the list
+    // incremental reward normaliser: window moments about c0, tail multisets, adaptive refresh parameters
+    double* mom_s1; double* mom_s2; double* mom_c0;   // [N]
+    float* tails;                  // [ceil(N/32)][2][kTailCap][32] interleaved (tail_ptr)
+    int32_t* tail_n;               // [N][2] set sizes, -1 = no valid sets
+    float* tail_thr;               // [N][4] TL, TH (inner thresholds), TL2, TH2 (outer thresholds)
+    int32_t* agg_n; double* agg_s; // [N][2] count, [N][2][2] sum / sum of squares about c0 of the values beyond TL2 / TH2
+    uint32_t* fast_cfg;            // [N] byte 0 tail slack exponent, 1 retry countdown, 2/3 interval width exponents (int8)
     int32_t* err;                  // [N] SDC_F_* bits
     // staged ("injected") next episodes; null until sdc_stage_episode is used
     uint8_t* pend_valid; int32_t* pend_day; int32_t* pend_hour; double* pend_tmin; double* pend_tmax;
@@ -269,6 +285,7 @@ struct StepResult {
     double nci_next;      // norm_CI of the next step (ci_i_future[0], sustaindc_env.py:681)
     double ls_penalty;    // (-0.3*sqrt(overdue)+0.3) + (-0.1*oldest_age)   reward_creator.py:67-82
     int terminal;
+    int step_after;       // steps taken in the episode including this one
     // logger metrics of this step
     double co2, water, ite_kw, ct_kw, comp_kw, hvac_kw, total_kw;
     int tasks_in_queue, tasks_dropped, overdue;
@@ -516,7 +533,7 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
 
     out.energy = energy; out.nci_next = nci_next;
     out.ls_penalty = (-0.3 * sqrt((double)over) + 0.3) + (-0.1 * ls.oldest);
-    out.terminal = terminal;
+    out.terminal = terminal; out.step_after = step_in_ep;
     out.co2 = co2; out.water = water; out.ite_kw = p_it / 1e3; out.ct_kw = ct / 1e3; out.comp_kw = comp / 1e3;
     out.hvac_kw = (ct + comp) / 1e3; out.total_kw = total_kw;
     out.tasks_in_queue = len; out.tasks_dropped = dropped; out.overdue = over;
@@ -529,31 +546,58 @@ SDC_HDN void emit_obs(const State& S, const Tables& T, int env, const ObsDeferre
     build_obs(S, T, env, od.tn, od.ls, od.soc, od.nm, obs);
 }
 
-// ---- rolling quartiles: exact order statistics kept in a small sorted bracket -----------------
-// For each quartile j the list lst[j][0..m) holds the order statistics of the window at ranks
-// a .. a+m-1 (rank-contiguous, ties allowed).  One value enters and at most one leaves per step, so a
-// rank moves by at most one list position per step; the list is updated in O(1) here, and a side that
-// runs short (< kWidenMargin ranks beyond the needed pair) is extended by one rank from the full-window
-// scan of the same step: at most one side per list per step, which is enough because the two margins of a
-// list cannot both shrink in the same step.  Exactness does not depend on the value distribution.
-struct QView {              // the caller stages the two lists (global rows, or shared memory in k_step)
+// ---- reward normaliser (utils/reward_creator.py:16-45) without a window pass per step ----------
+// The reference recomputes, every step, q1/q3 of the 10 000-sample energy window, clips the window to the IQR fences
+// and takes mean / std of the clipped values.  One sample enters and at most one leaves per step, so all of that
+// is maintained incrementally and EXACTLY (same multiset, same order statistics); the 40 KB window is streamed only
+// when a maintained structure runs out of slack ("refresh", a few times per thousand steps per env):
+//
+//  * quartile brackets  lst[j][0..m) = order statistics at ranks a .. a+m-1 around rank k_j = floor((n-1) p_j)
+//    (rank-contiguous, ties allowed).  Insert / evict update (a, m, lst) by comparing against the list ends only.  The
+//    position of k_j inside the list performs a random walk; when fewer than kRecentreMargin ranks remain on a side
+//    the next refresh re-centres the list: it collects ALL window values inside a value interval around the
+//    quartile plus the count of values below the interval, sorts them and cuts ranks k-31 .. k+32 out of them.
+//    Should the interval turn out too narrow / too wide (it adapts), the list is still extended by one exact rank
+//    per step from the same scan (count and extreme of the values beyond the list end), so ranks k, k+1 never
+//    leave the list whatever the distribution.
+//  * moments  S1 = sum(x - c0), S2 = sum((x - c0)^2) over the whole window in fp64 (add the new sample, subtract
+//    the evicted one; resynchronised exactly by every refresh).
+//  * tails    clipping only changes the values beyond the fences, so sum(clip(x)) = S1 + sum_{x<lo}(lo - x) -
+//    sum_{x>hi}(x - hi) (likewise for squares).  Around each fence a BAND of values (fence -/+ alpha IQR) is kept
+//    individually as an unsorted multiset, everything beyond the band as (count, sum, sum of squares): a loop over
+//    a few dozen floats instead of 10 000.  When a fence leaves its band, or a band overflows, the refresh rebuilds
+//    both (alpha adapts to the density at the fences; distributions with heavy ties exactly at a fence fall back to
+//    a plain clipped-moment pass every step).
+struct QView {              // the two lists of an env (rows of S.qlist)
     float* lst[2];
     int a[2], m[2];
 };
 enum ScanDir { SCAN_NONE = 0, SCAN_BELOW = 1, SCAN_ABOVE = 2 };
+enum ScanKind { SCAN_SKIP = 0, SCAN_PLAIN = 1, SCAN_REFRESH = 2 };
 struct ScanRequest {
     int n;                  // window length including the new value
-    float lo, hi, shift;    // IQR fences and the centring shift of the moment sums
+    float lo, hi, shift;    // IQR fences and the centring shift of the scanned moment sums
     int dir[2];             // per quartile list: SCAN_BELOW -> count x < thr and track their max (rank a-1),
     float thr[2];           //                    SCAN_ABOVE -> count x > thr and track their min (rank a+m)
     int degenerate;         // q1 == q3: sigma is exactly 0 (utils/reward_creator.py:43-45 divides by 1)
     double q1;
+    double lo64, hi64;      // the fences before the fp32 cast (the incremental path clips in fp64 like the reference)
+    // refresh plan
+    int kind;               // ScanKind
+    int rc[2], k[2];        // re-centre list j around rank k[j] from all values in [ca[j], cb[j]]
+    float ca[2], cb[2];
+    int tails;              // rebuild the tail bands: tl2 <= x < tl and th < x <= th2 individually, beyond that aggregated
+    float tl, th, tl2, th2;
+    float e, o; int evict;  // the appended / evicted sample
 };
 struct ScanResult {
     float s1, s2;           // sum(c - shift), sum((c - shift)^2) over the clipped window
     int cnt[2];
     float ext[2];
+    int recentred;          // bit j: the refresh rewrote list j (a, m in new_a / new_m)
+    int new_a[2], new_m[2];
 };
+struct Moments { double c1, c2, c0; int ok; };   // clipped sums about c0 from the incremental path
 
 #if defined(__CUDA_ARCH__)
 #define SDC_INF_F __int_as_float(0x7f800000)
@@ -561,14 +605,62 @@ struct ScanResult {
 #define SDC_INF_F INFINITY
 #endif
 
+// tail set `side` (0: below TL, 1: above TH) of an env: element i lives at p[i * kTailStride].  Interleaved by 32 envs
+// so that one lane per env walks its set with coalesced loads.
+constexpr int kTailStride = 32;
+SDC_HD float* tail_ptr(const State& S, int env, int side) {
+    return S.tails + ((size_t)(env >> 5) * 2 + side) * kTailCap * kTailStride + (env & 31);
+}
+
+// Shifts inside a bracket run in batches of 8 (all loads of a batch before its stores): one lane moves up to a
+// hundred floats through global memory, and element-by-element that is a chain of dependent round trips.
+SDC_HD void shift_down(float* lst, int from, int to) {        // lst[i] = lst[i + 1] for i in [from, to)
+    int i = from;
+    for (; i + 8 <= to; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = lst[i + 1 + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) lst[i + u] = v[u];
+    }
+    for (; i < to; ++i) lst[i] = lst[i + 1];
+}
+SDC_HD void shift_up(float* lst, int from, int to) {          // lst[i] = lst[i - 1] for i in (from, to], descending
+    int i = to;
+    for (; i - 8 >= from; i -= 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = lst[i - 1 - u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) lst[i - u] = v[u];
+    }
+    for (; i > from; --i) lst[i] = lst[i - 1];
+}
+// first index in [0, m) with lst[i] == o (batched compares), or m
+SDC_HD int find_equal(const float* lst, int m, float o) {
+    for (int i0 = 0; i0 < m; i0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (i0 + u < m) ? lst[i0 + u] : o;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (v[u] == o && i0 + u < m) return i0 + u;
+    }
+    return m;
+}
+// number of elements <= e in the sorted lst[0..m) (insertion point after ties)
+SDC_HD int upper_bound(const float* lst, int m, float e) {
+    int lo = 0, hi = m;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (lst[mid] <= e) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
 SDC_HD void list_remove(float* lst, int& a, int& m, float o, int& err) {
     if (m == 0) { err |= SDC_F_BRACKET; return; }
     if (o < lst[0]) { a -= 1; return; }
     if (o > lst[m - 1]) return;
-    int i = 0;
-    while (i < m && lst[i] != o) ++i;
+    const int i = find_equal(lst, m, o);
     if (i == m) { err |= SDC_F_BRACKET; return; }
-    for (; i + 1 < m; ++i) lst[i] = lst[i + 1];
+    shift_down(lst, i, m - 1);
     m -= 1;
 }
 
@@ -577,29 +669,28 @@ SDC_HD void list_insert(float* lst, int& a, int& m, float e, int n_after, int k_
     if (m > 0 && e < lst[0] && a > 0) { a += 1; return; }
     if (m > 0 && e > lst[m - 1] && a + m < n_after - 1) return;     // ranks above the list, list not at the top
     // e belongs inside the list (or extends a list that reaches the end of the window)
-    int pos = 0;
-    while (pos < m && lst[pos] <= e) ++pos;
+    const int pos = upper_bound(lst, m, e);
     if (m == kListCap) {
         // full: drop from the side with more spare ranks around the target k_after
         const int r = k_after - a;
         const int margin_lo = r, margin_hi = m - 1 - r;
         if (margin_lo > margin_hi) {            // drop lst[0]
             if (pos == 0) { a += 1; return; }   // e itself would be the dropped element
-            for (int i = 0; i + 1 < pos; ++i) lst[i] = lst[i + 1];
+            shift_down(lst, 0, pos - 1);
             lst[pos - 1] = e; a += 1; return;
         } else {                                // drop lst[m-1]
             if (pos == m) return;
-            for (int i = m - 1; i > pos; --i) lst[i] = lst[i - 1];
+            shift_up(lst, pos, m - 1);
             lst[pos] = e; return;
         }
     }
-    for (int i = m; i > pos; --i) lst[i] = lst[i - 1];
+    shift_up(lst, pos, m);
     lst[pos] = e;
     m += 1;
 }
 
 // Appends `energy` to the env's reward window (fp32 ring; `o` = the value it evicts, if any), updates both
-// quartile brackets and returns what the full-window scan must compute.  utils/reward_creator.py:16-45.
+// quartile brackets and derives the fences.  utils/reward_creator.py:16-45.
 SDC_HDN void reward_prepare(const State& S, int env, double energy, int len, int head, float evicted, QView& Q, ScanRequest& rq) {
     int err = 0;
     float e = (float)energy;
@@ -612,15 +703,17 @@ SDC_HDN void reward_prepare(const State& S, int env, double energy, int len, int
     head += 1; if (head == cap) head = 0;
     S.hist_len[env] = len; S.hist_head[env] = head;
     const int n = len;
-    rq.n = n; rq.degenerate = 0;
+    rq.n = n; rq.degenerate = 0; rq.e = e; rq.o = o; rq.evict = evict;
+    const uint32_t fc = S.fast_cfg[env];
     double qv[2] = {0.0, 0.0};
     for (int j = 0; j < 2; ++j) {
         float* lst = Q.lst[j];
         int a = Q.a[j], m = Q.m[j];
-        rq.dir[j] = SCAN_NONE; rq.thr[j] = 0.f;
+        rq.dir[j] = SCAN_NONE; rq.thr[j] = 0.f; rq.rc[j] = 0; rq.ca[j] = rq.cb[j] = 0.f;
         const int num = (j == 0 ? 1 : 3) * (n - 1);
         const int k = num / 4;                                   // np.percentile 'linear': idx = (n-1)*p
         const double frac = (double)(num % 4) * 0.25;
+        rq.k[j] = k;
         if (evict) list_remove(lst, a, m, o, err);
         if (m == 0) { lst[0] = e; a = 0; m = 1; }                // first value ever
         else list_insert(lst, a, m, e, n, k);
@@ -635,49 +728,251 @@ SDC_HDN void reward_prepare(const State& S, int env, double energy, int len, int
                 const int margin_lo = (a > 0) ? r : kListCap, margin_hi = (a + m < n) ? m - 2 - r : kListCap;
                 if (margin_lo < kWidenMargin && margin_lo <= margin_hi) { rq.dir[j] = SCAN_BELOW; rq.thr[j] = lst[0]; }
                 else if (margin_hi < kWidenMargin) { rq.dir[j] = SCAN_ABOVE; rq.thr[j] = lst[m - 1]; }
+                if (margin_lo < kRecentreMargin || margin_hi < kRecentreMargin) {
+                    // all values within ~kCollectAim average list gaps of the quartile pair (width adapts per env and list)
+                    const int wexp = (int)(int8_t)(fc >> (16 + 8 * j));
+                    const float gap = (lst[m - 1] - lst[0]) / (float)(m - 1);
+                    const float w = ldexpf(gap * (float)kCollectAim, wexp);
+                    rq.rc[j] = 1; rq.ca[j] = lst[r] - w; rq.cb[j] = lst[r + 1] + w;
+                }
             }
         }
         Q.a[j] = a; Q.m[j] = m;
     }
     const double iqr = qv[1] - qv[0];
     rq.q1 = qv[0];
-    rq.lo = (float)(qv[0] - 1.5 * iqr); rq.hi = (float)(qv[1] + 1.5 * iqr);
+    rq.lo64 = qv[0] - 1.5 * iqr; rq.hi64 = qv[1] + 1.5 * iqr;
+    rq.lo = (float)rq.lo64; rq.hi = (float)rq.hi64;
     rq.shift = (float)(0.5 * (qv[0] + qv[1]));
     rq.degenerate = (qv[0] == qv[1]);
     if (err) flag_error(S, env, err);
 }
 
-// Extends the brackets with the ranks found by the scan and turns the moments into the three rewards.
-SDC_HDN void reward_finish(const State& S, int env, const ScanRequest& rq, const ScanResult& rs, const RewardInputs& st,
-                           QView& Q, float* rew3) {
+// Incremental side of the normaliser: updates the window moments, the tail bands and the far-tail aggregates with
+// the step's sample, and returns the clipped sums when the bands still contain both fences.  Also decides what kind
+// of window pass (if any) the step needs and, for a refresh, the new band thresholds.
+//
+// Per side the values beyond the inner threshold are split once more: those in the BAND between the inner and the
+// outer threshold (TL2 <= x < TL, TH < x <= TH2; the fence lies inside the band) are kept individually, those
+// beyond the outer threshold only as (count, sum, sum of squares) -- they are clipped whatever the fence does inside
+// the band.  So a large outlier population (e.g. after a regime change) costs nothing per step.
+SDC_HD void tail_side(float* p, int& cnt, int& agg_n, double& agg_s1, double& agg_s2, bool below, float t_in, float t_out,
+                      double fence, double c0, float e, float o, bool evict, double& c1, double& c2, bool& valid, int& err) {
+    const double yf = fence - c0;
+    // far tail: clipped to the fence as a whole
+    const bool e_far = below ? e < t_out : e > t_out, o_far = evict && (below ? o < t_out : o > t_out);
+    if (e_far) { const double y = (double)e - c0; agg_n += 1; agg_s1 += y; agg_s2 = fma(y, y, agg_s2); }
+    if (o_far) { const double y = (double)o - c0; agg_n -= 1; agg_s1 -= y; agg_s2 = fma(-y, y, agg_s2); }
+    c1 += (double)agg_n * yf - agg_s1;
+    c2 += (double)agg_n * yf * yf - agg_s2;
+    // band: individual values; sum (fence - x) over those beyond the fence.  Batches of 8 loads issued together (the walk
+    // is latency-bound: one lane per env, the 32 envs of a unit interleaved so that a batch row is one 128-byte line).
+    const bool rm = evict && !o_far && (below ? o < t_in : o > t_in);
+    const float pad = below ? SDC_INF_F : -SDC_INF_F;            // contributes nothing, never equals o
+    int idx = -1;
+    for (int i0 = 0; i0 < cnt; i0 += 8) {
+        float xs[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xs[u] = (i0 + u < cnt) ? p[(size_t)(i0 + u) * kTailStride] : pad;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float x = xs[u];
+            if (rm && idx < 0 && x == o) { idx = i0 + u; continue; }
+            const double t = fence - (double)x;                  // > 0 below the lower fence, < 0 above the upper one
+            if (below ? t > 0.0 : t < 0.0) { c1 += t; c2 = fma(t, yf + ((double)x - c0), c2); }
+        }
+    }
+    if (rm) {
+        if (idx < 0) { err |= SDC_F_BRACKET; valid = false; }
+        else { cnt -= 1; if (idx != cnt) p[(size_t)idx * kTailStride] = p[(size_t)cnt * kTailStride]; }
+    }
+    if (!e_far && (below ? e < t_in : e > t_in)) {
+        if (cnt >= kTailCap) valid = false;
+        else {
+            p[(size_t)cnt * kTailStride] = e; cnt += 1;
+            const double t = fence - (double)e;
+            if (below ? t > 0.0 : t < 0.0) { c1 += t; c2 = fma(t, yf + ((double)e - c0), c2); }
+        }
+    }
+}
+
+SDC_HDN void reward_plan(const State& S, int env, ScanRequest& rq, Moments& M) {
+    const float e = rq.e, o = rq.o;
+    const bool evict = rq.evict != 0;
+    const double c0 = S.mom_c0[env];
+    double s1 = S.mom_s1[env], s2 = S.mom_s2[env];
+    { const double y = (double)e - c0; s1 += y; s2 = fma(y, y, s2); }
+    if (evict) { const double y = (double)o - c0; s1 -= y; s2 = fma(-y, y, s2); }
+    S.mom_s1[env] = s1; S.mom_s2[env] = s2;
+    int nl = S.tail_n[2 * env], nh = S.tail_n[2 * env + 1];
+    uint32_t fc = S.fast_cfg[env];
+    bool valid = nl >= 0;
+    M.ok = 0; M.c0 = c0; M.c1 = 0.0; M.c2 = 0.0;
+    if (valid) {
+        const float tl = S.tail_thr[4 * env], th = S.tail_thr[4 * env + 1], tl2 = S.tail_thr[4 * env + 2], th2 = S.tail_thr[4 * env + 3];
+        int al = S.agg_n[2 * env], ah = S.agg_n[2 * env + 1];
+        double al1 = S.agg_s[4 * env], al2 = S.agg_s[4 * env + 1], ah1 = S.agg_s[4 * env + 2], ah2 = S.agg_s[4 * env + 3];
+        const double lo = rq.lo64, hi = rq.hi64;
+        double c1 = 0.0, c2 = 0.0;
+        int err = 0;
+        tail_side(tail_ptr(S, env, 0), nl, al, al1, al2, true, tl, tl2, lo, c0, e, o, evict, c1, c2, valid, err);
+        tail_side(tail_ptr(S, env, 1), nh, ah, ah1, ah2, false, th, th2, hi, c0, e, o, evict, c1, c2, valid, err);
+        if (err) flag_error(S, env, err);
+        if (!valid) { nl = -1; nh = -1; }
+        S.tail_n[2 * env] = nl; S.tail_n[2 * env + 1] = nh;
+        S.agg_n[2 * env] = al; S.agg_n[2 * env + 1] = ah;
+        S.agg_s[4 * env] = al1; S.agg_s[4 * env + 1] = al2; S.agg_s[4 * env + 2] = ah1; S.agg_s[4 * env + 3] = ah2;
+        if (valid && (double)tl2 <= lo && lo <= (double)tl && (double)th <= hi && hi <= (double)th2) {
+            M.ok = 1; M.c1 = s1 + c1; M.c2 = s2 + c2;
+        }
+    }
+    // ---- what does this step need from the window? ----
+    const bool moments_needed = rq.n >= 2 && !rq.degenerate;
+    const bool lists = rq.rc[0] || rq.rc[1] || rq.dir[0] || rq.dir[1];
+    int retry = (int)((fc >> 8) & 0xffu);
+    rq.kind = SCAN_SKIP; rq.tails = 0; rq.tl = rq.tl2 = -SDC_INF_F; rq.th = rq.th2 = SDC_INF_F;
+    bool want_tails = false;
+    if (moments_needed && !M.ok) {
+        if (retry > 0) { retry -= 1; fc = (fc & ~0xff00u) | ((uint32_t)retry << 8); S.fast_cfg[env] = fc; }
+        else want_tails = true;
+    }
+    if (lists || want_tails) {
+        rq.kind = SCAN_REFRESH;
+        if (moments_needed && retry == 0) {
+            const int aexp = (int)(fc & 0xffu);
+            const double iqr4 = rq.hi64 - rq.lo64;              // = 4 (q3 - q1)
+            const double slack = ldexp(0.125 * iqr4, -aexp);    // half-width of the bands: alpha = 0.5 / 2^aexp of the IQR
+            float tl = (float)(rq.lo64 + slack), th = (float)(rq.hi64 - slack);
+            float tl2 = (float)(rq.lo64 - slack), th2 = (float)(rq.hi64 + slack);
+            if ((double)tl < rq.lo64) tl = nextafterf(tl, SDC_INF_F);
+            if ((double)th > rq.hi64) th = nextafterf(th, -SDC_INF_F);
+            if ((double)tl2 > rq.lo64) tl2 = nextafterf(tl2, -SDC_INF_F);
+            if ((double)th2 < rq.hi64) th2 = nextafterf(th2, SDC_INF_F);
+            rq.tails = (want_tails && nl >= 0) ? 2 : 1;         // 2: a fence left its (still valid) band
+            rq.tl = tl; rq.th = th; rq.tl2 = tl2; rq.th2 = th2;
+        }
+    } else if (moments_needed && !M.ok) {
+        rq.kind = SCAN_PLAIN;
+    }
+}
+
+// Raw output of a refresh pass over the window (the CUDA warp scan / the serial host scan fill this).
+struct RefreshRaw {
+    double s1, s2;          // exact unclipped sums about the new centre (ScanRequest::shift)
+    int n_tail[2];          // values inside the lower / upper band (may exceed kTailCap: then only the count is valid)
+    int agg_n[2]; double agg_s1[2], agg_s2[2];   // values beyond the outer thresholds: count and sums about the new centre
+    int c[2], below[2];     // per list: values inside [ca, cb] (may exceed kCollectCap), values below ca
+};
+
+// Turns the collected values into the env's new incremental state.  `sorted[j]`: the c[j] collected values of list j in
+// ascending order (valid when c[j] <= kCollectCap).  Lane-strided so that a warp can share the copying; all lanes get
+// the same return values.  On the host lane = 0, n_lanes = 1.
+SDC_HDN void refresh_commit(const State& S, int env, const ScanRequest& rq, const RefreshRaw& raw, const float* const* sorted,
+                            QView& Q, ScanResult& rs, int lane, int n_lanes) {
+    uint32_t fc = S.fast_cfg[env];
+    int aexp = (int)(fc & 0xffu), retry = (int)((fc >> 8) & 0xffu);
+    int wexp[2] = {(int)(int8_t)(fc >> 16), (int)(int8_t)(fc >> 24)};
+    rs.recentred = 0;
+    for (int j = 0; j < 2; ++j) {
+        rs.new_a[j] = Q.a[j]; rs.new_m[j] = Q.m[j];
+        if (!rq.rc[j]) continue;
+        const int n = rq.n, k = rq.k[j], c = raw.c[j], below = raw.below[j];
+        bool ok = false;
+        if (c > kCollectCap) {
+            if (wexp[j] > -kWexpMax) wexp[j] -= 1;                        // too wide for the scratch: halve next time
+        } else {
+            // The side that ran short tells which way the rank is drifting (a window in transition moves it steadily one
+            // way): give that side two thirds of the new list.
+            const int r_old = k - Q.a[j];
+            const bool short_hi = (Q.m[j] - 2 - r_old) < r_old;
+            int a_new = k - (short_hi ? kListCap / 3 : (2 * kListCap) / 3);
+            if (a_new < below) a_new = below;
+            int end = a_new + kListCap;
+            if (end > below + c) end = below + c;
+            if (end - a_new < kListCap) { a_new = end - kListCap; if (a_new < below) a_new = below; }
+            const int m_new = end - a_new, r = k - a_new;
+            if (r >= 0 && r + 1 < m_new) {
+                const int mlo = (a_new > 0) ? r : kListCap, mhi = (a_new + m_new < n) ? m_new - 2 - r : kListCap;
+                ok = mlo >= kRecentreOk && mhi >= kRecentreOk;
+            }
+            if (ok) {
+                for (int i = lane; i < m_new; i += n_lanes) Q.lst[j][i] = sorted[j][a_new - below + i];
+                rs.new_a[j] = a_new; rs.new_m[j] = m_new; rs.recentred |= 1 << j;
+            } else if (wexp[j] < kWexpMax) {
+                wexp[j] += 1;                                             // too narrow: double next time
+            }
+        }
+    }
+    if (rq.tails) {
+        const bool fits = raw.n_tail[0] <= kTailCap && raw.n_tail[1] <= kTailCap;
+        if (fits) {
+            const int big = raw.n_tail[0] > raw.n_tail[1] ? raw.n_tail[0] : raw.n_tail[1];
+            if (lane == 0) {
+                S.tail_n[2 * env] = raw.n_tail[0]; S.tail_n[2 * env + 1] = raw.n_tail[1];
+                S.tail_thr[4 * env] = rq.tl; S.tail_thr[4 * env + 1] = rq.th; S.tail_thr[4 * env + 2] = rq.tl2; S.tail_thr[4 * env + 3] = rq.th2;
+                S.agg_n[2 * env] = raw.agg_n[0]; S.agg_n[2 * env + 1] = raw.agg_n[1];
+                S.agg_s[4 * env] = raw.agg_s1[0]; S.agg_s[4 * env + 1] = raw.agg_s2[0];
+                S.agg_s[4 * env + 2] = raw.agg_s1[1]; S.agg_s[4 * env + 3] = raw.agg_s2[1];
+                S.mom_s1[env] = raw.s1; S.mom_s2[env] = raw.s2; S.mom_c0[env] = (double)rq.shift;
+            }
+            // band width policy: widen after a refresh that was forced by a fence leaving its band (rq.tails == 2),
+            // narrow when a band is more crowded than needed (the walk over the band is the per-step cost)
+            if (rq.tails == 2) { if (aexp > 0) aexp -= 1; }
+            else for (int b = big; b > kBandTarget && aexp < kAlphaOff; b >>= 1) aexp += 1;
+        } else {
+            if (lane == 0) { S.tail_n[2 * env] = -1; S.tail_n[2 * env + 1] = -1; }
+            if (aexp < kAlphaOff) aexp += 1;                             // dense around a fence: narrower bands
+            else retry = kTailRetry;                                     // hopeless (heavy ties at a fence): plain scans for a while
+        }
+    }
+    if (lane == 0)
+        S.fast_cfg[env] = (uint32_t)(aexp & 0xff) | ((uint32_t)(retry & 0xff) << 8) | ((uint32_t)(uint8_t)(int8_t)wexp[0] << 16) |
+                          ((uint32_t)(uint8_t)(int8_t)wexp[1] << 24);
+}
+
+// Applies the scan's results to the brackets (re-centred lists are taken over, the others extended by the one exact
+// rank the scan found) and turns the clipped moments into the three rewards.
+SDC_HDN void reward_finish(const State& S, int env, const ScanRequest& rq, const ScanResult& rs, const Moments& M,
+                           const RewardInputs& st, QView& Q, float* rew3) {
     int err = 0;
     const int n = rq.n;
-    for (int j = 0; j < 2; ++j) {
-        float* lst = Q.lst[j];
-        int a = Q.a[j], m = Q.m[j];
-        const int c = rs.cnt[j];
-        if (rq.dir[j] == SCAN_BELOW) {                           // rank a-1
-            if (c > a) err |= SDC_F_BRACKET;
-            const float v = (a > c) ? lst[0] : rs.ext[j];        // a tie copy of lst[0] sits below the list
-            if (m == kListCap) m -= 1;                           // drop the top (far side)
-            for (int i = m; i > 0; --i) lst[i] = lst[i - 1];
-            lst[0] = v; a -= 1; m += 1;
-        } else if (rq.dir[j] == SCAN_ABOVE) {                    // rank a+m
-            const int above = n - a - m;
-            if (c > above) err |= SDC_F_BRACKET;
-            const float v = (above > c) ? lst[m - 1] : rs.ext[j];
-            if (m == kListCap) { for (int i = 0; i + 1 < m; ++i) lst[i] = lst[i + 1]; m -= 1; a += 1; }
-            lst[m] = v; m += 1;
+    if (rq.kind == SCAN_REFRESH) {
+        for (int j = 0; j < 2; ++j) {
+            if (rs.recentred & (1 << j)) { Q.a[j] = rs.new_a[j]; Q.m[j] = rs.new_m[j]; continue; }
+            float* lst = Q.lst[j];
+            int a = Q.a[j], m = Q.m[j];
+            const int c = rs.cnt[j];
+            if (rq.dir[j] == SCAN_BELOW) {                           // rank a-1
+                if (c > a) err |= SDC_F_BRACKET;
+                const float v = (a > c) ? lst[0] : rs.ext[j];        // a tie copy of lst[0] sits below the list
+                if (m == kListCap) m -= 1;                           // drop the top (far side)
+                shift_up(lst, 0, m);
+                lst[0] = v; a -= 1; m += 1;
+            } else if (rq.dir[j] == SCAN_ABOVE) {                    // rank a+m
+                const int above = n - a - m;
+                if (c > above) err |= SDC_F_BRACKET;
+                const float v = (above > c) ? lst[m - 1] : rs.ext[j];
+                if (m == kListCap) { shift_down(lst, 0, m - 1); m -= 1; a += 1; }
+                lst[m] = v; m += 1;
+            }
+            Q.a[j] = a; Q.m[j] = m;
         }
-        Q.a[j] = a; Q.m[j] = m;
     }
     double z = 0.0;
     if (n >= 2) {
-        const double md = (double)rs.s1 / n;
-        double var = (double)rs.s2 / n - md * md;
-        double sd = (var > 0.0 && !rq.degenerate) ? sqrt(var) : 0.0;
-        const double mean = rq.degenerate ? rq.q1 : (double)rq.shift + md;
-        z = (st.energy - mean) / (sd > 0.0 ? sd : 1.0);
+        if (rq.degenerate) {
+            z = st.energy - rq.q1;                                   // every clipped value equals q1: std == 0 -> / 1
+        } else if (M.ok) {
+            const double md = M.c1 / n;
+            const double var = M.c2 / n - md * md;
+            const double sd = var > 0.0 ? sqrt(var) : 0.0;
+            z = (st.energy - (M.c0 + md)) / (sd > 0.0 ? sd : 1.0);
+        } else {
+            const double md = (double)rs.s1 / n;
+            const double var = (double)rs.s2 / n - md * md;
+            const double sd = var > 0.0 ? sqrt(var) : 0.0;
+            z = (st.energy - ((double)rq.shift + md)) / (sd > 0.0 ? sd : 1.0);
+        }
     }
     const double foot = -1.0 * (st.nci_next * z / 0.50);         // reward_creator.py:67-72
     double r_ls = foot + st.ls_penalty;
@@ -738,18 +1033,18 @@ struct StepArgs {
     const int32_t* actions; float* obs; float* share; float* rew; uint8_t* done; float* info; float* term_obs;
     // this step's counters (ctr) and the next step's (ctr_next, zeroed by this launch):
     //   [0] unit tickets  [1] finished envs appended to reset_list  [2] units past the scalar phase
-    //   [3] reset_list slots claimed by workers  [4] scan jobs published  [5] scan jobs claimed
+    //   [3] reset_list slots claimed by workers  [4..7] statistics: plain passes, refresh passes, by brackets, by tails
+    //   [8] envs appended to pre_list  [9] pre_list_prev entries claimed by workers
+    // three counter blocks rotate: the previous step's block (ctr_prev) still holds its pre_list count
     int32_t* ctr;
     int32_t* ctr_next;
+    const int32_t* ctr_prev;
     int32_t* reset_list;   // [N + slack], -1 = empty slot
-    float* reset_scratch;  // per-CTA scratch of the in-kernel reset workers
-    uint2* job_queue;      // [N][8]  (word, step tag): global queue of window-scan job records (env + parameters)
-    uint2* job_results;    // [N][8]  (word, step tag): scan results per env
+    int32_t* pre_list;     // [N] envs that finish two steps from now (filled by this launch)
+    const int32_t* pre_list_prev;   // the list the previous launch filled: episodes to pre-generate now
     double* metrics;
-    unsigned long long* phase_clocks;   // optional [8]: summed per-warp clock64 deltas of the k_step phases (diagnostics)
-    int32_t seq;           // step tag (never 0)
-    int32_t unit_envs, unroll, prefetch, blocks_per_sm;
-    int32_t local_jobs;    // envs of a unit scanned by the producing warp itself; the rest go to the global queue
+    unsigned long long* phase_clocks;   // optional [16]: summed per-warp clock64 deltas of the k_step phases (diagnostics)
+    int32_t unit_envs, unroll, blocks_per_sm;
 };
 
 // HARL shared observation (harl/envs/sustaindc/harlsustaindc_env.py:78-85): ls[0:26] | dc[11] | dc[13] |

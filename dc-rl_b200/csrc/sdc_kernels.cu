@@ -1,21 +1,20 @@
 // sdc_kernels.cu -- CUDA (sm_100a) backend of libsdc_b200.so.
 //
 // Kernels
-//   k_step    one launch per env-step for all N envs.  A warp takes a unit of U consecutive envs:
-//             phase A  one lane per env: load-shifting queue, IT/HVAC model, battery, trace gathers,
-//                      observations, info row, append of the step energy to the reward window and O(1)
-//                      update of the rolling quartile brackets (sdc_core.h, fp64 like the reference);
-//             phase B  the whole warp streams each env's fp32 reward window (40 KB at steady state, the
-//                      dominant HBM traffic) once with 128-bit loads and warp-shuffle reductions: clipped
-//                      moments, plus the next rank of a bracket side that runs short;
-//             phase C  one lane per env: z-score -> three rewards, bracket extension, metrics.
-//             Observation rows are staged in shared memory and written as one contiguous tile per unit.
-//   k_reset   one CTA per finished env: start day/hour, year-long weather random walk (Philox), day roll,
+//   k_step    one launch per env-step for all N envs.  A warp takes a unit of U consecutive envs, one lane per env:
+//             load-shifting queue, IT/HVAC model, battery, trace gathers, observations, info row (sdc_core.h, fp64
+//             like the reference), then the reward normaliser INCREMENTALLY: window append, exact rolling quartile
+//             brackets, fp64 window moments, tail multisets beyond the IQR fences -> clipped mean / std without
+//             touching the 40 KB window.  Only an env whose incremental state ran out of slack (a few per thousand
+//             env-steps) has its fp32 window streamed once by the whole warp (128-bit loads, warp-shuffle reductions,
+//             ballot compaction into the tail sets / a shared-memory scratch that is bitonic-sorted) -- "refresh".
+//             CTAs without units (and every CTA once the units are gone) serve as episode-reset workers.
+//   k_reset   explicit resets, one CTA per env: start day/hour, year-long weather random walk (Philox), day roll,
 //             clip, 30-day normalisation, queue clear, reset observation (or copies a staged episode).
 //   k_rebuild one CTA per env: full bitonic sort of the window in shared memory -> fresh brackets.
 //   k_build_reset_list  mask -> env list.
 //
-// No tensor cores: there is no dense contraction on this path (HBM-bound streaming + scalar physics).
+// No tensor cores: there is no dense contraction on this path (per-env scalar state machines + streaming passes).
 #include <cuda_runtime.h>
 
 #include "sdc_core.h"
@@ -70,7 +69,6 @@ static const char* event_elapsed_ms(Context&, void* a, void* b, double* ms) {
     float f = 0.f; CU(cudaEventElapsedTime(&f, (cudaEvent_t)a, (cudaEvent_t)b)); *ms = f; return nullptr;
 }
 static void event_destroy(Context&, void* ev) { cudaEventDestroy((cudaEvent_t)ev); }
-static size_t reset_scratch_floats(Context&) { return 4; }      // the reset workers need no global scratch any more
 static const char* dev_fill_bytes(Context&, void* p, int v, size_t bytes) { CU(cudaMemset(p, v, bytes)); return nullptr; }
 static const char* sync(Context& c) { CU(cudaSetDevice(c.device)); CU(cudaDeviceSynchronize()); return nullptr; }
 
@@ -80,7 +78,7 @@ static const char* sync(Context& c) { CU(cudaSetDevice(c.device)); CU(cudaDevice
 constexpr int kStepThreads = 256;
 constexpr int kWarpsPerBlock = kStepThreads / 32;
 constexpr int kObsRow = 3 * SDC_OBS_DIM;          // 78 floats per env
-constexpr int kListRow = 2 * sdc::kListCap + 4;   // both quartile lists of an env; 16-byte aligned rows for cp.async
+constexpr int kTileStride = kObsRow + 1;          // odd row stride of the shared-memory observation tile
 constexpr int kTableBytes = 8192;                 // shared-memory copy of the location / dc parameter tables
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -118,7 +116,9 @@ __device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("pre
 
 // Issues, up front and all at once, the second-level (address-dependent) reads of one env-step so that their
 // DRAM latencies overlap instead of being paid one after another inside the scalar phase.
-__device__ __forceinline__ void prefetch_env(const sdc::State& S, const sdc::Tables& T, int env) {
+// Called by the whole warp (`active` lanes own an env).
+__device__ __forceinline__ void prefetch_env(const sdc::State& S, const sdc::Tables& T, int env, bool active) {
+    if (!active) env = 0;
     const int t = S.t[env], t0 = S.t0[env], head = S.ls_head[env], hh = S.hist_head[env];
     const sdc::LocTables& L = T.loc[S.loc_id[env]];
     const double* wt = S.weather + (size_t)env * 2 * S.win_len + (t - t0);
@@ -130,25 +130,27 @@ __device__ __forceinline__ void prefetch_env(const sdc::State& S, const sdc::Tab
     prefetch_line(S.hist + (size_t)env * S.hist_cap + hh);
     prefetch_line(L.ci + t - 16); prefetch_line(L.ci + t); prefetch_line(L.ci + t + 9);
     prefetch_line(L.workload + t); prefetch_line(L.ns + t); prefetch_line(L.sh + t);
+    // reward normaliser: the bracket positions it will look at and the rows of the two tail bands
+    const int2 qa = reinterpret_cast<const int2*>(S.q_a)[env], qm = reinterpret_cast<const int2*>(S.q_m)[env];
+    const int2 tn = reinterpret_cast<const int2*>(S.tail_n)[env];
+    const int n_after = min(S.hist_len[env] + 1, S.hist_cap);
+    const float* l0 = S.qlist + (size_t)env * 2 * sdc::kListCap;
+    prefetch_line(l0); prefetch_line(l0 + max(qm.x - 1, 0)); prefetch_line(l0 + min(max((n_after - 1) / 4 - qa.x, 0), sdc::kListCap - 1));
+    const float* l1 = l0 + sdc::kListCap;
+    prefetch_line(l1); prefetch_line(l1 + max(qm.y - 1, 0)); prefetch_line(l1 + min(max((3 * (n_after - 1)) / 4 - qa.y, 0), sdc::kListCap - 1));
+    prefetch_line(S.agg_s + 4 * (size_t)env); prefetch_line(S.tail_thr + 4 * (size_t)env);
+    const int lane = threadIdx.x & 31;
+    int rows_lo = active ? tn.x : 0, rows_hi = active ? tn.y : 0;   // lane j fetches rows j, j+32, ... of the unit's interleaved band arrays
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        rows_lo = max(rows_lo, __shfl_xor_sync(0xffffffffu, rows_lo, o));
+        rows_hi = max(rows_hi, __shfl_xor_sync(0xffffffffu, rows_hi, o));
+    }
+    const float* band = S.tails + (size_t)(env >> 5) * 2 * sdc::kTailCap * sdc::kTailStride;
+    for (int r = lane; r < rows_lo; r += 32) prefetch_line(band + (size_t)r * sdc::kTailStride);
+    for (int r = lane; r < rows_hi; r += 32) prefetch_line(band + (size_t)(sdc::kTailCap + r) * sdc::kTailStride);
 }
 
-// Observation rows written straight to the output tensors: obs[env][3][26], the HARL shared observation
-// (ls[0:26] | dc[11] | dc[13] | padded battery row [25], harlsustaindc_env.py:78-85) and, for finished envs, term_obs.
-struct GlobalObsSink {
-    float* obs; float* share; float* term;
-    __device__ __forceinline__ void operator()(int agent, int idx, float v) {
-#ifdef SDC_EXPERIMENT_NO_OBS_STORES
-        if (v == 123.456f) obs[0] = v;
-        return;
-#endif
-        obs[agent * SDC_OBS_DIM + idx] = v;
-        if (term) term[agent * SDC_OBS_DIM + idx] = v;
-        if (agent == 0) share[idx] = v;
-        else if (agent == 1 && idx == 11) share[26] = v;
-        else if (agent == 1 && idx == 13) share[27] = v;
-        else if (agent == 2 && idx == 25) share[28] = v;
-    }
-};
 struct GlobalInfoSink {
     float* info; int n, env;
     __device__ __forceinline__ void operator()(int col, float v) { if (info) info[(size_t)col * n + env] = v; }
@@ -170,90 +172,193 @@ __device__ __forceinline__ float ld_stream(const float* p) {
     return v;
 }
 
-// ---- phase B: one warp streams one env's window -------------------------------------------------
-template <int D>
-__device__ __forceinline__ void track(int& cnt, float& ext, float x, float thr) {
-    if (D == sdc::SCAN_BELOW) { const bool b = x < thr; cnt += b; ext = fmaxf(ext, b ? x : -SDC_INF_F); }
-    if (D == sdc::SCAN_ABOVE) { const bool b = x > thr; cnt += b; ext = fminf(ext, b ? x : SDC_INF_F); }
-}
-
-template <int D0, int D1>
-struct Acc {
-    float s1[4], s2[4];
-    int cnt[2];
-    float ext[2];
-    float lo, hi, shift, thr0, thr1;
-    __device__ __forceinline__ void one(int k, float x) {
-        const float c = fminf(fmaxf(x, lo), hi);
-        const float d = c - shift;
-        s1[k] += d;
-        s2[k] = fmaf(d, d, s2[k]);
-        track<D0>(cnt[0], ext[0], x, thr0);
-        track<D1>(cnt[1], ext[1], x, thr1);
-    }
-    __device__ __forceinline__ void four(const float4& v) { one(0, v.x); one(1, v.y); one(2, v.z); one(3, v.w); }
+// ---- window pass: the whole CTA processes one env's window, staged in shared memory by the TMA engine -------
+// Parameters and results of the pass in flight (one at a time per CTA).
+struct PassJob {
+    // request (written by the lane that owns the env)
+    int env, n, kind;
+    float lo, hi, shift, tl, th, tl2, th2;
+    int dir[2]; float thr[2];
+    int rc[2], k[2]; float ca[2], cb[2];
+    int tails, degenerate;
+    int q_a[2], q_m[2];
+    // results (written by warp 0)
+    sdc::ScanResult rs;
+};
+struct PassShared {
+    unsigned long long bar;                 // mbarrier of the bulk copy
+    PassJob job;
+    int fill[4];                            // slots handed out: lower band, upper band, collect list 0, collect list 1
+    float red_f[kWarpsPerBlock][4];         // s1, s2, ext0, ext1
+    double red_d[kWarpsPerBlock][6];        // S1, S2, far sums
+    int red_i[kWarpsPerBlock][6];           // cnt0, cnt1, below0, below1, far counts
+    unsigned slow[kWarpsPerBlock];          // lanes of each warp that asked for a pass this round
 };
 
-template <int D0, int D1, int UNROLL>
-__device__ __forceinline__ void scan_window(const float* h, int n, float lo, float hi, float shift, float thr0, float thr1,
-                                            int lane, sdc::ScanResult& rs) {
-    Acc<D0, D1> A;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { A.s1[k] = 0.f; A.s2[k] = 0.f; }
-    A.cnt[0] = A.cnt[1] = 0;
-    A.ext[0] = D0 == sdc::SCAN_ABOVE ? SDC_INF_F : -SDC_INF_F;
-    A.ext[1] = D1 == sdc::SCAN_ABOVE ? SDC_INF_F : -SDC_INF_F;
-    A.lo = lo; A.hi = hi; A.shift = shift; A.thr0 = thr0; A.thr1 = thr1;
-    const float4* p = reinterpret_cast<const float4*>(h);
-    const int n4 = n >> 2;
-    // Full batches of UNROLL rows (UNROLL x 512 B per warp in flight).  Deeper per-warp queues (double buffering,
-    // UNROLL 16, bulk L2 prefetch) were measured SLOWER on B200: with ~2 400 independent 40 KB streams more
-    // outstanding requests only add DRAM row conflicts (profiles/r01_summary.md).
-    int c = lane;
-    const int nb = n4 / (UNROLL * 32);               // warp-uniform trip count (the fence below is a warp barrier)
-    for (int b = 0; b < nb; ++b, c += UNROLL * 32) {
-        float4 v[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) v[u] = ld_stream(p + c + u * 32);
-        __syncwarp();            // scheduling fence: ptxas must issue the whole batch before the first use (see scan_job)
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) A.four(v[u]);
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
     }
-    for (; c + 3 * 32 < n4; c += 4 * 32) {           // tail: groups of four rows, then single rows
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld_stream(p + c + u * 32);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) A.four(v[u]);
-    }
-    for (; c < n4; c += 32) A.four(ld_stream(p + c));
-    const int rem = n & 3;
-    if (lane < rem) A.one(0, ld_stream(h + (n4 << 2) + lane));
-    rs.s1 = warp_sum((A.s1[0] + A.s1[1]) + (A.s1[2] + A.s1[3]));
-    rs.s2 = warp_sum((A.s2[0] + A.s2[1]) + (A.s2[2] + A.s2[3]));
-    rs.cnt[0] = D0 ? warp_sum(A.cnt[0]) : 0;
-    rs.cnt[1] = D1 ? warp_sum(A.cnt[1]) : 0;
-    rs.ext[0] = D0 == sdc::SCAN_BELOW ? warp_max(A.ext[0]) : (D0 == sdc::SCAN_ABOVE ? warp_min(A.ext[0]) : 0.f);
-    rs.ext[1] = D1 == sdc::SCAN_BELOW ? warp_max(A.ext[1]) : (D1 == sdc::SCAN_ABOVE ? warp_min(A.ext[1]) : 0.f);
+}
+// One thread: global -> shared bulk copy by the TMA engine (UBLKCP), completion counted in bytes on the mbarrier.
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int UNROLL>
-// Inlined on purpose: results and parameters stay in registers.  Anything that goes through local memory in the
-// per-job path (a by-reference result struct, a State copy made for a non-inlined callee) misses the small L1 most of
-// the time and then costs a ~1.5 us round trip while HBM is saturated -- measured: +50 % per window scan.
-__device__ __forceinline__ void scan_dispatch(const float* h, int n, float lo, float hi, float shift, int d0, int d1, float t0, float t1,
-                                           int lane, sdc::ScanResult& rs) {
-    switch (d0 * 3 + d1) {
-        case 0: scan_window<0, 0, UNROLL>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
-        case 1: scan_window<0, 1, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
-        case 2: scan_window<0, 2, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
-        case 3: scan_window<1, 0, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
-        case 4: scan_window<1, 1, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
-        case 5: scan_window<1, 2, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
-        case 6: scan_window<2, 0, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
-        case 7: scan_window<2, 1, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
-        default: scan_window<2, 2, 8>(h, n, lo, hi, shift, t0, t1, lane, rs); break;
+// CTA-wide bitonic sort of buf[0..p2) (ascending), p2 a power of two <= 2 * blockDim.x.
+__device__ __forceinline__ void block_bitonic_sort(float* buf, int p2) {
+    for (int k = 2; k <= p2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < p2; i += kStepThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const float x = buf[i], y = buf[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { buf[i] = y; buf[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
     }
+}
+
+// The pass itself (sdc_core.h, "reward normaliser").  SCAN_PLAIN: clipped moments of this step only.  SCAN_REFRESH:
+// additionally the exact unclipped moments about the new centre, the values of the two tail bands (straight into the
+// env's band arrays) with the far-tail aggregates, all values inside the re-centring intervals of the brackets (into
+// `scr`, then sorted) and the single-rank fallback -- then warp 0 commits the env's new incremental state.
+// `win` = hist_cap floats of shared memory.  Called by all threads of the CTA; `phase` = parity of the mbarrier.
+__device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, float* win, float* scr, unsigned phase) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const PassJob& J = ps.job;
+    const int n = J.n, env = J.env;
+    const bool refresh = J.kind == sdc::SCAN_REFRESH;
+    if (tid == 0) {
+        const unsigned bytes = ((unsigned)n * 4u + 15u) & ~15u;          // rows are 16-byte multiples (hist_cap % 4 == 0)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of `win` are done
+        mbar_expect_tx(&ps.bar, bytes);
+        tma_load_1d(win, S.hist + (size_t)env * S.hist_cap, bytes, &ps.bar);
+    }
+    if (tid < 4) ps.fill[tid] = 0;
+    const float lo = J.lo, hi = J.hi, shift = J.shift;
+    const float tl = J.tl, th = J.th, tl2 = J.tl2, th2 = J.th2;
+    const int dir0 = J.dir[0], dir1 = J.dir[1];
+    const float thr0 = J.thr[0], thr1 = J.thr[1];
+    const float ca0 = (refresh && J.rc[0]) ? J.ca[0] : SDC_INF_F, cb0 = (refresh && J.rc[0]) ? J.cb[0] : -SDC_INF_F;   // empty when not re-centring
+    const float ca1 = (refresh && J.rc[1]) ? J.ca[1] : SDC_INF_F, cb1 = (refresh && J.rc[1]) ? J.cb[1] : -SDC_INF_F;
+    const float quiet_lo = refresh ? fmaxf(tl, fmaxf(dir0 == sdc::SCAN_BELOW ? thr0 : -SDC_INF_F, dir1 == sdc::SCAN_BELOW ? thr1 : -SDC_INF_F)) : -SDC_INF_F;
+    const float quiet_hi = refresh ? fminf(th, fminf(dir0 == sdc::SCAN_ABOVE ? thr0 : SDC_INF_F, dir1 == sdc::SCAN_ABOVE ? thr1 : SDC_INF_F)) : SDC_INF_F;
+    float* tail_lo = sdc::tail_ptr(S, env, 0);
+    float* tail_hi = sdc::tail_ptr(S, env, 1);
+    float s1 = 0.f, s2 = 0.f;
+    double S1 = 0.0, S2 = 0.0;
+    const double c0 = (double)shift;
+    int cnt0 = 0, cnt1 = 0, below0 = 0, below1 = 0, far_n0 = 0, far_n1 = 0;
+    float ext0 = dir0 == sdc::SCAN_ABOVE ? SDC_INF_F : -SDC_INF_F, ext1 = dir1 == sdc::SCAN_ABOVE ? SDC_INF_F : -SDC_INF_F;
+    double far_a0 = 0.0, far_b0 = 0.0, far_a1 = 0.0, far_b1 = 0.0;
+    __syncthreads();                                                     // fill[] zeroed
+    mbar_wait(&ps.bar, phase);                                           // the window is in shared memory
+    // Per value: accumulate + one combined "is it interesting" test; the rare hits (a few hundred of 10 000) take the
+    // slow path, where shared-memory atomics hand out the slots (the sets are unordered).  Conflict-free LDS.
+#pragma unroll 4
+    for (int i = tid; i < n; i += kStepThreads) {
+        const float x = win[i];
+        const float d = fminf(fmaxf(x, lo), hi) - shift;
+        s1 += d; s2 = fmaf(d, d, s2);
+        const double y = (double)x - c0;
+        if (refresh) { S1 += y; S2 = fma(y, y, S2); }
+        below0 += x < ca0; below1 += x < ca1;
+        if (x < quiet_lo || x > quiet_hi || (x >= ca0 && x <= cb0) || (x >= ca1 && x <= cb1)) {
+            if (dir0 == sdc::SCAN_BELOW && x < thr0) { cnt0 += 1; ext0 = fmaxf(ext0, x); }
+            if (dir0 == sdc::SCAN_ABOVE && x > thr0) { cnt0 += 1; ext0 = fminf(ext0, x); }
+            if (dir1 == sdc::SCAN_BELOW && x < thr1) { cnt1 += 1; ext1 = fmaxf(ext1, x); }
+            if (dir1 == sdc::SCAN_ABOVE && x > thr1) { cnt1 += 1; ext1 = fminf(ext1, x); }
+            if (x < tl2) { far_n0 += 1; far_a0 += y; far_b0 = fma(y, y, far_b0); }
+            else if (x < tl) { const int pos = atomicAdd(&ps.fill[0], 1); if (pos < sdc::kTailCap) tail_lo[(size_t)pos * sdc::kTailStride] = x; }
+            if (x > th2) { far_n1 += 1; far_a1 += y; far_b1 = fma(y, y, far_b1); }
+            else if (x > th) { const int pos = atomicAdd(&ps.fill[1], 1); if (pos < sdc::kTailCap) tail_hi[(size_t)pos * sdc::kTailStride] = x; }
+            if (x >= ca0 && x <= cb0) { const int pos = atomicAdd(&ps.fill[2], 1); if (pos < sdc::kCollectCap) scr[pos] = x; }
+            if (x >= ca1 && x <= cb1) { const int pos = atomicAdd(&ps.fill[3], 1); if (pos < sdc::kCollectCap) scr[sdc::kCollectCap + pos] = x; }
+        }
+    }
+    // ---- block reduction: warp shuffles, then the per-warp partials through shared memory ----
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (refresh) {
+        S1 = warp_sum(S1); S2 = warp_sum(S2);
+        cnt0 = warp_sum(cnt0); cnt1 = warp_sum(cnt1); below0 = warp_sum(below0); below1 = warp_sum(below1);
+        far_n0 = warp_sum(far_n0); far_n1 = warp_sum(far_n1);
+        far_a0 = warp_sum(far_a0); far_b0 = warp_sum(far_b0); far_a1 = warp_sum(far_a1); far_b1 = warp_sum(far_b1);
+        ext0 = dir0 == sdc::SCAN_BELOW ? warp_max(ext0) : warp_min(ext0);
+        ext1 = dir1 == sdc::SCAN_BELOW ? warp_max(ext1) : warp_min(ext1);
+    }
+    if (lane == 0) {
+        ps.red_f[warp][0] = s1; ps.red_f[warp][1] = s2; ps.red_f[warp][2] = ext0; ps.red_f[warp][3] = ext1;
+        ps.red_d[warp][0] = S1; ps.red_d[warp][1] = S2; ps.red_d[warp][2] = far_a0; ps.red_d[warp][3] = far_b0;
+        ps.red_d[warp][4] = far_a1; ps.red_d[warp][5] = far_b1;
+        ps.red_i[warp][0] = cnt0; ps.red_i[warp][1] = cnt1; ps.red_i[warp][2] = below0; ps.red_i[warp][3] = below1;
+        ps.red_i[warp][4] = far_n0; ps.red_i[warp][5] = far_n1;
+    }
+    __syncthreads();                                                     // partials + all band / collect stores visible
+    sdc::RefreshRaw raw;
+    sdc::ScanResult rs;
+    {
+        float f[4] = {0.f, 0.f, ps.red_f[0][2], ps.red_f[0][3]};
+        double d[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        int c[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; ++w) {
+            f[0] += ps.red_f[w][0]; f[1] += ps.red_f[w][1];
+            f[2] = dir0 == sdc::SCAN_BELOW ? fmaxf(f[2], ps.red_f[w][2]) : fminf(f[2], ps.red_f[w][2]);
+            f[3] = dir1 == sdc::SCAN_BELOW ? fmaxf(f[3], ps.red_f[w][3]) : fminf(f[3], ps.red_f[w][3]);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { d[q] += ps.red_d[w][q]; c[q] += ps.red_i[w][q]; }
+        }
+        rs.s1 = f[0]; rs.s2 = f[1];
+        rs.ext[0] = dir0 == sdc::SCAN_NONE ? 0.f : f[2]; rs.ext[1] = dir1 == sdc::SCAN_NONE ? 0.f : f[3];
+        rs.cnt[0] = c[0]; rs.cnt[1] = c[1]; rs.recentred = 0;
+        rs.new_a[0] = J.q_a[0]; rs.new_a[1] = J.q_a[1]; rs.new_m[0] = J.q_m[0]; rs.new_m[1] = J.q_m[1];
+        raw.s1 = d[0]; raw.s2 = d[1];
+        raw.below[0] = c[2]; raw.below[1] = c[3];
+        raw.agg_n[0] = c[4]; raw.agg_n[1] = c[5];
+        raw.agg_s1[0] = d[2]; raw.agg_s2[0] = d[3]; raw.agg_s1[1] = d[4]; raw.agg_s2[1] = d[5];
+        raw.n_tail[0] = ps.fill[0]; raw.n_tail[1] = ps.fill[1]; raw.c[0] = ps.fill[2]; raw.c[1] = ps.fill[3];
+    }
+    if (refresh) {
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {                                    // uniform across the CTA
+            const int c = raw.c[j];
+            if (c > 1 && c <= sdc::kCollectCap) {
+                int p2 = 2;
+                while (p2 < c) p2 <<= 1;
+                float* buf = scr + j * sdc::kCollectCap;
+                for (int i = c + tid; i < p2; i += kStepThreads) buf[i] = SDC_INF_F;
+                __syncthreads();
+                block_bitonic_sort(buf, p2);
+            }
+        }
+        if (warp == 0) {
+            sdc::ScanRequest rl;
+            rl.n = n; rl.kind = J.kind; rl.shift = shift; rl.tl = tl; rl.th = th; rl.tl2 = tl2; rl.th2 = th2;
+            rl.rc[0] = J.rc[0]; rl.rc[1] = J.rc[1]; rl.k[0] = J.k[0]; rl.k[1] = J.k[1];
+            rl.tails = J.tails; rl.degenerate = J.degenerate;
+            sdc::QView Ql;
+            Ql.lst[0] = S.qlist + (size_t)env * 2 * sdc::kListCap; Ql.lst[1] = Ql.lst[0] + sdc::kListCap;
+            Ql.a[0] = J.q_a[0]; Ql.a[1] = J.q_a[1]; Ql.m[0] = J.q_m[0]; Ql.m[1] = J.q_m[1];
+            const float* sorted[2] = {scr, scr + sdc::kCollectCap};
+            sdc::refresh_commit(S, env, rl, raw, sorted, Ql, rs, lane, 32);
+        }
+    }
+    if (tid == 0) ps.job.rs = rs;
+    __syncthreads();                                                     // results visible; `win`, `scr`, partials free again
 }
 
 // =================================================================================================
@@ -308,77 +413,102 @@ constexpr int kNormWindow = 2880;                 // 30 days of quarter-hours (u
 // values that land in the 30-day window after the start are kept (in shared memory).  The emit pass then runs over
 // window positions, so its trace reads are coalesced and independent.  No global scratch: a dependent global access
 // costs ~2 us while the other CTAs saturate HBM with window scans.
-__device__ __forceinline__ void reset_one_env(const sdc::State& S, int env, float* obs, float* share, double* runbuf, ResetShared& sh) {
+// Generates the next episode of `env` (start day / hour, realised weather window, 30-day temperature range) from the
+// env's counter-based RNG stream into (wt, ww, *tmin_out, *tmax_out, sh.start).  All threads of the CTA.
+__device__ __forceinline__ void generate_episode(const sdc::State& S, int env, double* wt, double* ww, double* tmin_out, double* tmax_out,
+                                                 double* runbuf, ResetShared& sh) {
     const int tid = threadIdx.x;
     const int n = SDC_YEAR_STEPS;
+    const uint32_t ep = S.episode[env];
+    const uint64_t seed = S.seed[env];
+    __syncthreads();
+    if (tid == 0) sdc::draw_episode_start(seed, ep, S.day_lo[env], S.day_hi[env], &sh.start[0], &sh.start[1], &sh.start[2]);
+    __syncthreads();
+    const int t0 = sh.start[0] * 96 + sh.start[1] * 4, roll = sh.start[2];
+    const int k_max = min(kNormWindow, n - t0);            // the reference's slice is truncated at the year end
+    // pass 1: this thread's segment of the walk (utils/managers.py:45-46)
+    double run = 0.0, sum_run = 0.0, sum_run2 = 0.0;
+    int cnt = 0;
+    for (int q = 0; q < sdc::kNoiseSeg / 4; ++q) {
+        float z[4];
+        const int j0 = tid * sdc::kNoiseSeg + q * 4;
+        sdc::noise_normals4(seed, ep, (uint32_t)(j0 >> 2), z);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u;
+            if (j < n) {
+                run += (double)(0.02f * z[u]);
+                sum_run += run; sum_run2 += run * run; cnt += 1;
+                int t = j + 96 * roll; if (t >= n) t -= n;
+                const int k = t - t0;
+                if (k >= 0 && k < k_max) runbuf[k] = run;
+            }
+        }
+    }
+    sh.seg_off[tid] = run;
+    __syncthreads();
+    if (tid == 0) {                           // serial exclusive prefix, same order as the host statement
+        double acc = 0.0;
+        for (int k = 0; k < kResetThreads; ++k) { const double s = sh.seg_off[k]; sh.seg_off[k] = acc; acc += s; }
+    }
+    __syncthreads();
+    const double off = sh.seg_off[tid];
+    // walk_j = off + run_j  ->  sums of w and w^2 from the partial sums
+    const double sw = block_sum(cnt * off + sum_run, sh.red);
+    const double sw2 = block_sum(cnt * off * off + 2.0 * off * sum_run + sum_run2, sh.red);
+    const double mean = sw / n;
+    const double scale = 0.75 / sqrt(sw2 / n - mean * mean);              // managers.py:46-48
+    // emit: roll, clip, window, 30-day min/max (managers.py:598-608), one window position per thread and trip
+    const sdc::LocTables& L = S.loc[S.loc_id[env]];
+    double tmin = INFINITY, tmax = -INFINITY;
+    for (int k = tid; k < max(k_max, S.win_len); k += kResetThreads) {
+        if (k < k_max) {
+            int j = t0 + k - 96 * roll; if (j < 0) j += n;
+            const double noise = (sh.seg_off[j / sdc::kNoiseSeg] + runbuf[k]) * scale;
+            const double vt = fmin(fmax(L.temp_base[j] + noise, 0.0), 45.0);
+            tmin = fmin(tmin, vt); tmax = fmax(tmax, vt);
+            if (k < S.win_len) { wt[k] = vt; ww[k] = fmin(fmax(L.wetb_base[j] + noise, 0.0), 45.0); }
+        } else if (k < S.win_len) {
+            wt[k] = 0.0; ww[k] = 0.0;                                      // beyond the year end (flagged domain)
+        }
+    }
+    tmin = block_minmax(tmin, true, sh.red);
+    tmax = block_minmax(tmax, false, sh.red);
+    if (tid == 0) { *tmin_out = tmin; *tmax_out = tmax; }
+}
+
+// Look-ahead: an env that will finish two steps from now gets its next episode generated into the staging buffers
+// (the ones sdc_stage_episode fills in replay mode) while the other CTAs step, so that the reset itself is a copy.
+__device__ __forceinline__ void pregen_one_env(const sdc::State& S, int env, double* runbuf, ResetShared& sh) {
+    if (S.pend_valid[env]) return;                      // uniform: a host-staged (or already generated) episode is waiting
+    double* wt = S.pend_weather + (size_t)env * 2 * S.win_len;
+    generate_episode(S, env, wt, wt + S.win_len, S.pend_tmin + env, S.pend_tmax + env, runbuf, sh);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        S.pend_day[env] = sh.start[0]; S.pend_hour[env] = sh.start[1];
+        __threadfence();
+        S.pend_valid[env] = 1;
+    }
+}
+
+// Episode reset of one env by one CTA.  `runbuf` = kNormWindow doubles of shared memory.
+__device__ __forceinline__ void reset_one_env(const sdc::State& S, int env, float* obs, float* share, double* runbuf, ResetShared& sh) {
+    const int tid = threadIdx.x;
     double* wt = S.weather + (size_t)env * 2 * S.win_len;
     double* ww = wt + S.win_len;
-    const bool staged = S.pend_valid && S.pend_valid[env];
+    const bool staged = S.pend_valid[env] != 0;
     __syncthreads();
     if (staged) {
         if (tid == 0) { sh.start[0] = S.pend_day[env]; sh.start[1] = S.pend_hour[env]; sh.start[2] = 0; }
-        const double* src = S.pend_weather + (size_t)env * 2 * S.win_len;
-        for (int k = tid; k < 2 * S.win_len; k += kResetThreads) wt[k] = src[k];
+        const double2* src = reinterpret_cast<const double2*>(S.pend_weather + (size_t)env * 2 * S.win_len);
+        double2* dst = reinterpret_cast<double2*>(wt);                    // win_len is even, rows are 16-byte aligned
+        for (int k = tid; k < S.win_len; k += kResetThreads) dst[k] = src[k];
         if (tid == 0) { S.t_min[env] = S.pend_tmin[env]; S.t_max[env] = S.pend_tmax[env]; }
     } else {
-        const uint32_t ep = S.episode[env];
-        const uint64_t seed = S.seed[env];
-        if (tid == 0) sdc::draw_episode_start(seed, ep, S.day_lo[env], S.day_hi[env], &sh.start[0], &sh.start[1], &sh.start[2]);
-        __syncthreads();
-        const int t0 = sh.start[0] * 96 + sh.start[1] * 4, roll = sh.start[2];
-        const int k_max = min(kNormWindow, n - t0);            // the reference's slice is truncated at the year end
-        // pass 1: this thread's segment of the walk (utils/managers.py:45-46)
-        double run = 0.0, sum_run = 0.0, sum_run2 = 0.0;
-        int cnt = 0;
-        for (int q = 0; q < sdc::kNoiseSeg / 4; ++q) {
-            float z[4];
-            const int j0 = tid * sdc::kNoiseSeg + q * 4;
-            sdc::noise_normals4(seed, ep, (uint32_t)(j0 >> 2), z);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = j0 + u;
-                if (j < n) {
-                    run += (double)(0.02f * z[u]);
-                    sum_run += run; sum_run2 += run * run; cnt += 1;
-                    int t = j + 96 * roll; if (t >= n) t -= n;
-                    const int k = t - t0;
-                    if (k >= 0 && k < k_max) runbuf[k] = run;
-                }
-            }
-        }
-        sh.seg_off[tid] = run;
-        __syncthreads();
-        if (tid == 0) {                           // serial exclusive prefix, same order as the host statement
-            double acc = 0.0;
-            for (int k = 0; k < kResetThreads; ++k) { const double s = sh.seg_off[k]; sh.seg_off[k] = acc; acc += s; }
-        }
-        __syncthreads();
-        const double off = sh.seg_off[tid];
-        // walk_j = off + run_j  ->  sums of w and w^2 from the partial sums
-        const double sw = block_sum(cnt * off + sum_run, sh.red);
-        const double sw2 = block_sum(cnt * off * off + 2.0 * off * sum_run + sum_run2, sh.red);
-        const double mean = sw / n;
-        const double scale = 0.75 / sqrt(sw2 / n - mean * mean);              // managers.py:46-48
-        // emit: roll, clip, window, 30-day min/max (managers.py:598-608), one window position per thread and trip
-        const sdc::LocTables& L = S.loc[S.loc_id[env]];
-        double tmin = INFINITY, tmax = -INFINITY;
-        for (int k = tid; k < max(k_max, S.win_len); k += kResetThreads) {
-            if (k < k_max) {
-                int j = t0 + k - 96 * roll; if (j < 0) j += n;
-                const double noise = (sh.seg_off[j / sdc::kNoiseSeg] + runbuf[k]) * scale;
-                const double vt = fmin(fmax(L.temp_base[j] + noise, 0.0), 45.0);
-                tmin = fmin(tmin, vt); tmax = fmax(tmax, vt);
-                if (k < S.win_len) { wt[k] = vt; ww[k] = fmin(fmax(L.wetb_base[j] + noise, 0.0), 45.0); }
-            } else if (k < S.win_len) {
-                wt[k] = 0.0; ww[k] = 0.0;                                      // beyond the year end (flagged domain)
-            }
-        }
-        tmin = block_minmax(tmin, true, sh.red);
-        tmax = block_minmax(tmax, false, sh.red);
-        if (tid == 0) { S.t_min[env] = tmin; S.t_max[env] = tmax; }
+        generate_episode(S, env, wt, ww, S.t_min + env, S.t_max + env, runbuf, sh);
     }
-    uint8_t* ring = S.ls_ring + (size_t)env * (S.ls_mask + 1);
-    for (int k = tid; k <= S.ls_mask; k += kResetThreads) ring[k] = 0;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(S.ls_ring + (size_t)env * (S.ls_mask + 1));
+    for (int k = tid; k < (S.ls_mask + 1) / 4; k += kResetThreads) ring[k] = 0u;
     __syncthreads();                               // weather window + norms visible to thread 0
     if (tid == 0) {
         if (staged) S.pend_valid[env] = 0;
@@ -409,45 +539,14 @@ __global__ void __launch_bounds__(kResetThreads) k_reset(const sdc::State S, con
 // =================================================================================================
 // k_step
 // =================================================================================================
-// The window scan as a separate (non-inlined) function: with its own register allocation ptxas keeps all UNROLL
-// 128-bit loads of a batch in flight before the first use; inlined into the large kernel it sinks the loads next to
-// their uses to save registers and the scan runs ~45 % slower.  Results go through SHARED memory (8 words per warp):
-// a by-reference struct would live in local memory, which misses the small L1 and then costs a DRAM-latency round
-// trip per access while HBM is saturated.
-template <int UNROLL>
-__device__ __noinline__ void scan_job(const float* h, int n, float lo, float hi, float shift, int dirs, float t0, float t1,
-                                      float* out) {
-    const int lane = threadIdx.x & 31;
-    sdc::ScanResult rs;
-    scan_dispatch<UNROLL>(h, n, lo, hi, shift, dirs & 3, dirs >> 2, t0, t1, lane, rs);
-    if (lane == 0) {
-        out[0] = rs.s1; out[1] = rs.s2; out[2] = rs.ext[0]; out[3] = rs.ext[1];
-        reinterpret_cast<int*>(out)[4] = rs.cnt[0] | (rs.cnt[1] << 16);
-    }
-    __syncwarp();
-}
-
-// Flag-tagged 8-byte words (value, step tag) for the lock-free hand-offs between warps: an aligned 8-byte store is
-// atomic, so a reader that sees the current step's tag also sees the value -- no fences (a gpu-scope fence costs
-// microseconds while HBM is saturated).
-__device__ __forceinline__ void st_pair(uint2* p, uint32_t val, uint32_t tag) {
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(val), "r"(tag) : "memory");
-}
-__device__ __forceinline__ uint2 ld_pair(const uint2* p) {
-    uint2 r;
-    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
-    return r;
-}
-enum { JP_ENV = 0, JP_N, JP_LO, JP_HI, JP_SHIFT, JP_DIRS, JP_THR0, JP_THR1, JP_WORDS = 8 };  // words of one queue record
-enum { JR_S1 = 0, JR_S2, JR_EXT0, JR_EXT1, JR_CNTS, JR_WORDS = 8 };                     // job result words per env
-
 template <int UNROLL>
 __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, const StepArgs a, const int n_unit_ctas) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int U = a.unit_envs;
     // location / dc-parameter tables -> shared memory (removes one level of pointer chasing per env)
     sdc::Tables T{S.loc, S.dc};
+    __shared__ PassShared ps;
     {
         const int loc_bytes = S.n_loc * (int)sizeof(sdc::LocTables), dc_bytes = S.n_cfg * (int)sizeof(sdc_dc_params);
         if (loc_bytes + dc_bytes <= kTableBytes) {
@@ -459,179 +558,179 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
             T.loc = reinterpret_cast<const sdc::LocTables*>(smem_raw);
             T.dc = reinterpret_cast<const sdc_dc_params*>(smem_raw + loc_bytes);
         }
+        if (threadIdx.x == 0) {
+            mbar_init(&ps.bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
         __syncthreads();
     }
-    __shared__ float scan_out[kWarpsPerBlock * 8];
-    float* tile = reinterpret_cast<float*>(smem_raw + kTableBytes) + (size_t)warp * U * kListRow;     // this warp's bracket lists
+    float* scr = reinterpret_cast<float*>(smem_raw + kTableBytes);      // [2][kCollectCap] collect scratch of the window pass
+    float* win = scr + 2 * sdc::kCollectCap;                            // [hist_cap] the staged window
+    unsigned pass_phase = 0;
     const int N = S.n_envs;
     const int n_units = (N + U - 1) / U;
-    const uint32_t seq = (uint32_t)a.seq;
-    const int total_jobs = (N / U) * max(U - a.local_jobs, 0) + max(N % U - a.local_jobs, 0);       // records the queue will hold
-    if (blockIdx.x == 0 && threadIdx.x < 8) a.ctr_next[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < 16) a.ctr_next[threadIdx.x] = 0;
 
     // ------------------------------------------------------------------------------------------------------------
-    // Every warp of a unit CTA runs this small state machine until no unit and no scan job is left:
-    //   produce  take a unit of U envs: scalar phase (one lane per env), then publish one window-scan job per env
-    //   consume  take any published job (global queue, any env of any warp) and stream that env's window
-    //   finish   once all jobs of the own unit have results: rewards, bracket write-back
-    // Jobs are balanced over all warps of the chip; a warp never blocks on a single condition, so there is no
-    // hold-and-wait cycle whatever the number of units per warp.
+    // Rounds (CTA-synchronous).  In a round every warp takes a unit of U consecutive envs from the ticket counter,
+    // one lane per env:
+    //   physics (load shifting, data centre, battery, traces) -> the step's energy
+    //   reward normaliser, incremental: window append, quartile brackets, moments, tail bands (sdc_core.h)
+    // then the CTA as a whole streams the windows of the few envs whose incremental state ran out of slack (TMA bulk
+    // copy into shared memory, all 256 threads scan, sort and commit), and the warps finish their units: rewards,
+    // observations, logger sums, hand-over of finished envs to the reset workers.
     // ------------------------------------------------------------------------------------------------------------
-    if (a.phase_clocks && threadIdx.x == 0) atomicMin(a.phase_clocks + 8, gtime_ns());
-    bool have_unit = false, units_left = blockIdx.x < n_unit_ctas, jobs_left = blockIdx.x < n_unit_ctas;
-    int pending = -1;                                              // claimed job ticket not yet consumed
-    int env0 = 0, n_here = 0;
-    sdc::RewardInputs en;
-    en.energy = 0.0; en.nci_next = 0.0; en.ls_penalty = 0.0;
-    sdc::QView Q;
-    Q.lst[0] = tile + lane * kListRow; Q.lst[1] = Q.lst[0] + sdc::kListCap;
-    Q.a[0] = Q.a[1] = Q.m[0] = Q.m[1] = 0;
-    sdc::ScanRequest rq;                                           // the own env's request (phase C needs n, dirs, shift, q1)
-    rq.n = 0; rq.lo = rq.hi = rq.shift = 0.f; rq.dir[0] = rq.dir[1] = 0; rq.thr[0] = rq.thr[1] = 0.f; rq.degenerate = 0; rq.q1 = 0.0;
-    sdc::ScanResult mine;                                          // results of the locally scanned envs (lane l <-> env l)
-    mine.s1 = mine.s2 = 0.f; mine.cnt[0] = mine.cnt[1] = 0; mine.ext[0] = mine.ext[1] = 0.f;
-    int unit_n_local = 0;
-    long long clk_scan = 0, clk_idle = 0;
-    int n_jobs_done = 0;
-
-    while (have_unit || units_left || jobs_left || pending >= 0) {
-        // ---------------- produce ----------------
-        if (!have_unit && units_left) {
-            int unit = 0;
-            if (lane == 0) unit = atomicAdd(a.ctr + 0, 1);
-            unit = __shfl_sync(0xffffffffu, unit, 0);
-            if (unit >= n_units) { units_left = false; continue; }
-            env0 = unit * U;
-            const int env = env0 + lane;
-            const bool active = lane < U && env < N;
-            n_here = min(U, N - env0);
+    if (a.phase_clocks && threadIdx.x == 0) atomicMin(a.phase_clocks + 13, gtime_ns());
+    if (blockIdx.x < n_unit_ctas) for (;;) {
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(a.ctr + 0, 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        const bool have_unit = unit < n_units;
+        if (!__syncthreads_or(have_unit)) break;
+        const int env0 = unit * U;
+        const int env = env0 + lane;
+        const bool active = have_unit && lane < U && env < N;
         const long long tk0 = clock64();
-        // ---------------- scalar phase, one lane per env ----------------
-        // (1) the unit's quartile brackets (one contiguous 8 KB block) start moving into shared memory asynchronously
-        {
-            const float4* src = reinterpret_cast<const float4*>(S.qlist + (size_t)env0 * 2 * sdc::kListCap);
-            const int total4 = n_here * (2 * sdc::kListCap / 4);
-#if defined(SDC_LIST_STAGING_SERIAL)
-            for (int i = lane; i < total4; i += 32) {
-                const float4 v = src[i];
-                float* d = tile + (i >> 4) * kListRow + (i & 15) * 4;
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-            }
-#elif defined(SDC_LIST_STAGING_CA)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int i = lane + 32 * j;
-                if (i < total4) {
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + (i >> 4) * kListRow + (i & 15) * 4);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + i) : "memory");
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-#else
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int i = lane + 32 * j;
-                if (i < total4) {
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + (i >> 4) * kListRow + (i & 15) * 4);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + i) : "memory");
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-        }
-        int2 qa = make_int2(0, 0), qm = make_int2(0, 0);
-        if (active) { qa = reinterpret_cast<const int2*>(S.q_a)[env]; qm = reinterpret_cast<const int2*>(S.q_m)[env]; }
-        // (2) load shifting, data centre, battery -> the step's energy
-        en.energy = 0.0; en.nci_next = 0.0; en.ls_penalty = 0.0;
         sdc::StepResult st;
         sdc::ObsDeferred od;
+        sdc::RewardInputs en;
+        sdc::ScanRequest rq;
+        sdc::ScanResult rs;
+        sdc::Moments M;
+        sdc::QView Q;
         st.terminal = 0;
+        en.energy = 0.0; en.nci_next = 0.0; en.ls_penalty = 0.0;
+        rq.kind = sdc::SCAN_SKIP; rq.n = 0; rq.lo = rq.hi = rq.shift = 0.f; rq.tl = rq.th = rq.tl2 = rq.th2 = 0.f; rq.tails = 0;
+        rq.dir[0] = rq.dir[1] = 0; rq.thr[0] = rq.thr[1] = 0.f; rq.rc[0] = rq.rc[1] = 0; rq.k[0] = rq.k[1] = 0;
+        rq.ca[0] = rq.ca[1] = rq.cb[0] = rq.cb[1] = 0.f; rq.degenerate = 0;
+        rs.s1 = rs.s2 = 0.f; rs.cnt[0] = rs.cnt[1] = 0; rs.ext[0] = rs.ext[1] = 0.f; rs.recentred = 0;
+        rs.new_a[0] = rs.new_a[1] = rs.new_m[0] = rs.new_m[1] = 0;
+        M.ok = 0; M.c0 = M.c1 = M.c2 = 0.0;
+        Q.lst[0] = S.qlist + (size_t)(active ? env : 0) * 2 * sdc::kListCap; Q.lst[1] = Q.lst[0] + sdc::kListCap;
+        Q.a[0] = Q.a[1] = Q.m[0] = Q.m[1] = 0;
+        long long tk1 = tk0;
+        prefetch_env(S, T, env, active);
         if (active) {
-            prefetch_env(S, T, env);
-            if (a.prefetch & 1) {
-                const int len = S.hist_len[env];
-                if (len >= 4 && lane < 2) l2_prefetch_bulk(S.hist + (size_t)env * S.hist_cap, (unsigned)((len * 4) & ~15));
-            }
+            const int2 qa = reinterpret_cast<const int2*>(S.q_a)[env], qm = reinterpret_cast<const int2*>(S.q_m)[env];
             const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
             GlobalInfoSink info{a.info, N, env};
             sdc::physics_step(S, T, env, a_ls, a_dc, a_bat, info, st, od);
             en.energy = st.energy; en.nci_next = st.nci_next; en.ls_penalty = st.ls_penalty;
-        }
-        const long long tk1 = clock64();
-        // (3) append the energy to the reward window, update the brackets, publish the window-scan jobs
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        Q.a[0] = Q.a[1] = Q.m[0] = Q.m[1] = 0;
-        rq.n = 0; rq.dir[0] = rq.dir[1] = 0; rq.degenerate = 0; rq.q1 = 0.0; rq.shift = 0.f;
-        if (active) {
+            tk1 = clock64();
             Q.a[0] = qa.x; Q.a[1] = qa.y; Q.m[0] = qm.x; Q.m[1] = qm.y;
             sdc::reward_prepare(S, env, en.energy, st.hist_len, st.hist_head, st.evicted, Q, rq);
-        }
-        // The first `local_jobs` envs of the unit are scanned by this warp right away (parameters stay in registers);
-        // the others become records of the global job queue, which any warp of the chip consumes (load balance).
-        const int n_local = min(a.local_jobs, n_here);
-        unit_n_local = n_local;
-        mine.s1 = mine.s2 = 0.f; mine.cnt[0] = mine.cnt[1] = 0; mine.ext[0] = mine.ext[1] = 0.f;
-        {
-            const bool queued = active && lane >= n_local;
-            const unsigned act = __ballot_sync(0xffffffffu, queued);
-            int base = 0;
-            if (lane == 0 && act) base = atomicAdd(a.ctr + 4, __popc(act));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (queued) {
-                uint2* jp = a.job_queue + (size_t)(base + __popc(act & ((1u << lane) - 1u))) * JP_WORDS;
-                st_pair(jp + JP_ENV, (uint32_t)env, seq); st_pair(jp + JP_N, (uint32_t)rq.n, seq);
-                st_pair(jp + JP_LO, __float_as_uint(rq.lo), seq); st_pair(jp + JP_HI, __float_as_uint(rq.hi), seq);
-                st_pair(jp + JP_SHIFT, __float_as_uint(rq.shift), seq); st_pair(jp + JP_DIRS, (uint32_t)(rq.dir[0] | (rq.dir[1] << 2)), seq);
-                st_pair(jp + JP_THR0, __float_as_uint(rq.thr[0]), seq); st_pair(jp + JP_THR1, __float_as_uint(rq.thr[1]), seq);
-            }
+            sdc::reward_plan(S, env, rq, M);
         }
         __syncwarp();
-        const long long tl0 = clock64();
-        for (int l = 0; l < n_local; ++l) {
-            const int n = __shfl_sync(0xffffffffu, rq.n, l);
-            if (n < 2) continue;                                   // z = 0 (utils/reward_creator.py:26-27)
-            const int dirs = __shfl_sync(0xffffffffu, rq.dir[0] | (rq.dir[1] << 2), l);
-            float* rs_slot = scan_out + warp * 8;
-            scan_job<UNROLL>(S.hist + (size_t)(env0 + l) * S.hist_cap, n, __shfl_sync(0xffffffffu, rq.lo, l),
-                             __shfl_sync(0xffffffffu, rq.hi, l), __shfl_sync(0xffffffffu, rq.shift, l), dirs,
-                             __shfl_sync(0xffffffffu, rq.thr[0], l), __shfl_sync(0xffffffffu, rq.thr[1], l), rs_slot);
-            if (lane == l) {
-                mine.s1 = rs_slot[0]; mine.s2 = rs_slot[1]; mine.ext[0] = rs_slot[2]; mine.ext[1] = rs_slot[3];
-                const int c = reinterpret_cast<const int*>(rs_slot)[4];
-                mine.cnt[0] = c & 0xffff; mine.cnt[1] = c >> 16;
+        const long long tk2 = clock64();
+        // ---- window passes for the envs that need one (whole CTA per env) ----
+        {
+            const unsigned slow = __ballot_sync(0xffffffffu, active && rq.kind != sdc::SCAN_SKIP);
+            const unsigned n_refresh = __popc(__ballot_sync(0xffffffffu, active && rq.kind == sdc::SCAN_REFRESH));
+            const unsigned n_lists = __popc(__ballot_sync(0xffffffffu, active && (rq.rc[0] || rq.rc[1])));
+            const unsigned n_tails = __popc(__ballot_sync(0xffffffffu, active && rq.kind == sdc::SCAN_REFRESH && !M.ok && rq.tails));
+            if (lane == 0) {
+                ps.slow[warp] = slow;
+                if (slow) {          // statistics only
+                    atomicAdd(a.ctr + 4, __popc(slow) - (int)n_refresh); atomicAdd(a.ctr + 5, (int)n_refresh);
+                    atomicAdd(a.ctr + 6, (int)n_lists); atomicAdd(a.ctr + 7, (int)n_tails);
+                }
+            }
+        }
+        __syncthreads();                      // the step's ring / bracket / band updates of all warps are visible CTA-wide
+#pragma unroll 1
+        for (int w = 0; w < kWarpsPerBlock; ++w) {
+            unsigned mask = ps.slow[w];       // uniform across the CTA
+#pragma unroll 1
+            while (mask) {
+                const int l = __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (warp == w && lane == l) {
+                    PassJob& J = ps.job;
+                    J.env = env; J.n = rq.n; J.kind = rq.kind;
+                    J.lo = rq.lo; J.hi = rq.hi; J.shift = rq.shift; J.tl = rq.tl; J.th = rq.th; J.tl2 = rq.tl2; J.th2 = rq.th2;
+                    J.dir[0] = rq.dir[0]; J.dir[1] = rq.dir[1]; J.thr[0] = rq.thr[0]; J.thr[1] = rq.thr[1];
+                    J.rc[0] = rq.rc[0]; J.rc[1] = rq.rc[1]; J.k[0] = rq.k[0]; J.k[1] = rq.k[1];
+                    J.ca[0] = rq.ca[0]; J.ca[1] = rq.ca[1]; J.cb[0] = rq.cb[0]; J.cb[1] = rq.cb[1];
+                    J.tails = rq.tails; J.degenerate = rq.degenerate;
+                    J.q_a[0] = Q.a[0]; J.q_a[1] = Q.a[1]; J.q_m[0] = Q.m[0]; J.q_m[1] = Q.m[1];
+                }
+                __syncthreads();
+                window_pass(S, ps, win, scr, pass_phase);
+                pass_phase ^= 1u;
+                if (warp == w && lane == l) rs = ps.job.rs;
+                __syncthreads();              // the owner has its results before the next owner overwrites the slot
+            }
+        }
+        const long long tk3 = clock64();
+        // ---- rewards, bracket cursors ----
+        double m_sum = 0.0, m_ls = 0.0, m_dc = 0.0;
+        if (active) {
+            float r3[3];
+            sdc::reward_finish(S, env, rq, rs, M, en, Q, r3);
+            reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
+            reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
+            a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
+            m_sum = (double)r3[0] + r3[1] + r3[2]; m_ls = r3[0]; m_dc = r3[1];
+        }
+        const long long tk3b = clock64();
+        // ---- observations (written straight to obs / share / term_obs; the L2 merges the per-lane 4-byte stores into
+        //      full sectors), logger sums, hand-over of finished envs to the reset workers ----
+        {
+            double m[16];
+            long long tk3c = tk3b;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m[k] = 0.0;
+            const int finished = st.terminal;
+            // Observation rows go through a shared-memory tile (odd row stride: conflict-free) and leave as contiguous
+            // 128-bit stores; 107 scattered 4-byte stores per env would keep the LSU busy for ~50 k cycles per unit.
+            float* tile = reinterpret_cast<float*>(smem_raw + kTableBytes) + (size_t)warp * 32 * kTileStride;
+            if (active) {
+                RowSink sink{tile + lane * kTileStride};
+                sdc::emit_obs(S, T, env, od, sink);
+                a.done[env] = (uint8_t)finished;
             }
             __syncwarp();
-            n_jobs_done += 1;
-        }
-        clk_scan += clock64() - tl0;
-        __syncwarp();
-        have_unit = true;
-        const long long tk2 = clock64();
-        // (4) off the queue's critical path: observations (written straight to obs / share / term_obs; the L2 merges the
-        //     per-lane 4-byte stores into full sectors), logger sums, hand-over of finished envs to the reset workers
-        {
-            double m[13];
+            if (have_unit) {
+                const int n_here = min(U, N - env0);
+                const int total = n_here * kObsRow;
+                float4* dst4 = reinterpret_cast<float4*>(a.obs + (size_t)env0 * kObsRow);      // env0 is a multiple of 8
+                for (int i = lane; i < total / 4; i += 32) {
+                    float v[4];
 #pragma unroll
-            for (int k = 0; k < 13; ++k) m[k] = 0.0;
-            const int finished = st.terminal;
+                    for (int q = 0; q < 4; ++q) { const int f = 4 * i + q; const int e = f / kObsRow; v[q] = tile[e * kTileStride + (f - e * kObsRow)]; }
+                    dst4[i] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                for (int f = (total & ~3) + lane; f < total; f += 32) { const int e = f / kObsRow; a.obs[(size_t)env0 * kObsRow + f] = tile[e * kTileStride + (f - e * kObsRow)]; }
+                float* dsh = a.share + (size_t)env0 * SDC_SHARE_DIM;
+                for (int f = lane; f < n_here * SDC_SHARE_DIM; f += 32) {
+                    const int e = f / SDC_SHARE_DIM, k = f - e * SDC_SHARE_DIM;
+                    const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
+                    dsh[f] = tile[e * kTileStride + src];
+                }
+                unsigned fin = __ballot_sync(0xffffffffu, finished != 0);
+                while (fin && a.term_obs) {
+                    const int l = __ffs(fin) - 1;
+                    fin &= fin - 1;
+                    for (int k = lane; k < kObsRow; k += 32) a.term_obs[(size_t)(env0 + l) * kObsRow + k] = tile[l * kTileStride + k];
+                }
+            }
             if (active) {
-                GlobalObsSink obs{a.obs + (size_t)env * kObsRow, a.share + (size_t)env * SDC_SHARE_DIM,
-                                  (finished && a.term_obs) ? a.term_obs + (size_t)env * kObsRow : nullptr};
-                sdc::emit_obs(S, T, env, od, obs);
-                a.done[env] = (uint8_t)finished;
+                tk3c = clock64();
                 m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
                 m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
-                m[11] = st.overdue; m[12] = st.total_kw;
+                m[11] = st.overdue; m[12] = st.total_kw; m[13] = m_sum; m[14] = m_ls; m[15] = m_dc;
             }
             // logger sums (harl/envs/sustaindc/sustaindc_logger.py:86-101): warp reduce, one atomic per metric
-            constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
+            constexpr int slot[16] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
                                       sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
-                                      sdc::M_OVERDUE, sdc::M_TOTAL_KW};
+                                      sdc::M_OVERDUE, sdc::M_TOTAL_KW, sdc::M_REWARD_SUM, sdc::M_REWARD_LS, sdc::M_REWARD_DC};
+            if (have_unit) {
 #pragma unroll
-            for (int k = 0; k < 13; ++k) {
-                const double v = warp_sum(m[k]);
-                if (lane == 0) atomicAdd(a.metrics + slot[k], v);
+                for (int k = 0; k < 16; ++k) {
+                    const double v = warp_sum(m[k]);
+                    if (lane == 0) atomicAdd(a.metrics + slot[k], v);
+                }
             }
             // Finished envs go to the reset workers (other CTAs of this launch).  Order matters: the terminal observation
             // is in global memory before the env is published, because the worker overwrites obs/share with the reset
@@ -642,119 +741,52 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                 __threadfence();
                 __syncwarp();
             }
-            if (lane == 0) atomicAdd(a.ctr + 2, 1);
+            // look-ahead: envs that will finish two steps from now -> pre-generation list consumed by the next launch
+            if (active && st.step_after + 2 == S.ep_len) a.pre_list[atomicAdd(a.ctr + 8, 1)] = env;
+            if (lane == 0 && have_unit) atomicAdd(a.ctr + 2, 1);
+            if (a.phase_clocks && lane == 0 && have_unit) {
+                atomicAdd(a.phase_clocks + 8, (unsigned long long)(tk3b - tk3));    // reward_finish
+                atomicAdd(a.phase_clocks + 9, (unsigned long long)(tk3c - tk3b));   // emit_obs
+            }
         }
-        if (a.phase_clocks && lane == 0) {
-            const long long tk2b = clock64();
+        if (a.phase_clocks && lane == 0 && have_unit) {
+            const long long tk4 = clock64();
             atomicAdd(a.phase_clocks + 0, (unsigned long long)(tk1 - tk0));   // load shifting + data centre + battery
-            atomicAdd(a.phase_clocks + 1, (unsigned long long)(tk2 - tk1));   // window append, bracket update, publish (+ local scans)
-            atomicAdd(a.phase_clocks + 13, (unsigned long long)(tk2b - tk2)); // deferred observations + metrics
+            atomicAdd(a.phase_clocks + 1, (unsigned long long)(tk2 - tk1));   // window append, brackets, moments, tail bands
+            atomicAdd(a.phase_clocks + 2, (unsigned long long)(tk3 - tk2));   // waiting for the CTA + window passes
+            atomicAdd(a.phase_clocks + 3, (unsigned long long)(tk4 - tk3));   // rewards, observations, metrics
             atomicAdd(a.phase_clocks + 4, 1ull);                              // units
-            atomicMax(a.phase_clocks + 9, gtime_ns());
+            atomicMax(a.phase_clocks + 14, gtime_ns());                       // timeline: last unit done
+            atomicMax(a.phase_clocks + 10, (unsigned long long)(tk4 - tk0));  // slowest unit (clocks)
+            atomicMax(a.phase_clocks + 11, (unsigned long long)(tk2 - tk0));  // slowest scalar phase
         }
-        continue;
-        }
-
-        // ---------------- consume ----------------
-        if (pending < 0 && jobs_left) {
-            int j = 0;
-            if (lane == 0) j = atomicAdd(a.ctr + 5, 1);
-            j = __shfl_sync(0xffffffffu, j, 0);
-            if (j >= total_jobs) jobs_left = false; else pending = j;
-        }
-        if (pending >= 0) {
-            uint2 w = make_uint2(0u, seq);
-            if (lane < JP_WORDS) w = ld_pair(a.job_queue + (size_t)pending * JP_WORDS + lane);       // one round trip: whole record
-            if (__all_sync(0xffffffffu, w.y == seq)) {
-                const long long tc0 = clock64();
-                const int jenv = (int)__shfl_sync(0xffffffffu, w.x, JP_ENV);
-                const int n = (int)__shfl_sync(0xffffffffu, w.x, JP_N);
-                float* rs_slot = scan_out + warp * 8;
-                if (n >= 2) {                                      // n < 2: z = 0 (utils/reward_creator.py:26-27)
-                    scan_job<UNROLL>(S.hist + (size_t)jenv * S.hist_cap, n, __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_LO)),
-                                     __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_HI)),
-                                     __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_SHIFT)), (int)__shfl_sync(0xffffffffu, w.x, JP_DIRS),
-                                     __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_THR0)),
-                                     __uint_as_float(__shfl_sync(0xffffffffu, w.x, JP_THR1)), rs_slot);
-                } else {
-                    if (lane < 5) rs_slot[lane] = 0.f;
-                    __syncwarp();
-                }
-                if (lane < 5) st_pair(a.job_results + (size_t)jenv * JR_WORDS + lane, __float_as_uint(rs_slot[lane]), seq);
-                __syncwarp();
-                pending = -1;
-                clk_scan += clock64() - tc0; n_jobs_done += 1;
-                if (a.phase_clocks && lane == 0) atomicMax(a.phase_clocks + 10, gtime_ns());
-                continue;
-            }
-        }
-
-        // ---------------- finish ----------------
-        if (have_unit) {
-            const int env = env0 + lane;
-            const bool active = lane < U && env < N;
-            uint2 r[5];
-            bool ok = true;
-            const bool remote = active && lane >= unit_n_local;
-            if (remote) {
-#pragma unroll
-                for (int k = 0; k < 5; ++k) { r[k] = ld_pair(a.job_results + (size_t)env * JR_WORDS + k); ok = ok && r[k].y == seq; }
-            }
-            if (__all_sync(0xffffffffu, ok)) {
-                const long long tk3 = clock64();
-                double m_sum = 0.0, m_ls = 0.0, m_dc = 0.0;
-                if (active) {
-                    if (remote) {
-                        mine.s1 = __uint_as_float(r[JR_S1].x); mine.s2 = __uint_as_float(r[JR_S2].x);
-                        mine.ext[0] = __uint_as_float(r[JR_EXT0].x); mine.ext[1] = __uint_as_float(r[JR_EXT1].x);
-                        mine.cnt[0] = (int)(r[JR_CNTS].x & 0xffffu); mine.cnt[1] = (int)(r[JR_CNTS].x >> 16);
-                    }
-                    float r3[3];
-                    sdc::reward_finish(S, env, rq, mine, en, Q, r3);
-                    reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
-                    reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
-                    a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
-                    m_sum = (double)r3[0] + r3[1] + r3[2]; m_ls = r3[0]; m_dc = r3[1];
-                }
-                m_sum = warp_sum(m_sum); m_ls = warp_sum(m_ls); m_dc = warp_sum(m_dc);
-                if (lane == 0) {
-                    atomicAdd(a.metrics + sdc::M_REWARD_SUM, m_sum); atomicAdd(a.metrics + sdc::M_REWARD_LS, m_ls);
-                    atomicAdd(a.metrics + sdc::M_REWARD_DC, m_dc);
-                }
-                __syncwarp();
-                {
-                    float4* dst = reinterpret_cast<float4*>(S.qlist + (size_t)env0 * 2 * sdc::kListCap);
-                    const int total4 = n_here * (2 * sdc::kListCap / 4);
-                    for (int i = lane; i < total4; i += 32) {
-                        const int e = i >> 4, k = (i & 15) * 4;
-                        const float* d = tile + e * kListRow + k;
-                        dst[i] = make_float4(d[0], d[1], d[2], d[3]);
-                    }
-                }
-                __syncwarp();
-                have_unit = false;
-                if (a.phase_clocks && lane == 0) { atomicAdd(a.phase_clocks + 3, (unsigned long long)(clock64() - tk3)); atomicMax(a.phase_clocks + 11, gtime_ns()); }
-                continue;
-            }
-        }
-        // nothing to do right now: the claimed job is not published yet and the own unit is still being scanned elsewhere
-        { const long long ti = clock64(); __nanosleep(100); clk_idle += clock64() - ti; }
-    }
-    if (a.phase_clocks && lane == 0) {
-        atomicAdd(a.phase_clocks + 2, (unsigned long long)clk_scan);      // window scans (all jobs this warp consumed)
-        atomicAdd(a.phase_clocks + 5, (unsigned long long)clk_idle);      // waiting
-        atomicAdd(a.phase_clocks + 6, (unsigned long long)n_jobs_done);
-        atomicAdd(a.phase_clocks + 7, 1ull);                              // warps
     }
 
     // ---------------- episode resets: every CTA turns into a reset worker once it has no unit left ----------------
-    // CTAs beyond n_unit_ctas start here immediately, so resets of envs that finished in this step overlap with the
-    // window scans of the other CTAs.  A worker claims the next slot of reset_list and waits until it is filled or
-    // until every unit is past phase A (then no further env can be appended).
+    // CTAs beyond n_unit_ctas start here immediately, so episode generation and resets overlap with the
+    // other CTAs' units.  A worker claims the next slot of reset_list and waits until it is filled or until every unit
+    // is past its hand-over (then no further env can be appended).
     __shared__ ResetShared rsh;
     __shared__ int s_env;
     __syncthreads();
-    double* runbuf = reinterpret_cast<double*>(smem_raw + kTableBytes);   // the warps' scratch tiles are free by now
+    double* runbuf = reinterpret_cast<double*>(smem_raw + kTableBytes);   // the window-pass buffers are free by now
+    // (1) pre-generation jobs published by the previous launch: independent of this step, so the CTAs without units
+    //     work on them from the first cycle on
+    {
+        const int n_pre = *reinterpret_cast<volatile const int32_t*>(a.ctr_prev + 8);
+        for (;;) {
+            if (threadIdx.x == 0) {
+                const int idx = atomicAdd(a.ctr + 9, 1);
+                s_env = idx < n_pre ? a.pre_list_prev[idx] : -1;
+            }
+            __syncthreads();
+            const int env = s_env;
+            __syncthreads();
+            if (env < 0) break;
+            pregen_one_env(S, env, runbuf, rsh);
+        }
+    }
+    // (2) resets of the envs that finished in this step
     for (;;) {
         if (threadIdx.x == 0) {
             const int my = atomicAdd(a.ctr + 3, 1);
@@ -777,7 +809,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         reset_one_env(S, env, a.obs, a.share, runbuf, rsh);
         __syncthreads();
     }
-    if (a.phase_clocks && threadIdx.x == 0) atomicMax(a.phase_clocks + 12, gtime_ns());
+    if (a.phase_clocks && threadIdx.x == 0) atomicMax(a.phase_clocks + 15, gtime_ns());   // timeline: CTA done
 }
 
 __global__ void k_build_reset_list(int n_envs, const uint8_t* __restrict__ mask, int32_t* list, int32_t* count) {
@@ -826,6 +858,7 @@ __global__ void __launch_bounds__(kSortThreads) k_rebuild(const sdc::State S) {
             for (int i = 0; i < m; ++i) lst[i] = buf[a + i];
         }
         S.q_a[env * 2 + j] = a; S.q_m[env * 2 + j] = m;
+        S.tail_n[env * 2 + j] = -1;                // moments / tail sets are rebuilt by the env's next step
     }
 }
 
@@ -834,8 +867,9 @@ __global__ void __launch_bounds__(kSortThreads) k_rebuild(const sdc::State S) {
 // =================================================================================================
 static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& a, void* stream) {
     const int U = a.unit_envs;
-    size_t smem = (size_t)kWarpsPerBlock * U * kListRow * sizeof(float);
-    if (smem < kNormWindow * sizeof(double)) smem = kNormWindow * sizeof(double);      // reset workers reuse the tile region
+    size_t smem = (size_t)(2 * sdc::kCollectCap + S.hist_cap) * sizeof(float);         // collect scratch + the staged window
+    if (smem < (size_t)kWarpsPerBlock * 32 * kTileStride * sizeof(float)) smem = (size_t)kWarpsPerBlock * 32 * kTileStride * sizeof(float);   // obs tiles (same region)
+    if (smem < kNormWindow * sizeof(double)) smem = kNormWindow * sizeof(double);      // reset workers reuse the region
     smem += kTableBytes;
     const int n_units = (S.n_envs + U - 1) / U;
     const int bps = a.blocks_per_sm > 0 ? a.blocks_per_sm : c.step_blocks_per_sm;

@@ -35,3 +35,45 @@ def traj_cfg(g):
 def rel_err(a, b):
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))
+
+
+def check_incremental_state(eng, envs=None, tag=""):
+    """The incremental reward-normaliser state of every env must describe its window EXACTLY: quartile brackets ==
+    the corresponding slice of the fully sorted window, tail bands == the multisets between the inner and outer thresholds, far-tail aggregates == direct sums, window
+    moments == the direct sums (fp64 rounding only).  Returns (#envs with valid tail sets, #envs checked)."""
+    from dc_rl_b200 import _lib
+    n = eng.n_envs
+    L = _lib.LIST_CAP
+    q_a, q_m, ql = eng.read_state("q_a").reshape(n, 2), eng.read_state("q_m").reshape(n, 2), eng.read_state("qlist").reshape(n, 2, L)
+    hl = eng.read_state("hist_len").reshape(n)
+    hist = eng.read_state("hist").reshape(n, -1)
+    tn, thr, tails = eng.read_state("tail_n").reshape(n, 2), eng.read_state("tail_thr").reshape(n, 4), eng.read_state("tails")
+    an, ag = eng.read_state("agg_n").reshape(n, 2), eng.read_state("agg_s").reshape(n, 2, 2)
+    s1, s2, c0 = (eng.read_state(k).reshape(n) for k in ("mom_s1", "mom_s2", "mom_c0"))
+    valid = 0
+    for e in (range(n) if envs is None else envs):
+        w = hist[e, :hl[e]]
+        srt = np.sort(w)
+        for j in range(2):
+            a, m = int(q_a[e, j]), int(q_m[e, j])
+            assert np.array_equal(ql[e, j, :m], srt[a:a + m]), (tag, "bracket", e, j, a, m)
+            if hl[e] >= 2:
+                k = ((1, 3)[j] * (hl[e] - 1)) // 4
+                assert a <= k and k + 1 < a + m, (tag, "rank outside bracket", e, j, a, m, k)
+        if tn[e, 0] < 0:
+            continue
+        valid += 1
+        lo_set = np.sort(tails[e // 32, 0, :tn[e, 0], e % 32])
+        hi_set = np.sort(tails[e // 32, 1, :tn[e, 1], e % 32])
+        assert np.array_equal(lo_set, srt[(srt < thr[e, 0]) & (srt >= thr[e, 2])]), (tag, "low band", e)
+        assert np.array_equal(hi_set, srt[(srt > thr[e, 1]) & (srt <= thr[e, 3])]), (tag, "high band", e)
+        for side, far in enumerate((srt[srt < thr[e, 2]], srt[srt > thr[e, 3]])):
+            yf = far.astype(np.float64) - c0[e]
+            assert an[e, side] == len(far), (tag, "far count", e, side)
+            assert abs(yf.sum() - ag[e, side, 0]) <= 1e-9 * max(1.0, float(np.abs(yf).sum())), (tag, "far s1", e, side)
+            assert abs((yf * yf).sum() - ag[e, side, 1]) <= 1e-9 * max(1.0, float((yf * yf).sum())), (tag, "far s2", e, side)
+        y = w.astype(np.float64) - c0[e]
+        scale = max(1.0, float(np.sum(np.abs(y))))
+        assert abs(y.sum() - s1[e]) <= 1e-9 * scale, (tag, "s1", e, y.sum(), s1[e])
+        assert abs((y * y).sum() - s2[e]) <= 1e-9 * max(1.0, float((y * y).sum())), (tag, "s2", e)
+    return valid, (n if envs is None else len(envs))

@@ -35,7 +35,6 @@ static void pinned_free(Context&, void* p) { free(p); }
 static const char* stream_create(Context&, void** s) { *s = nullptr; return nullptr; }
 static const char* stream_sync(Context&, void*) { return nullptr; }
 static const char* sync(Context&) { return nullptr; }
-static size_t reset_scratch_floats(Context&) { return 4; }
 static const char* dev_fill_bytes(Context&, void* p, int v, size_t bytes) { memset(p, v, bytes); return nullptr; }
 static const char* event_create(Context&, void** ev) { *ev = nullptr; return nullptr; }
 static const char* event_record(Context&, void*, void*) { return nullptr; }
@@ -51,27 +50,62 @@ struct InfoCol {
     void operator()(int col, float v) { if (info) info[(size_t)col * n + env] = v; }
 };
 
-static void scan_window(const sdc::State& S, int env, const sdc::ScanRequest& rq, sdc::ScanResult& rs) {
+// plain pass: clipped moments
+static void scan_plain(const sdc::State& S, int env, const sdc::ScanRequest& rq, sdc::ScanResult& rs) {
     const float* h = S.hist + (size_t)env * S.hist_cap;
     float s1 = 0.f, s2 = 0.f;
-    for (int j = 0; j < 2; ++j) { rs.cnt[j] = 0; rs.ext[j] = rq.dir[j] == sdc::SCAN_ABOVE ? INFINITY : -INFINITY; }
+    for (int i = 0; i < rq.n; ++i) {
+        const float d = fminf(fmaxf(h[i], rq.lo), rq.hi) - rq.shift;
+        s1 += d; s2 += d * d;
+    }
+    rs.s1 = s1; rs.s2 = s2;
+}
+
+// refresh pass: serial statement of scan_refresh in sdc_kernels.cu
+static void scan_refresh(const sdc::State& S, int env, const sdc::ScanRequest& rq, sdc::RefreshRaw& raw, sdc::ScanResult& rs,
+                         std::vector<float> coll[2]) {
+    const float* h = S.hist + (size_t)env * S.hist_cap;
+    float s1 = 0.f, s2 = 0.f;
+    double S1 = 0.0, S2 = 0.0;
+    const double c0 = (double)rq.shift;
+    float* tl = sdc::tail_ptr(S, env, 0);
+    float* th = sdc::tail_ptr(S, env, 1);
+    raw.n_tail[0] = raw.n_tail[1] = 0;
+    for (int j = 0; j < 2; ++j) { raw.agg_n[j] = 0; raw.agg_s1[j] = raw.agg_s2[j] = 0.0; }
+    for (int j = 0; j < 2; ++j) {
+        rs.cnt[j] = 0; rs.ext[j] = rq.dir[j] == sdc::SCAN_ABOVE ? INFINITY : -INFINITY;
+        raw.c[j] = 0; raw.below[j] = 0; coll[j].clear();
+    }
     for (int i = 0; i < rq.n; ++i) {
         const float x = h[i];
-        const float c = fminf(fmaxf(x, rq.lo), rq.hi);
-        const float d = c - rq.shift;
+        const float d = fminf(fmaxf(x, rq.lo), rq.hi) - rq.shift;
         s1 += d; s2 += d * d;
+        const double y = (double)x - c0;
+        S1 += y; S2 += y * y;
         for (int j = 0; j < 2; ++j) {
             if (rq.dir[j] == sdc::SCAN_BELOW && x < rq.thr[j]) { rs.cnt[j]++; rs.ext[j] = fmaxf(rs.ext[j], x); }
             if (rq.dir[j] == sdc::SCAN_ABOVE && x > rq.thr[j]) { rs.cnt[j]++; rs.ext[j] = fminf(rs.ext[j], x); }
+            if (rq.rc[j]) {
+                if (x < rq.ca[j]) raw.below[j]++;
+                else if (x <= rq.cb[j]) { raw.c[j]++; if ((int)coll[j].size() < sdc::kCollectCap) coll[j].push_back(x); }
+            }
         }
+        if (x < rq.tl2) { raw.agg_n[0]++; raw.agg_s1[0] += y; raw.agg_s2[0] += y * y; }
+        else if (x < rq.tl) { if (raw.n_tail[0] < sdc::kTailCap) tl[(size_t)raw.n_tail[0] * sdc::kTailStride] = x; raw.n_tail[0]++; }
+        if (x > rq.th2) { raw.agg_n[1]++; raw.agg_s1[1] += y; raw.agg_s2[1] += y * y; }
+        else if (x > rq.th) { if (raw.n_tail[1] < sdc::kTailCap) th[(size_t)raw.n_tail[1] * sdc::kTailStride] = x; raw.n_tail[1]++; }
     }
-    rs.s1 = s1; rs.s2 = s2;
+    for (int j = 0; j < 2; ++j) {
+        if (rq.dir[j] == sdc::SCAN_NONE) rs.ext[j] = 0.f;
+        std::sort(coll[j].begin(), coll[j].end());
+    }
+    rs.s1 = s1; rs.s2 = s2; raw.s1 = S1; raw.s2 = S2;
 }
 
 static const char* launch_reset(Context&, const sdc::State& S, const int32_t* list, const int32_t* count, float* obs, float* share, void*);
 
 static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs& a, void*) {
-    for (int k = 0; k < 8; ++k) a.ctr_next[k] = 0;
+    for (int k = 0; k < 16; ++k) a.ctr_next[k] = 0;
     const int N = S.n_envs;
     for (int env = 0; env < N; ++env) {
         ObsRow obs{a.obs + (size_t)env * 3 * SDC_OBS_DIM};
@@ -82,15 +116,27 @@ static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs&
         sdc::physics_step(S, T, env, a.actions[env * 3 + 0], a.actions[env * 3 + 1], a.actions[env * 3 + 2], info, st, od);
         sdc::emit_obs(S, T, env, od, obs);
         sdc::share_from_obs(obs.row, a.share + (size_t)env * SDC_SHARE_DIM);
-        sdc::ScanRequest rq; sdc::ScanResult rs;
+        sdc::ScanRequest rq; sdc::ScanResult rs; sdc::Moments mo;
+        rs.s1 = rs.s2 = 0.f; rs.cnt[0] = rs.cnt[1] = 0; rs.ext[0] = rs.ext[1] = 0.f; rs.recentred = 0;
         sdc::QView Q;
         for (int j = 0; j < 2; ++j) {
             Q.lst[j] = S.qlist + ((size_t)env * 2 + j) * sdc::kListCap; Q.a[j] = S.q_a[env * 2 + j]; Q.m[j] = S.q_m[env * 2 + j];
         }
         sdc::reward_prepare(S, env, st.energy, st.hist_len, st.hist_head, st.evicted, Q, rq);
-        scan_window(S, env, rq, rs);
+        sdc::reward_plan(S, env, rq, mo);
+        if (rq.kind == sdc::SCAN_PLAIN) {
+            scan_plain(S, env, rq, rs);
+            a.ctr[4] += 1;
+        } else if (rq.kind == sdc::SCAN_REFRESH) {
+            sdc::RefreshRaw raw;
+            std::vector<float> coll[2];
+            scan_refresh(S, env, rq, raw, rs, coll);
+            const float* sorted[2] = {coll[0].data(), coll[1].data()};
+            sdc::refresh_commit(S, env, rq, raw, sorted, Q, rs, 0, 1);
+            a.ctr[5] += 1;
+        }
         sdc::RewardInputs en{st.energy, st.nci_next, st.ls_penalty};
-        sdc::reward_finish(S, env, rq, rs, en, Q, a.rew + (size_t)env * 3);
+        sdc::reward_finish(S, env, rq, rs, mo, en, Q, a.rew + (size_t)env * 3);
         for (int j = 0; j < 2; ++j) { S.q_a[env * 2 + j] = Q.a[j]; S.q_m[env * 2 + j] = Q.m[j]; }
         a.done[env] = (uint8_t)st.terminal;
         if (st.terminal) {
@@ -199,6 +245,7 @@ static const char* launch_rebuild(Context&, const sdc::State& S, void*) {
                 for (int i = 0; i < m; ++i) lst[i] = v[a + i];
             }
             S.q_a[env * 2 + j] = a; S.q_m[env * 2 + j] = m;
+            S.tail_n[env * 2 + j] = -1;
         }
     }
     return nullptr;

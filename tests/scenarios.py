@@ -4,6 +4,8 @@ import random
 
 import numpy as np
 
+from helpers import check_incremental_state
+
 
 class Buffers:
     """I/O buffers of the device-pointer API: torch CUDA tensors on the GPU, numpy arrays for the hostsim."""
@@ -163,15 +165,57 @@ def rolling_quartiles_with_ties_and_small_windows(lib):
         for s in range(700):
             eng.step_host(rng.randint(0, 3, size=(N, 3)).astype(np.int32), want_info=False, want_term=False)
             if s % 97 == 0 or s == 699:
-                q_a, q_m, ql = eng.read_state("q_a"), eng.read_state("q_m"), eng.read_state("qlist").reshape(N, 2, 32)
-                hl = eng.read_state("hist_len")
-                hist = eng.read_state("hist")
-                for e in range(N):
-                    srt = np.sort(hist[e, :hl[e]])
-                    for j in range(2):
-                        a, m = int(q_a[e, j]), int(q_m[e, j])
-                        assert np.array_equal(ql[e, j, :m], srt[a:a + m]), (cap, s, e, j)
+                check_incremental_state(eng, tag=(cap, s))
         assert not eng.read_state("err").any()
+
+
+def incremental_normaliser_under_drift(lib, steps=1300, N=48):
+    """The incremental reward normaliser (brackets + moments + tail sets, sdc_core.h) against a direct numpy statement
+    of utils/reward_creator.py:16-45 on the env's window, under conditions that force its refresh machinery: a
+    pre-filled window far from the real energies (drift: re-centring, moving fences), heavy tails (tail sets
+    overflow -> slack adapts / plain passes), heavy ties, and a wrapping window."""
+    from dc_rl_b200 import info_layout
+    from dc_rl_b200.dc_config import size_datacenter
+    from dc_rl_b200.engine import Engine
+    from replay import location_traces
+    col_e, col_ci = info_layout.COL["bat_total_energy_with_battery_KWh"], info_layout.COL["norm_CI"]
+    stats = {}
+    for name in ("drift", "heavy", "ties"):
+        cap = 2000
+        eng = Engine(N, [location_traces("ny")], [size_datacenter("ny")[0]], months=np.arange(N) % 12, days_per_episode=3,
+                     hist_cap=cap, lib=lib)
+        rng = np.random.RandomState(hash(name) % 1000)
+        if name == "drift":
+            pre = 150.0 + 15.0 * rng.standard_normal((N, cap))
+        elif name == "heavy":
+            pre = 400.0 + 30.0 * rng.standard_t(1.5, size=(N, cap))
+        else:
+            pre = np.round(380.0 + 60.0 * rng.standard_normal((N, cap)) / 25.0) * 25.0
+        eng.prefill_history(pre.astype(np.float32))
+        eng.reset_host()
+        worst, scans = 0.0, np.zeros(2, np.int64)
+        for s in range(steps):
+            obs, share, rew, done, info, _ = eng.step_host(rng.randint(0, 3, size=(N, 3)).astype(np.int32))
+            scans += eng.read_state("pass_stats")[:2]
+            if s % 61 == 0 or s >= steps - 3:
+                check_incremental_state(eng, tag=(name, s))
+                hist = eng.read_state("hist").astype(np.float64)
+                e, nci = info[col_e].astype(np.float64), info[col_ci].astype(np.float64)
+                for i in range(N):
+                    w = hist[i]
+                    q1, q3 = np.percentile(w, 25), np.percentile(w, 75)
+                    cl = np.clip(w, q1 - 1.5 * (q3 - q1), q3 + 1.5 * (q3 - q1))
+                    sd = cl.std()
+                    z = (e[i] - cl.mean()) / (sd if sd > 0 else 1.0)
+                    exp = -(nci[i] * z / 0.5)
+                    worst = max(worst, abs(rew[i, 1] - exp) / max(1.0, abs(exp)))
+        assert worst <= 1e-4, (name, worst)
+        assert not eng.read_state("err").any(), name
+        stats[name] = dict(worst=worst, plain=int(scans[0]), refresh=int(scans[1]), env_steps=N * steps,
+                           valid=int((eng.read_state("tail_n").reshape(N, 2)[:, 0] >= 0).sum()))
+    # the point of the design: in the well-behaved case almost no env-step needs a window pass
+    assert stats["drift"]["plain"] + stats["drift"]["refresh"] < 0.1 * stats["drift"]["env_steps"], stats
+    return stats
 
 
 def prefill_and_constant_history_branches(lib):

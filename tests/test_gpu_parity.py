@@ -47,14 +47,12 @@ def test_long_replay_window_saturates(lib):
     eng = w["engine"]
     assert (eng.read_state("hist_len") == 10000).all()
     # brackets maintained incrementally == brackets from a full sort of the window
-    q_a, q_m, ql = eng.read_state("q_a"), eng.read_state("q_m"), eng.read_state("qlist").reshape(3, 2, 32)
+    from helpers import check_incremental_state
+    valid, _ = check_incremental_state(eng, tag="long replay")
+    assert valid == 3                       # the tail sets are in use at the end of the run
     hist = np.sort(eng.read_state("hist"), axis=1)
-    for e in range(3):
-        for j in range(2):
-            a, m = int(q_a[e, j]), int(q_m[e, j])
-            assert np.array_equal(ql[e, j, :m], hist[e, a:a + m])
     eng.rebuild_brackets()
-    ql2, a2, m2 = eng.read_state("qlist").reshape(3, 2, 32), eng.read_state("q_a"), eng.read_state("q_m")
+    ql2, a2, m2 = eng.read_state("qlist").reshape(3, 2, -1), eng.read_state("q_a"), eng.read_state("q_m")
     for e in range(3):
         for j in range(2):
             assert np.array_equal(ql2[e, j, :m2[e, j]], hist[e, a2[e, j]:a2[e, j] + m2[e, j]])
@@ -75,6 +73,11 @@ def test_device_generated_resets_match_host_statement(lib):
 def test_rolling_quartiles_with_ties_and_small_windows(lib):
     import scenarios
     scenarios.rolling_quartiles_with_ties_and_small_windows(lib)
+
+
+def test_incremental_normaliser_under_drift(lib):
+    import scenarios
+    print(scenarios.incremental_normaliser_under_drift(lib))
 
 
 def test_prefill_and_constant_history_branches(lib):

@@ -29,6 +29,14 @@ def test_long_replay_window_saturates(lib):
     assert w["err_flags"] == 0
     assert w["rew"] <= 1e-4 and w["info"] <= 1e-6, w
     assert int(w["engine"].read_state("hist_len")[0]) == 10000
+    from helpers import check_incremental_state
+    valid, n = check_incremental_state(w["engine"], tag="long replay")
+    assert valid == n
+
+
+def test_incremental_normaliser_under_drift(lib):
+    import scenarios
+    print(scenarios.incremental_normaliser_under_drift(lib))
 
 
 def test_batched_mixed_locations_vs_oracle(lib):
