@@ -36,6 +36,7 @@ constexpr int kWexpMax = 6;           // |log2| range of the adaptive interval w
 constexpr int kTailCap = 128;         // values per tail band
 constexpr int kBandTarget = 40;       // a refresh narrows the bands when one holds more values than this
 constexpr int kAlphaOff = 12;         // narrowest tail band: alpha = 0.5 / 2^12 of the IQR
+constexpr int kPassJobBytes = 192;     // size of one maintenance-pass record (sdc_kernels.cu PassJob)
 constexpr int kTailRetry = 200;       // steps of plain scans before another attempt at tail sets that did not fit
 constexpr double kSpMin = 15.0, kSpMax = 21.6;   // utils/make_envs_pyenv.py:124-126
 
@@ -1035,11 +1036,15 @@ struct StepArgs {
     //   [0] unit tickets  [1] finished envs appended to reset_list  [2] units past the scalar phase
     //   [3] reset_list slots claimed by workers  [4..7] statistics: plain passes, refresh passes, by brackets, by tails
     //   [8] envs appended to pre_list  [9] pre_list_prev entries claimed by workers
+    //   [10] maintenance passes published  [11] claimed by workers
     // three counter blocks rotate: the previous step's block (ctr_prev) still holds its pre_list count
     int32_t* ctr;
     int32_t* ctr_next;
     const int32_t* ctr_prev;
     int32_t* reset_list;   // [N + slack], -1 = empty slot
+    void* pass_jobs;       // [N] records of maintenance passes (window refreshes whose result this step does not need)
+    int32_t* pass_ready;   // [N] == seq once record i is complete
+    int32_t seq;           // step tag (never 0)
     int32_t* pre_list;     // [N] envs that finish two steps from now (filled by this launch)
     const int32_t* pre_list_prev;   // the list the previous launch filled: episodes to pre-generate now
     double* metrics;

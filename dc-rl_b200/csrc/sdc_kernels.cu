@@ -185,6 +185,7 @@ struct PassJob {
     // results (written by warp 0)
     sdc::ScanResult rs;
 };
+static_assert(sizeof(PassJob) <= sdc::kPassJobBytes && sdc::kPassJobBytes % 16 == 0, "maintenance pass record size");
 struct PassShared {
     unsigned long long bar;                 // mbarrier of the bulk copy
     PassJob job;
@@ -336,15 +337,25 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {                                    // uniform across the CTA
             const int c = raw.c[j];
-            if (c > 1 && c <= sdc::kCollectCap) {
-                int p2 = 2;
-                while (p2 < c) p2 <<= 1;
+            if (c >= 1 && c <= sdc::kCollectCap) {
+                // rank sort: every thread places up to two of the collected values (broadcast reads, one barrier)
                 float* buf = scr + j * sdc::kCollectCap;
-                for (int i = c + tid; i < p2; i += kStepThreads) buf[i] = SDC_INF_F;
-                __syncthreads();
-                block_bitonic_sort(buf, p2);
+                float* out = win + j * sdc::kCollectCap;              // the staged window is no longer needed
+                float x0 = 0.f, x1 = 0.f;
+                int r0 = 0, r1 = 0;
+                const bool h0 = tid < c, h1 = tid + kStepThreads < c;
+                if (h0) x0 = buf[tid];
+                if (h1) x1 = buf[tid + kStepThreads];
+                for (int i = 0; i < c; ++i) {
+                    const float y = buf[i];
+                    r0 += (y < x0) || (y == x0 && i < tid);
+                    r1 += (y < x1) || (y == x1 && i < tid + kStepThreads);
+                }
+                if (h0) out[r0] = x0;
+                if (h1) out[r1] = x1;
             }
         }
+        __syncthreads();
         if (warp == 0) {
             sdc::ScanRequest rl;
             rl.n = n; rl.kind = J.kind; rl.shift = shift; rl.tl = tl; rl.th = th; rl.tl2 = tl2; rl.th2 = th2;
@@ -353,8 +364,10 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
             sdc::QView Ql;
             Ql.lst[0] = S.qlist + (size_t)env * 2 * sdc::kListCap; Ql.lst[1] = Ql.lst[0] + sdc::kListCap;
             Ql.a[0] = J.q_a[0]; Ql.a[1] = J.q_a[1]; Ql.m[0] = J.q_m[0]; Ql.m[1] = J.q_m[1];
-            const float* sorted[2] = {scr, scr + sdc::kCollectCap};
+            const float* sorted[2] = {win, win + sdc::kCollectCap};
             sdc::refresh_commit(S, env, rl, raw, sorted, Ql, rs, lane, 32);
+            // cursors of the re-centred brackets (a maintenance pass has no owner lane that would store them)
+            if (lane < 2 && (rs.recentred & (1 << lane))) { S.q_a[env * 2 + lane] = rs.new_a[lane]; S.q_m[env * 2 + lane] = rs.new_m[lane]; }
         }
     }
     if (tid == 0) ps.job.rs = rs;
@@ -623,67 +636,63 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         }
         __syncwarp();
         const long long tk2 = clock64();
-        // ---- window passes for the envs that need one (whole CTA per env) ----
+        // A pass whose result this step's reward does not need (the brackets still hold the quartile ranks and the tail
+        // bands still contain the fences: the refresh only restores slack for FUTURE steps) is a maintenance pass: its
+        // record goes to a global queue served by whichever CTA is free.  Only the rare env that cannot price this step
+        // without the window keeps the CTA-synchronous path.
+        const bool wants_pass = active && rq.kind != sdc::SCAN_SKIP;
+        const bool moments_needed = rq.n >= 2 && !rq.degenerate;
+        const bool slow_lane = wants_pass && ((moments_needed && !M.ok) || rq.dir[0] || rq.dir[1]);
+        const bool async_lane = wants_pass && !slow_lane;
         {
-            const unsigned slow = __ballot_sync(0xffffffffu, active && rq.kind != sdc::SCAN_SKIP);
+            const unsigned slow = __ballot_sync(0xffffffffu, wants_pass);
             const unsigned n_refresh = __popc(__ballot_sync(0xffffffffu, active && rq.kind == sdc::SCAN_REFRESH));
             const unsigned n_lists = __popc(__ballot_sync(0xffffffffu, active && (rq.rc[0] || rq.rc[1])));
             const unsigned n_tails = __popc(__ballot_sync(0xffffffffu, active && rq.kind == sdc::SCAN_REFRESH && !M.ok && rq.tails));
             if (lane == 0) {
-                ps.slow[warp] = slow;
                 if (slow) {          // statistics only
                     atomicAdd(a.ctr + 4, __popc(slow) - (int)n_refresh); atomicAdd(a.ctr + 5, (int)n_refresh);
                     atomicAdd(a.ctr + 6, (int)n_lists); atomicAdd(a.ctr + 7, (int)n_tails);
                 }
             }
         }
-        __syncthreads();                      // the step's ring / bracket / band updates of all warps are visible CTA-wide
-#pragma unroll 1
-        for (int w = 0; w < kWarpsPerBlock; ++w) {
-            unsigned mask = ps.slow[w];       // uniform across the CTA
-#pragma unroll 1
-            while (mask) {
-                const int l = __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (warp == w && lane == l) {
-                    PassJob& J = ps.job;
-                    J.env = env; J.n = rq.n; J.kind = rq.kind;
-                    J.lo = rq.lo; J.hi = rq.hi; J.shift = rq.shift; J.tl = rq.tl; J.th = rq.th; J.tl2 = rq.tl2; J.th2 = rq.th2;
-                    J.dir[0] = rq.dir[0]; J.dir[1] = rq.dir[1]; J.thr[0] = rq.thr[0]; J.thr[1] = rq.thr[1];
-                    J.rc[0] = rq.rc[0]; J.rc[1] = rq.rc[1]; J.k[0] = rq.k[0]; J.k[1] = rq.k[1];
-                    J.ca[0] = rq.ca[0]; J.ca[1] = rq.ca[1]; J.cb[0] = rq.cb[0]; J.cb[1] = rq.cb[1];
-                    J.tails = rq.tails; J.degenerate = rq.degenerate;
-                    J.q_a[0] = Q.a[0]; J.q_a[1] = Q.a[1]; J.q_m[0] = Q.m[0]; J.q_m[1] = Q.m[1];
-                }
-                __syncthreads();
-                window_pass(S, ps, win, scr, pass_phase);
-                pass_phase ^= 1u;
-                if (warp == w && lane == l) rs = ps.job.rs;
-                __syncthreads();              // the owner has its results before the next owner overwrites the slot
-            }
+        // ---- everything that does not depend on a window pass happens BEFORE the CTA meets for the passes, so the wait
+        //      for the slowest warp of the CTA is filled with work: rewards of the incremental lanes, observations, sums ----
+        {
+            const unsigned sync_mask = __ballot_sync(0xffffffffu, slow_lane);
+            if (lane == 0) ps.slow[warp] = sync_mask;
         }
-        const long long tk3 = clock64();
-        // ---- rewards, bracket cursors ----
-        double m_sum = 0.0, m_ls = 0.0, m_dc = 0.0;
-        if (active) {
-            float r3[3];
+        float r3[3] = {0.f, 0.f, 0.f};
+        if (active && !slow_lane) {
+            const int kind = rq.kind;
+            rq.kind = sdc::SCAN_SKIP;              // no pass results to apply: price the step from the incremental state
             sdc::reward_finish(S, env, rq, rs, M, en, Q, r3);
             reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
             reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
             a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
-            m_sum = (double)r3[0] + r3[1] + r3[2]; m_ls = r3[0]; m_dc = r3[1];
+            if (async_lane) {
+                // publish the maintenance pass: record first, then its tag (the pass CTA rewrites q_a / q_m / brackets /
+                // bands / moments of this env, all of which this lane has finished writing)
+                const int idx = atomicAdd(a.ctr + 10, 1);
+                PassJob J;
+                J.env = env; J.n = rq.n; J.kind = kind;
+                J.lo = rq.lo; J.hi = rq.hi; J.shift = rq.shift; J.tl = rq.tl; J.th = rq.th; J.tl2 = rq.tl2; J.th2 = rq.th2;
+                J.dir[0] = 0; J.dir[1] = 0; J.thr[0] = 0.f; J.thr[1] = 0.f;
+                J.rc[0] = rq.rc[0]; J.rc[1] = rq.rc[1]; J.k[0] = rq.k[0]; J.k[1] = rq.k[1];
+                J.ca[0] = rq.ca[0]; J.ca[1] = rq.ca[1]; J.cb[0] = rq.cb[0]; J.cb[1] = rq.cb[1];
+                J.tails = rq.tails; J.degenerate = rq.degenerate;
+                J.q_a[0] = Q.a[0]; J.q_a[1] = Q.a[1]; J.q_m[0] = Q.m[0]; J.q_m[1] = Q.m[1];
+                reinterpret_cast<PassJob*>(reinterpret_cast<unsigned char*>(a.pass_jobs) + (size_t)idx * sdc::kPassJobBytes)[0] = J;
+                __threadfence();
+                *reinterpret_cast<volatile int32_t*>(a.pass_ready + idx) = a.seq;
+            }
         }
-        const long long tk3b = clock64();
-        // ---- observations (written straight to obs / share / term_obs; the L2 merges the per-lane 4-byte stores into
-        //      full sectors), logger sums, hand-over of finished envs to the reset workers ----
+        const long long tk2b = clock64();
+        const int finished = st.terminal;
         {
-            double m[16];
-            long long tk3c = tk3b;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) m[k] = 0.0;
-            const int finished = st.terminal;
             // Observation rows go through a shared-memory tile (odd row stride: conflict-free) and leave as contiguous
             // 128-bit stores; 107 scattered 4-byte stores per env would keep the LSU busy for ~50 k cycles per unit.
+            // The tile shares its memory with the window-pass buffers (used only after the barrier below).
             float* tile = reinterpret_cast<float*>(smem_raw + kTableBytes) + (size_t)warp * 32 * kTileStride;
             if (active) {
                 RowSink sink{tile + lane * kTileStride};
@@ -714,100 +723,155 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                     fin &= fin - 1;
                     for (int k = lane; k < kObsRow; k += 32) a.term_obs[(size_t)(env0 + l) * kObsRow + k] = tile[l * kTileStride + k];
                 }
-            }
-            if (active) {
-                tk3c = clock64();
-                m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
-                m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
-                m[11] = st.overdue; m[12] = st.total_kw; m[13] = m_sum; m[14] = m_ls; m[15] = m_dc;
-            }
-            // logger sums (harl/envs/sustaindc/sustaindc_logger.py:86-101): warp reduce, one atomic per metric
-            constexpr int slot[16] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
-                                      sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
-                                      sdc::M_OVERDUE, sdc::M_TOTAL_KW, sdc::M_REWARD_SUM, sdc::M_REWARD_LS, sdc::M_REWARD_DC};
-            if (have_unit) {
+                // logger sums (harl/envs/sustaindc/sustaindc_logger.py:86-101): warp reduce, one atomic per metric
+                double m[13];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
+                for (int k = 0; k < 13; ++k) m[k] = 0.0;
+                if (active) {
+                    m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
+                    m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
+                    m[11] = st.overdue; m[12] = st.total_kw;
+                }
+                constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
+                                          sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
+                                          sdc::M_OVERDUE, sdc::M_TOTAL_KW};
+#pragma unroll
+                for (int k = 0; k < 13; ++k) {
                     const double v = warp_sum(m[k]);
                     if (lane == 0) atomicAdd(a.metrics + slot[k], v);
                 }
             }
-            // Finished envs go to the reset workers (other CTAs of this launch).  Order matters: the terminal observation
-            // is in global memory before the env is published, because the worker overwrites obs/share with the reset
-            // ones.  Only the ~5 % of units that contain a finished env pay the gpu-scope fences.
-            if (__any_sync(0xffffffffu, finished)) {
-                __threadfence();
-                if (finished) a.reset_list[atomicAdd(a.ctr + 1, 1)] = env;
-                __threadfence();
-                __syncwarp();
-            }
-            // look-ahead: envs that will finish two steps from now -> pre-generation list consumed by the next launch
-            if (active && st.step_after + 2 == S.ep_len) a.pre_list[atomicAdd(a.ctr + 8, 1)] = env;
-            if (lane == 0 && have_unit) atomicAdd(a.ctr + 2, 1);
-            if (a.phase_clocks && lane == 0 && have_unit) {
-                atomicAdd(a.phase_clocks + 8, (unsigned long long)(tk3b - tk3));    // reward_finish
-                atomicAdd(a.phase_clocks + 9, (unsigned long long)(tk3c - tk3b));   // emit_obs
+        }
+        const long long tk2c = clock64();
+        // ---- window passes for the envs that need one (whole CTA per env) ----
+        __syncthreads();                      // the step's ring / bracket / band updates of all warps are visible CTA-wide
+#pragma unroll 1
+        for (int w = 0; w < kWarpsPerBlock; ++w) {
+            unsigned mask = ps.slow[w];       // uniform across the CTA
+#pragma unroll 1
+            while (mask) {
+                const int l = __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (warp == w && lane == l) {
+                    PassJob& J = ps.job;
+                    J.env = env; J.n = rq.n; J.kind = rq.kind;
+                    J.lo = rq.lo; J.hi = rq.hi; J.shift = rq.shift; J.tl = rq.tl; J.th = rq.th; J.tl2 = rq.tl2; J.th2 = rq.th2;
+                    J.dir[0] = rq.dir[0]; J.dir[1] = rq.dir[1]; J.thr[0] = rq.thr[0]; J.thr[1] = rq.thr[1];
+                    J.rc[0] = rq.rc[0]; J.rc[1] = rq.rc[1]; J.k[0] = rq.k[0]; J.k[1] = rq.k[1];
+                    J.ca[0] = rq.ca[0]; J.ca[1] = rq.ca[1]; J.cb[0] = rq.cb[0]; J.cb[1] = rq.cb[1];
+                    J.tails = rq.tails; J.degenerate = rq.degenerate;
+                    J.q_a[0] = Q.a[0]; J.q_a[1] = Q.a[1]; J.q_m[0] = Q.m[0]; J.q_m[1] = Q.m[1];
+                }
+                __syncthreads();
+                window_pass(S, ps, win, scr, pass_phase);
+                pass_phase ^= 1u;
+                if (warp == w && lane == l) rs = ps.job.rs;
+                __syncthreads();              // the owner has its results before the next owner overwrites the slot
             }
         }
+        const long long tk3 = clock64();
+        // ---- rewards of the envs that had a pass; reward sums ----
+        if (slow_lane) {
+            sdc::reward_finish(S, env, rq, rs, M, en, Q, r3);
+            reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
+            reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
+            a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
+        }
+        if (have_unit) {
+            const double m_sum = warp_sum((double)r3[0] + r3[1] + r3[2]), m_ls = warp_sum((double)r3[0]), m_dc = warp_sum((double)r3[1]);
+            if (lane == 0) {
+                atomicAdd(a.metrics + sdc::M_REWARD_SUM, m_sum); atomicAdd(a.metrics + sdc::M_REWARD_LS, m_ls);
+                atomicAdd(a.metrics + sdc::M_REWARD_DC, m_dc);
+            }
+        }
+        // Finished envs go to the reset workers (other CTAs of this launch).  Order matters: the terminal observation
+        // is in global memory before the env is published, because the worker overwrites obs/share with the reset
+        // ones.  Only the ~5 % of units that contain a finished env pay the gpu-scope fences.
+        if (__any_sync(0xffffffffu, finished)) {
+            __threadfence();
+            if (finished) a.reset_list[atomicAdd(a.ctr + 1, 1)] = env;
+            __threadfence();
+            __syncwarp();
+        }
+        // look-ahead: envs that will finish two steps from now -> pre-generation list consumed by the next launch
+        if (active && st.step_after + 2 == S.ep_len) a.pre_list[atomicAdd(a.ctr + 8, 1)] = env;
+        __syncwarp();
+        if (lane == 0 && have_unit) { __threadfence(); atomicAdd(a.ctr + 2, 1); }     // after every publication of this unit
         if (a.phase_clocks && lane == 0 && have_unit) {
             const long long tk4 = clock64();
             atomicAdd(a.phase_clocks + 0, (unsigned long long)(tk1 - tk0));   // load shifting + data centre + battery
             atomicAdd(a.phase_clocks + 1, (unsigned long long)(tk2 - tk1));   // window append, brackets, moments, tail bands
-            atomicAdd(a.phase_clocks + 2, (unsigned long long)(tk3 - tk2));   // waiting for the CTA + window passes
-            atomicAdd(a.phase_clocks + 3, (unsigned long long)(tk4 - tk3));   // rewards, observations, metrics
+            atomicAdd(a.phase_clocks + 8, (unsigned long long)(tk2b - tk2));  // rewards of the incremental lanes
+            atomicAdd(a.phase_clocks + 9, (unsigned long long)(tk2c - tk2b)); // observations + sums
+            atomicAdd(a.phase_clocks + 2, (unsigned long long)(tk3 - tk2c));  // waiting for the CTA + window passes
+            atomicAdd(a.phase_clocks + 3, (unsigned long long)(tk4 - tk3));   // rewards after passes, hand-overs
             atomicAdd(a.phase_clocks + 4, 1ull);                              // units
             atomicMax(a.phase_clocks + 14, gtime_ns());                       // timeline: last unit done
             atomicMax(a.phase_clocks + 10, (unsigned long long)(tk4 - tk0));  // slowest unit (clocks)
-            atomicMax(a.phase_clocks + 11, (unsigned long long)(tk2 - tk0));  // slowest scalar phase
+            atomicMax(a.phase_clocks + 11, (unsigned long long)(tk2c - tk0)); // slowest unit before the barrier
         }
     }
 
-    // ---------------- episode resets: every CTA turns into a reset worker once it has no unit left ----------------
-    // CTAs beyond n_unit_ctas start here immediately, so episode generation and resets overlap with the
-    // other CTAs' units.  A worker claims the next slot of reset_list and waits until it is filled or until every unit
-    // is past its hand-over (then no further env can be appended).
+    // ---------------- workers: every CTA becomes one once it has no unit left ----------------
+    // CTAs beyond n_unit_ctas start here immediately, so episode generation, maintenance passes and resets overlap
+    // with the other CTAs' units.
     __shared__ ResetShared rsh;
     __shared__ int s_env;
     __syncthreads();
     double* runbuf = reinterpret_cast<double*>(smem_raw + kTableBytes);   // the window-pass buffers are free by now
-    // (1) pre-generation jobs published by the previous launch: independent of this step, so the CTAs without units
-    //     work on them from the first cycle on
+    // A worker always holds one ticket of the reset queue and one of the maintenance-pass queue (a ticket is a slot
+    // index; it is served as soon as the slot is filled) and takes look-ahead generation jobs -- which were published by
+    // the PREVIOUS launch and are therefore available from the first cycle on -- when neither is ready.  It leaves when
+    // every unit is past its hand-overs and its tickets lie beyond what was published.
     {
         const int n_pre = *reinterpret_cast<volatile const int32_t*>(a.ctr_prev + 8);
+        __shared__ int s_kind;                  // 0 exit, 1 reset, 2 maintenance pass, 3 generation
+        int my_reset = -1, my_pass = -1;        // thread 0 only
+        bool pre_left = n_pre > 0;
         for (;;) {
             if (threadIdx.x == 0) {
-                const int idx = atomicAdd(a.ctr + 9, 1);
-                s_env = idx < n_pre ? a.pre_list_prev[idx] : -1;
+                volatile int32_t* list = a.reset_list;
+                volatile int32_t* ready = a.pass_ready;
+                volatile int32_t* units_done = a.ctr + 2;
+                int kind = -1, env = -1;
+                while (kind < 0) {
+                    if (my_reset < 0) my_reset = atomicAdd(a.ctr + 3, 1);
+                    if (my_pass < 0) my_pass = atomicAdd(a.ctr + 11, 1);
+                    const bool all_done = *units_done >= n_units;       // read BEFORE the slots: nothing is published after it
+                    if (all_done) __threadfence();
+                    const int e = list[my_reset];
+                    if (e >= 0) { list[my_reset] = -1; my_reset = -1; kind = 1; env = e; break; }
+                    if (my_pass < N && ready[my_pass] == a.seq) { __threadfence(); env = my_pass; my_pass = -1; kind = 2; break; }
+                    if (pre_left) {
+                        const int idx = atomicAdd(a.ctr + 9, 1);
+                        if (idx < n_pre) { kind = 3; env = a.pre_list_prev[idx]; break; }
+                        pre_left = false;
+                    }
+                    if (all_done) { kind = 0; break; }
+                    __nanosleep(200);
+                }
+                s_kind = kind; s_env = env;
             }
             __syncthreads();
-            const int env = s_env;
+            const int kind = s_kind, env = s_env;
             __syncthreads();
-            if (env < 0) break;
-            pregen_one_env(S, env, runbuf, rsh);
-        }
-    }
-    // (2) resets of the envs that finished in this step
-    for (;;) {
-        if (threadIdx.x == 0) {
-            const int my = atomicAdd(a.ctr + 3, 1);
-            volatile int32_t* list = a.reset_list;
-            volatile int32_t* units_done = a.ctr + 2;
-            int env = -1;
-            for (;;) {
-                env = list[my];
-                if (env >= 0) break;
-                if (*units_done >= n_units) { __threadfence(); env = list[my]; break; }
-                __nanosleep(200);
+            if (kind == 0) break;
+            if (kind == 1) {
+                __threadfence();
+                reset_one_env(S, env, a.obs, a.share, runbuf, rsh);
+                __syncthreads();
+            } else if (kind == 2) {
+                const int* src = reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(a.pass_jobs) + (size_t)env * sdc::kPassJobBytes);
+                int* dst = reinterpret_cast<int*>(&ps.job);
+                for (int i = threadIdx.x; i < (int)(sizeof(PassJob) / 4); i += kStepThreads) dst[i] = __ldcg(src + i);
+                __syncthreads();
+                window_pass(S, ps, win, scr, pass_phase);
+                pass_phase ^= 1u;
+            } else {
+                pregen_one_env(S, env, runbuf, rsh);
+                __syncthreads();
             }
-            if (env >= 0) list[my] = -1;
-            s_env = env;
         }
-        __syncthreads();
-        const int env = s_env;
-        if (env < 0) break;
-        __threadfence();
-        reset_one_env(S, env, a.obs, a.share, runbuf, rsh);
-        __syncthreads();
     }
     if (a.phase_clocks && threadIdx.x == 0) atomicMax(a.phase_clocks + 15, gtime_ns());   // timeline: CTA done
 }
@@ -867,7 +931,8 @@ __global__ void __launch_bounds__(kSortThreads) k_rebuild(const sdc::State S) {
 // =================================================================================================
 static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& a, void* stream) {
     const int U = a.unit_envs;
-    size_t smem = (size_t)(2 * sdc::kCollectCap + S.hist_cap) * sizeof(float);         // collect scratch + the staged window
+    // collect scratch + the staged window (which also receives the sorted collections: at least 2 x kCollectCap floats)
+    size_t smem = (size_t)(2 * sdc::kCollectCap + (S.hist_cap > 2 * sdc::kCollectCap ? S.hist_cap : 2 * sdc::kCollectCap)) * sizeof(float);
     if (smem < (size_t)kWarpsPerBlock * 32 * kTileStride * sizeof(float)) smem = (size_t)kWarpsPerBlock * 32 * kTileStride * sizeof(float);   // obs tiles (same region)
     if (smem < kNormWindow * sizeof(double)) smem = kNormWindow * sizeof(double);      // reset workers reuse the region
     smem += kTableBytes;
