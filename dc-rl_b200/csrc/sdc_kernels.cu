@@ -856,6 +856,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
             const int kind = s_kind, env = s_env;
             __syncthreads();
             if (kind == 0) break;
+            const long long tw0 = clock64();
             if (kind == 1) {
                 __threadfence();
                 reset_one_env(S, env, a.obs, a.share, runbuf, rsh);
@@ -870,6 +871,11 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
             } else {
                 pregen_one_env(S, env, runbuf, rsh);
                 __syncthreads();
+            }
+            if (a.phase_clocks && threadIdx.x == 0) {
+                const int slot = kind == 1 ? 5 : (kind == 2 ? 7 : 6);            // clocks: resets, generation, passes
+                atomicAdd(a.phase_clocks + slot, (unsigned long long)(clock64() - tw0));
+                atomicAdd(a.phase_clocks + 12, 1ull << (16 * (kind - 1)));       // packed job counts (16 bits each)
             }
         }
     }

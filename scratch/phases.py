@@ -39,6 +39,9 @@ torch.cuda.synchronize(); e0.record(); eng.step_device(acts[0], obs, share, rew,
 p1 = eng.read_state("phase_clocks").astype(np.float64)
 print("single step: event %.1f us; first CTA start -> last unit done %.1f us -> last CTA done %.1f us; slowest unit %.0f clocks (scalar phase %.0f); passes %s" % (
     e0.elapsed_time(e1) * 1e3, (p1[14] - p1[13]) / 1e3, (p1[15] - p1[13]) / 1e3, p1[10], p1[11], eng.read_state("pass_stats")))
+cnt = int(p1[12]); nres, npass, ngen = cnt & 0xffff, (cnt >> 16) & 0xffff, (cnt >> 32) & 0xffff
+print("worker jobs in that step: %d resets x %.0f clk, %d passes x %.0f clk, %d generations x %.0f clk" % (
+    nres, p1[5] / max(nres, 1), npass, p1[7] / max(npass, 1), ngen, p1[6] / max(ngen, 1)))
 print("err", int(np.bitwise_or.reduce(eng.read_state("err"))), "valid tails", int((eng.read_state("tail_n").reshape(n, 2)[:, 0] >= 0).sum()))
 fc = eng.read_state("fast_cfg")
 print("alpha exp hist", np.bincount(fc & 0xff)[:14], "retry>0", int(((fc >> 8) & 0xff > 0).sum()))
