@@ -10,7 +10,8 @@ import os
 MAX_RACK_CLASSES = 32
 N_AGENTS, OBS_DIM, SHARE_DIM, INFO_STRIDE = 3, 26, 29, 64
 YEAR_STEPS, TRACE_PAD, HIST_CAP, N_METRICS = 35040, 64, 10000, 16
-LIST_CAP, TAIL_CAP = 128, 128          # sdc_core.h kListCap / kTailCap (state inspection only)
+LIST_CAP, TAIL_CAP = 128, 128
+HVAC_BINS = 4096          # sdc_core.h kListCap / kTailCap (state inspection only)
 ABI_VERSION = 1
 
 F_WORKLOAD_RANGE, F_CPU_LOAD_RANGE, F_OUTLET_DELTA, F_TRACE_DOMAIN, F_BRACKET, F_NONFINITE, F_BATTERY = (
@@ -63,6 +64,7 @@ _PROTOS = {
     "sdc_reset_host": (C.c_int, [_P, _P, _P, _P]),
     "sdc_host_buffers": (C.c_int, [_P] + [C.POINTER(_P)] * 7),
     "sdc_metrics": (C.c_int, [_P, _P, C.c_int32]),
+    "sdc_hvac_histogram": (C.c_int, [_P, _P, _P, C.c_int32]),
     "sdc_prefill_history": (C.c_int, [_P, _P, C.c_int32, C.c_int32]),
     "sdc_rebuild_brackets": (C.c_int, [_P, _P]),
     "sdc_read_state": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64]),
@@ -80,7 +82,7 @@ EXPORTS = tuple(_PROTOS)
 
 def load(path=None):
     """Loads the shared library and attaches prototypes. Raises if it is missing (no fallback)."""
-    path = path or LIB_PATH
+    path = path or os.environ.get("SDC_B200_LIB") or LIB_PATH
     if not os.path.isfile(path):
         raise ImportError(
             "dc_rl_b200: CUDA library %s not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -1048,6 +1048,8 @@ struct StepArgs {
     int32_t* pre_list;     // [N] envs that finish two steps from now (filled by this launch)
     const int32_t* pre_list_prev;   // the list the previous launch filled: episodes to pre-generate now
     double* metrics;
+    unsigned long long* hvac_hist;      // [SDC_HVAC_BINS] counts of positive HVAC power samples
+    float hvac_bins_per_kw;             // SDC_HVAC_BINS / range
     unsigned long long* phase_clocks;   // optional [16]: summed per-warp clock64 deltas of the k_step phases (diagnostics)
     int32_t unit_envs, unroll, blocks_per_sm;
 };

@@ -59,8 +59,12 @@ static const char* h2d_async(Context&, void* d, const void* s, size_t n, void* s
 static const char* d2h_async(Context&, void* d, const void* s, size_t n, void* st) {
     CU(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, (cudaStream_t)st)); return nullptr;
 }
-static const char* pinned_alloc(Context&, void** p, size_t bytes) { CU(cudaMallocHost(p, bytes ? bytes : 16)); return nullptr; }
+static const char* pinned_alloc(Context&, void** p, size_t bytes) { CU(cudaHostAlloc(p, bytes ? bytes : 16, cudaHostAllocMapped | cudaHostAllocPortable)); return nullptr; }
 static void pinned_free(Context&, void* p) { cudaFreeHost(p); }
+static bool host_memory_is_device_visible(Context& c) {
+    int uva = 0;
+    return cudaDeviceGetAttribute(&uva, cudaDevAttrUnifiedAddressing, c.device) == cudaSuccess && uva != 0;
+}
 static const char* stream_create(Context&, void** s) { cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); *s = st; return nullptr; }
 static const char* stream_sync(Context&, void* s) { CU(cudaStreamSynchronize((cudaStream_t)s)); return nullptr; }
 static const char* event_create(Context&, void** ev) { cudaEvent_t e; CU(cudaEventCreate(&e)); *ev = e; return nullptr; }
@@ -731,6 +735,11 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                     m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
                     m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
                     m[11] = st.overdue; m[12] = st.total_kw;
+                    if (st.hvac_kw > 0.0) {             // fire-and-forget reduction; the logger's p90 comes from these bins
+                        int bin = (int)(st.hvac_kw * (double)a.hvac_bins_per_kw);
+                        bin = bin < 0 ? 0 : (bin >= SDC_HVAC_BINS ? SDC_HVAC_BINS - 1 : bin);
+                        atomicAdd(a.hvac_hist + bin, 1ull);
+                    }
                 }
                 constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
                                           sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,

@@ -40,3 +40,34 @@ def gather_metrics(local_metrics, device=None):
     out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
     dist.all_gather(out, t)
     return torch.stack(out).cpu().numpy()
+
+
+def reduce_hvac_histogram(counts, device=None):
+    """Sums the ranks' HVAC power histograms (Engine.hvac_histogram): one all-reduce of 32 KB instead of gathering every
+    sample for the logger's 90th percentile (harl/envs/sustaindc/sustaindc_logger.py:98-99,152-155)."""
+    import torch
+    import torch.distributed as dist
+    c = np.asarray(counts, np.int64)
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return c.astype(np.uint64)
+    t = torch.from_numpy(c.copy())
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy().astype(np.uint64)
+
+
+def histogram_percentile(counts, range_kw, q):
+    """q-th percentile (0..100) of the histogrammed samples: linear interpolation inside the bin that holds the target
+    rank (bin width = range_kw / len(counts): 0.02 % of the range with 4096 bins)."""
+    c = np.asarray(counts, np.float64)
+    total = c.sum()
+    if total == 0:
+        return 0.0
+    target = q / 100.0 * total
+    cum = np.cumsum(c)
+    b = int(np.searchsorted(cum, target, side="left"))
+    b = min(b, len(c) - 1)
+    below = cum[b] - c[b]
+    frac = (target - below) / c[b] if c[b] > 0 else 0.0
+    return (b + frac) * range_kw / len(c)

@@ -182,6 +182,14 @@ class Engine:
         self._check(self.lib.sdc_metrics(self._h, _ptr(out), int(bool(clear))))
         return out
 
+    def hvac_histogram(self, clear=False):
+        """(counts[HVAC_BINS] uint64, range_kw): histogram of the positive dc_HVAC_total_power_kW samples since the last
+        clear, equal bins over [0, range_kw) -- what the logger's mean / max / p90 are computed from."""
+        counts = np.zeros(_lib.HVAC_BINS, np.uint64)
+        rng = C.c_double(0.0)
+        self._check(self.lib.sdc_hvac_histogram(self._h, _ptr(counts), C.byref(rng), int(bool(clear))))
+        return counts, float(rng.value)
+
     def prefill_history(self, values):
         """values: fp32 [count] (shared by all envs) or [N, count]."""
         v = np.ascontiguousarray(values, np.float32)

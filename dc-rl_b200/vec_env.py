@@ -252,6 +252,22 @@ class CudaShareVecEnv:
         return dict(zip(METRIC_NAMES, m.tolist()))
 
 
+    def hvac_power_stats(self, clear=False):
+        """mean / max / 90th percentile of the positive dc_HVAC_total_power_kW samples since the last clear, from the
+        device histogram (what SustainDCLogger.episode_log derives from its list of samples, sustaindc_logger.py:152-155).
+        max is the upper edge of the highest occupied bin."""
+        from .distributed import histogram_percentile
+        counts, rng = self.engine.hvac_histogram(clear)
+        total = float(counts.sum())
+        if total == 0:
+            return {"mean": 0.0, "max": 0.0, "p90": 0.0, "samples": 0}
+        width = rng / len(counts)
+        centres = (np.arange(len(counts)) + 0.5) * width
+        top = int(np.nonzero(counts)[0][-1])
+        return {"mean": float((centres * counts).sum() / total), "max": (top + 1) * width,
+                "p90": histogram_percentile(counts, rng, 90.0), "samples": int(total)}
+
+
 METRIC_NAMES = ("bat_total_energy_with_battery_KWh", "bat_CO2_footprint", "dc_water_usage", "ls_tasks_in_queue", "ls_tasks_dropped",
                 "dc_ITE_total_power_kW", "dc_CT_total_power_kW", "dc_Compressor_total_power_kW", "dc_HVAC_total_power_kW",
                 "env_steps", "reward_sum", "episodes", "reward_ls_sum", "reward_dc_sum", "ls_overdue_penalty", "dc_total_power_kW")

@@ -33,6 +33,7 @@ extern "C" {
 #define SDC_MAX_RACK_CLASSES 32
 #define SDC_HIST_CAP 10000      /* reward window                             utils/reward_creator.py:5 */
 #define SDC_N_METRICS 16
+#define SDC_HVAC_BINS 4096
 
 /* error codes */
 #define SDC_OK 0
@@ -157,6 +158,12 @@ int sdc_host_buffers(sdc_env* env, int32_t** actions, float** obs, float** share
 /* Running sums since the last call with clear!=0 (SustainDCLogger.per_step,
  * harl/envs/sustaindc/sustaindc_logger.py:86-101): out[SDC_N_METRICS] doubles, HOST pointer. */
 int sdc_metrics(sdc_env* env, double* out, int32_t clear);
+/* Histogram of every positive dc_HVAC_total_power_kW sample since the last clear: SDC_HVAC_BINS equal bins over
+ * [0, *range_kw) (range = the largest power upper bound of the handle's dc configs), samples beyond the range in the
+ * last bin.  Replaces the list of all samples the reference logger keeps for its mean / max / 90th percentile
+ * (harl/envs/sustaindc/sustaindc_logger.py:98-99,152-155); ranks sum their histograms (one all-reduce of 32 KB) instead
+ * of gathering the samples.  counts[SDC_HVAC_BINS] uint64 and range_kw: HOST pointers. */
+int sdc_hvac_histogram(sdc_env* env, uint64_t* counts, double* range_kw, int32_t clear);
 /* Fill every env's reward window with `count` values each (host fp32 [N][count], or [count] shared by
  * all envs when per_env==0) and rebuild the quartile brackets -- benchmark / resume helper. */
 int sdc_prefill_history(sdc_env* env, const float* values, int32_t count, int32_t per_env);

@@ -32,6 +32,7 @@ static const char* h2d_async(Context&, void* d, const void* s, size_t n, void*) 
 static const char* d2h_async(Context&, void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return nullptr; }
 static const char* pinned_alloc(Context&, void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? nullptr : "malloc"; }
 static void pinned_free(Context&, void* p) { free(p); }
+static bool host_memory_is_device_visible(Context&) { return true; }
 static const char* stream_create(Context&, void** s) { *s = nullptr; return nullptr; }
 static const char* stream_sync(Context&, void*) { return nullptr; }
 static const char* sync(Context&) { return nullptr; }
@@ -148,6 +149,11 @@ static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs&
         M[sdc::M_TASKS_IN_QUEUE] += st.tasks_in_queue; M[sdc::M_TASKS_DROPPED] += st.tasks_dropped;
         M[sdc::M_ITE_KW] += st.ite_kw; M[sdc::M_CT_KW] += st.ct_kw; M[sdc::M_COMP_KW] += st.comp_kw; M[sdc::M_HVAC_KW] += st.hvac_kw;
         M[sdc::M_STEPS] += 1; M[sdc::M_EPISODES] += st.terminal;
+        if (st.hvac_kw > 0.0) {
+            int bin = (int)(st.hvac_kw * (double)a.hvac_bins_per_kw);
+            bin = bin < 0 ? 0 : (bin >= SDC_HVAC_BINS ? SDC_HVAC_BINS - 1 : bin);
+            a.hvac_hist[bin] += 1;
+        }
         const float* r = a.rew + (size_t)env * 3;
         M[sdc::M_REWARD_SUM] += (double)r[0] + r[1] + r[2]; M[sdc::M_REWARD_LS] += r[0]; M[sdc::M_REWARD_DC] += r[1];
         M[sdc::M_OVERDUE] += st.overdue; M[sdc::M_TOTAL_KW] += st.total_kw;

@@ -128,6 +128,29 @@ def test_info_rows_expose_every_key_the_runners_read(lib):
     v.close()
 
 
+def test_hvac_histogram_matches_sample_percentile(lib):
+    """the logger's mean / max / p90 of the positive HVAC power samples come from a fixed-bin device histogram."""
+    g, cfg, v, stage = _vec_from_golden(lib, "ny_m3_s1", 8)
+    stage(v.engine, g, 0, np.arange(8, dtype=np.int32))
+    v.reset()
+    rng = np.random.RandomState(3)
+    samples = []
+    for _ in range(60):
+        _, _, _, _, infos, _ = v.step(rng.randint(0, 3, size=(8, 3, 1)))
+        samples.append(np.array(infos.column("dc_HVAC_total_power_kW"), np.float64))
+    samples = np.concatenate(samples)
+    samples = samples[samples > 0]
+    counts, range_kw = v.engine.hvac_histogram()
+    width = range_kw / len(counts)
+    assert int(counts.sum()) == len(samples) and range_kw > samples.max()
+    st = v.hvac_power_stats()
+    assert abs(st["p90"] - np.percentile(samples, 90)) <= 2 * width
+    assert abs(st["mean"] - samples.mean()) <= width and 0 <= st["max"] - samples.max() <= width
+    v.engine.hvac_histogram(clear=True)
+    assert v.engine.hvac_histogram()[0].sum() == 0
+    v.close()
+
+
 def test_make_env_month_and_seed_rules(lib):
     """harl/utils/envs_tools.py:56-67,95: month by rank unless pinned; seed + rank*1000 / seed*50000 + rank*10000."""
     from dc_rl_b200.dc_config import start_day_range
@@ -187,7 +210,7 @@ import os, sys
 sys.path[:0] = [{repo!r}, {repo!r} + "/tests"]
 import numpy as np, torch.distributed as dist
 import hostsim_build
-from dc_rl_b200.distributed import gather_metrics, make_sharded_env, shard_range
+from dc_rl_b200.distributed import gather_metrics, make_sharded_env, reduce_hvac_histogram, shard_range
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 rank = dist.get_rank()
 args = {{"location": "ny", "traces": "synthetic", "days_per_episode": 1, "nonoverlapping_shared_obs_space": True}}
@@ -201,7 +224,9 @@ for s in range(40):
     o, _, r, d, _, _ = env.step(acts[s, lo:hi])
     outs.append((o.copy(), r.copy()))
 allm = gather_metrics(env.engine.metrics())
-np.savez({out!r} + "/rank%d.npz" % rank, obs=np.stack([o for o, _ in outs]), rew=np.stack([r for _, r in outs]), metrics=allm, lo=lo, hi=hi)
+hist = reduce_hvac_histogram(env.engine.hvac_histogram()[0])
+np.savez({out!r} + "/rank%d.npz" % rank, obs=np.stack([o for o, _ in outs]), rew=np.stack([r for _, r in outs]), metrics=allm, lo=lo, hi=hi,
+         hist=hist)
 dist.destroy_process_group()
 """
 
@@ -238,5 +263,6 @@ def test_two_rank_sharding_is_equivalent_to_one_process(lib, tmp_path):
         assert np.array_equal(z["obs"], obs[:, lo:hi]) and np.array_equal(z["rew"], rew[:, lo:hi])
         assert z["metrics"].shape == (2, 16)
         total = z["metrics"].sum(0)
+        assert np.array_equal(z["hist"], env.engine.hvac_histogram()[0])       # all-reduced histogram == single process
     assert np.allclose(total, env.engine.metrics(), rtol=1e-12)
     assert shard_range(10, 0, 3) == (0, 4) and shard_range(10, 2, 3) == (7, 10)
