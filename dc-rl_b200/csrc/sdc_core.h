@@ -706,6 +706,14 @@ SDC_HDN void reward_prepare(const State& S, int env, double energy, int len, int
     const int n = len;
     rq.n = n; rq.degenerate = 0; rq.e = e; rq.o = o; rq.evict = evict;
     const uint32_t fc = S.fast_cfg[env];
+    // The ends of both brackets are read together, before any store to the lists: almost every step only compares
+    // against them (each a dependent L2 / DRAM round trip otherwise).
+    float first[2], last[2];
+    for (int j = 0; j < 2; ++j) {
+        const int m = Q.m[j];
+        first[j] = m > 0 ? Q.lst[j][0] : 0.f;
+        last[j] = m > 0 ? Q.lst[j][m - 1] : 0.f;
+    }
     double qv[2] = {0.0, 0.0};
     for (int j = 0; j < 2; ++j) {
         float* lst = Q.lst[j];
@@ -715,8 +723,15 @@ SDC_HDN void reward_prepare(const State& S, int env, double energy, int len, int
         const int k = num / 4;                                   // np.percentile 'linear': idx = (n-1)*p
         const double frac = (double)(num % 4) * 0.25;
         rq.k[j] = k;
-        if (evict) list_remove(lst, a, m, o, err);
+        bool touched = false;                                    // list contents changed: the cached ends are stale
+        if (evict) {
+            if (m > 0 && o < first[j]) a -= 1;
+            else if (m > 0 && o > last[j]) { }
+            else { list_remove(lst, a, m, o, err); touched = true; }
+        }
         if (m == 0) { lst[0] = e; a = 0; m = 1; }                // first value ever
+        else if (!touched && e < first[j] && a > 0) a += 1;
+        else if (!touched && e > last[j] && a + m < n - 1) { }   // ranks above the list, list not at the top
         else list_insert(lst, a, m, e, n, k);
         if (n >= 2) {
             const int r = k - a;
@@ -757,8 +772,14 @@ SDC_HDN void reward_prepare(const State& S, int env, double energy, int len, int
 // outer threshold (TL2 <= x < TL, TH < x <= TH2; the fence lies inside the band) are kept individually, those
 // beyond the outer threshold only as (count, sum, sum of squares) -- they are clipped whatever the fence does inside
 // the band.  So a large outlier population (e.g. after a regime change) costs nothing per step.
+SDC_HD void tail_load8(const float* p, int cnt, int i0, float pad, float* xs) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xs[u] = (i0 + u < cnt) ? p[(size_t)(i0 + u) * kTailStride] : pad;
+}
+// `first8`: the band's first batch, loaded by the caller (so that both bands' first rows are in flight together)
 SDC_HD void tail_side(float* p, int& cnt, int& agg_n, double& agg_s1, double& agg_s2, bool below, float t_in, float t_out,
-                      double fence, double c0, float e, float o, bool evict, double& c1, double& c2, bool& valid, int& err) {
+                      double fence, double c0, float e, float o, bool evict, double& c1, double& c2, bool& valid, int& err,
+                      const float* first8) {
     const double yf = fence - c0;
     // far tail: clipped to the fence as a whole
     const bool e_far = below ? e < t_out : e > t_out, o_far = evict && (below ? o < t_out : o > t_out);
@@ -773,8 +794,12 @@ SDC_HD void tail_side(float* p, int& cnt, int& agg_n, double& agg_s1, double& ag
     int idx = -1;
     for (int i0 = 0; i0 < cnt; i0 += 8) {
         float xs[8];
+        if (i0 == 0) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) xs[u] = (i0 + u < cnt) ? p[(size_t)(i0 + u) * kTailStride] : pad;
+            for (int u = 0; u < 8; ++u) xs[u] = first8[u];
+        } else {
+            tail_load8(p, cnt, i0, pad, xs);
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const float x = xs[u];
@@ -800,24 +825,30 @@ SDC_HD void tail_side(float* p, int& cnt, int& agg_n, double& agg_s1, double& ag
 SDC_HDN void reward_plan(const State& S, int env, ScanRequest& rq, Moments& M) {
     const float e = rq.e, o = rq.o;
     const bool evict = rq.evict != 0;
+    // all loads of the env's incremental state first (independent, in flight together), stores afterwards
     const double c0 = S.mom_c0[env];
     double s1 = S.mom_s1[env], s2 = S.mom_s2[env];
+    int nl = S.tail_n[2 * env], nh = S.tail_n[2 * env + 1];
+    uint32_t fc = S.fast_cfg[env];
+    const float tl = S.tail_thr[4 * env], th = S.tail_thr[4 * env + 1], tl2 = S.tail_thr[4 * env + 2], th2 = S.tail_thr[4 * env + 3];
+    int al = S.agg_n[2 * env], ah = S.agg_n[2 * env + 1];
+    double al1 = S.agg_s[4 * env], al2 = S.agg_s[4 * env + 1], ah1 = S.agg_s[4 * env + 2], ah2 = S.agg_s[4 * env + 3];
     { const double y = (double)e - c0; s1 += y; s2 = fma(y, y, s2); }
     if (evict) { const double y = (double)o - c0; s1 -= y; s2 = fma(-y, y, s2); }
     S.mom_s1[env] = s1; S.mom_s2[env] = s2;
-    int nl = S.tail_n[2 * env], nh = S.tail_n[2 * env + 1];
-    uint32_t fc = S.fast_cfg[env];
     bool valid = nl >= 0;
     M.ok = 0; M.c0 = c0; M.c1 = 0.0; M.c2 = 0.0;
     if (valid) {
-        const float tl = S.tail_thr[4 * env], th = S.tail_thr[4 * env + 1], tl2 = S.tail_thr[4 * env + 2], th2 = S.tail_thr[4 * env + 3];
-        int al = S.agg_n[2 * env], ah = S.agg_n[2 * env + 1];
-        double al1 = S.agg_s[4 * env], al2 = S.agg_s[4 * env + 1], ah1 = S.agg_s[4 * env + 2], ah2 = S.agg_s[4 * env + 3];
         const double lo = rq.lo64, hi = rq.hi64;
         double c1 = 0.0, c2 = 0.0;
         int err = 0;
-        tail_side(tail_ptr(S, env, 0), nl, al, al1, al2, true, tl, tl2, lo, c0, e, o, evict, c1, c2, valid, err);
-        tail_side(tail_ptr(S, env, 1), nh, ah, ah1, ah2, false, th, th2, hi, c0, e, o, evict, c1, c2, valid, err);
+        float* p_lo = tail_ptr(S, env, 0);
+        float* p_hi = tail_ptr(S, env, 1);
+        float x_lo[8], x_hi[8];
+        tail_load8(p_lo, nl, 0, SDC_INF_F, x_lo);
+        tail_load8(p_hi, nh, 0, -SDC_INF_F, x_hi);
+        tail_side(p_lo, nl, al, al1, al2, true, tl, tl2, lo, c0, e, o, evict, c1, c2, valid, err, x_lo);
+        tail_side(p_hi, nh, ah, ah1, ah2, false, th, th2, hi, c0, e, o, evict, c1, c2, valid, err, x_hi);
         if (err) flag_error(S, env, err);
         if (!valid) { nl = -1; nh = -1; }
         S.tail_n[2 * env] = nl; S.tail_n[2 * env + 1] = nh;
@@ -1051,7 +1082,7 @@ struct StepArgs {
     unsigned long long* hvac_hist;      // [SDC_HVAC_BINS] counts of positive HVAC power samples
     float hvac_bins_per_kw;             // SDC_HVAC_BINS / range
     unsigned long long* phase_clocks;   // optional [16]: summed per-warp clock64 deltas of the k_step phases (diagnostics)
-    int32_t unit_envs, unroll, blocks_per_sm;
+    int32_t unit_envs, blocks_per_sm;
 };
 
 // HARL shared observation (harl/envs/sustaindc/harlsustaindc_env.py:78-85): ls[0:26] | dc[11] | dc[13] |

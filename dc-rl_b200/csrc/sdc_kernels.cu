@@ -193,7 +193,7 @@ static_assert(sizeof(PassJob) <= sdc::kPassJobBytes && sdc::kPassJobBytes % 16 =
 struct PassShared {
     unsigned long long bar;                 // mbarrier of the bulk copy
     PassJob job;
-    int fill[4];                            // slots handed out: lower band, upper band, collect list 0, collect list 1
+    int fill[5];                            // slots handed out: lower band, upper band, collect list 0, collect list 1, hit list
     float red_f[kWarpsPerBlock][4];         // s1, s2, ext0, ext1
     double red_d[kWarpsPerBlock][6];        // S1, S2, far sums
     int red_i[kWarpsPerBlock][6];           // cnt0, cnt1, below0, below1, far counts
@@ -242,7 +242,7 @@ __device__ __forceinline__ void block_bitonic_sort(float* buf, int p2) {
 // env's band arrays) with the far-tail aggregates, all values inside the re-centring intervals of the brackets (into
 // `scr`, then sorted) and the single-rank fallback -- then warp 0 commits the env's new incremental state.
 // `win` = hist_cap floats of shared memory.  Called by all threads of the CTA; `phase` = parity of the mbarrier.
-__device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, float* win, float* scr, unsigned phase) {
+__device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, float* win, float* scr, float* hits, int hit_cap, unsigned phase) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PassJob& J = ps.job;
     const int n = J.n, env = J.env;
@@ -253,7 +253,7 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
         mbar_expect_tx(&ps.bar, bytes);
         tma_load_1d(win, S.hist + (size_t)env * S.hist_cap, bytes, &ps.bar);
     }
-    if (tid < 4) ps.fill[tid] = 0;
+    if (tid < 5) ps.fill[tid] = 0;
     const float lo = J.lo, hi = J.hi, shift = J.shift;
     const float tl = J.tl, th = J.th, tl2 = J.tl2, th2 = J.th2;
     const int dir0 = J.dir[0], dir1 = J.dir[1];
@@ -270,30 +270,44 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
     int cnt0 = 0, cnt1 = 0, below0 = 0, below1 = 0, far_n0 = 0, far_n1 = 0;
     float ext0 = dir0 == sdc::SCAN_ABOVE ? SDC_INF_F : -SDC_INF_F, ext1 = dir1 == sdc::SCAN_ABOVE ? SDC_INF_F : -SDC_INF_F;
     double far_a0 = 0.0, far_b0 = 0.0, far_a1 = 0.0, far_b1 = 0.0;
-    __syncthreads();                                                     // fill[] zeroed
-    mbar_wait(&ps.bar, phase);                                           // the window is in shared memory
-    // Per value: accumulate + one combined "is it interesting" test; the rare hits (a few hundred of 10 000) take the
-    // slow path, where shared-memory atomics hand out the slots (the sets are unordered).  Conflict-free LDS.
+    if (warp == 0) mbar_wait(&ps.bar, phase);                            // one warp polls; the others sleep at the barrier
+    __syncthreads();                                                     // the window is in shared memory, fill[] zeroed
+    // Per value: accumulate + one combined "is it interesting" test.  The rare hits (a few hundred of 10 000) are only
+    // parked in a shared-memory list inside the loop -- with ~5 % hits nearly every warp iteration contains one, and a
+    // divergent 80-instruction classification per iteration tripled the cost of the scan -- and classified densely
+    // afterwards (shared-memory atomics hand out the slots of the bands / collections; the sets are unordered).
+    auto classify = [&](float x) {
+        const double y = (double)x - c0;
+        if (dir0 | dir1) {
+            if (dir0 == sdc::SCAN_BELOW && x < thr0) { cnt0 += 1; ext0 = fmaxf(ext0, x); }
+            if (dir0 == sdc::SCAN_ABOVE && x > thr0) { cnt0 += 1; ext0 = fminf(ext0, x); }
+            if (dir1 == sdc::SCAN_BELOW && x < thr1) { cnt1 += 1; ext1 = fmaxf(ext1, x); }
+            if (dir1 == sdc::SCAN_ABOVE && x > thr1) { cnt1 += 1; ext1 = fminf(ext1, x); }
+        }
+        if (x < tl2) { far_n0 += 1; far_a0 += y; far_b0 = fma(y, y, far_b0); }
+        else if (x < tl) { const int pos = atomicAdd(&ps.fill[0], 1); if (pos < sdc::kTailCap) tail_lo[(size_t)pos * sdc::kTailStride] = x; }
+        if (x > th2) { far_n1 += 1; far_a1 += y; far_b1 = fma(y, y, far_b1); }
+        else if (x > th) { const int pos = atomicAdd(&ps.fill[1], 1); if (pos < sdc::kTailCap) tail_hi[(size_t)pos * sdc::kTailStride] = x; }
+        if (x >= ca0 && x <= cb0) { const int pos = atomicAdd(&ps.fill[2], 1); if (pos < sdc::kCollectCap) scr[pos] = x; }
+        if (x >= ca1 && x <= cb1) { const int pos = atomicAdd(&ps.fill[3], 1); if (pos < sdc::kCollectCap) scr[sdc::kCollectCap + pos] = x; }
+    };
 #pragma unroll 4
     for (int i = tid; i < n; i += kStepThreads) {
         const float x = win[i];
         const float d = fminf(fmaxf(x, lo), hi) - shift;
         s1 += d; s2 = fmaf(d, d, s2);
-        const double y = (double)x - c0;
-        if (refresh) { S1 += y; S2 = fma(y, y, S2); }
+        if (refresh) { const double y = (double)x - c0; S1 += y; S2 = fma(y, y, S2); }
         below0 += x < ca0; below1 += x < ca1;
         if (x < quiet_lo || x > quiet_hi || (x >= ca0 && x <= cb0) || (x >= ca1 && x <= cb1)) {
-            if (dir0 == sdc::SCAN_BELOW && x < thr0) { cnt0 += 1; ext0 = fmaxf(ext0, x); }
-            if (dir0 == sdc::SCAN_ABOVE && x > thr0) { cnt0 += 1; ext0 = fminf(ext0, x); }
-            if (dir1 == sdc::SCAN_BELOW && x < thr1) { cnt1 += 1; ext1 = fmaxf(ext1, x); }
-            if (dir1 == sdc::SCAN_ABOVE && x > thr1) { cnt1 += 1; ext1 = fminf(ext1, x); }
-            if (x < tl2) { far_n0 += 1; far_a0 += y; far_b0 = fma(y, y, far_b0); }
-            else if (x < tl) { const int pos = atomicAdd(&ps.fill[0], 1); if (pos < sdc::kTailCap) tail_lo[(size_t)pos * sdc::kTailStride] = x; }
-            if (x > th2) { far_n1 += 1; far_a1 += y; far_b1 = fma(y, y, far_b1); }
-            else if (x > th) { const int pos = atomicAdd(&ps.fill[1], 1); if (pos < sdc::kTailCap) tail_hi[(size_t)pos * sdc::kTailStride] = x; }
-            if (x >= ca0 && x <= cb0) { const int pos = atomicAdd(&ps.fill[2], 1); if (pos < sdc::kCollectCap) scr[pos] = x; }
-            if (x >= ca1 && x <= cb1) { const int pos = atomicAdd(&ps.fill[3], 1); if (pos < sdc::kCollectCap) scr[sdc::kCollectCap + pos] = x; }
+            const int pos = atomicAdd(&ps.fill[4], 1);
+            if (pos < hit_cap) hits[pos] = x; else classify(x);
         }
+    }
+    __syncthreads();
+    {
+        const int n_hits = min(ps.fill[4], hit_cap);
+#pragma unroll 1
+        for (int i = tid; i < n_hits; i += kStepThreads) classify(hits[i]);
     }
     // ---- block reduction: warp shuffles, then the per-warp partials through shared memory ----
     s1 = warp_sum(s1); s2 = warp_sum(s2);
@@ -342,21 +356,28 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
         for (int j = 0; j < 2; ++j) {                                    // uniform across the CTA
             const int c = raw.c[j];
             if (c >= 1 && c <= sdc::kCollectCap) {
-                // rank sort: every thread places up to two of the collected values (broadcast reads, one barrier)
+                // rank sort: every thread places up to two of the collected values (broadcast reads, one barrier).  Ties are
+                // ordered by slot, so the ranks are a permutation.
                 float* buf = scr + j * sdc::kCollectCap;
                 float* out = win + j * sdc::kCollectCap;              // the staged window is no longer needed
-                float x0 = 0.f, x1 = 0.f;
-                int r0 = 0, r1 = 0;
                 const bool h0 = tid < c, h1 = tid + kStepThreads < c;
-                if (h0) x0 = buf[tid];
-                if (h1) x1 = buf[tid + kStepThreads];
-                for (int i = 0; i < c; ++i) {
-                    const float y = buf[i];
-                    r0 += (y < x0) || (y == x0 && i < tid);
-                    r1 += (y < x1) || (y == x1 && i < tid + kStepThreads);
+                const float x0 = h0 ? buf[tid] : 0.f;
+                int r0 = 0;
+                if (c <= kStepThreads) {
+#pragma unroll 4
+                    for (int i = 0; i < c; ++i) { const float y = buf[i]; r0 += (y < x0) | ((y == x0) & (i < tid)); }
+                } else {
+                    const float x1 = h1 ? buf[tid + kStepThreads] : 0.f;
+                    int r1 = 0;
+#pragma unroll 2
+                    for (int i = 0; i < c; ++i) {
+                        const float y = buf[i];
+                        r0 += (y < x0) | ((y == x0) & (i < tid));
+                        r1 += (y < x1) | ((y == x1) & (i < tid + kStepThreads));
+                    }
+                    if (h1) out[r1] = x1;
                 }
                 if (h0) out[r0] = x0;
-                if (h1) out[r1] = x1;
             }
         }
         __syncthreads();
@@ -556,7 +577,6 @@ __global__ void __launch_bounds__(kResetThreads) k_reset(const sdc::State S, con
 // =================================================================================================
 // k_step
 // =================================================================================================
-template <int UNROLL>
 __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, const StepArgs a, const int n_unit_ctas) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -583,6 +603,9 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
     }
     float* scr = reinterpret_cast<float*>(smem_raw + kTableBytes);      // [2][kCollectCap] collect scratch of the window pass
     float* win = scr + 2 * sdc::kCollectCap;                            // [hist_cap] the staged window
+    const int win_floats = S.hist_cap > 2 * sdc::kCollectCap ? S.hist_cap : 2 * sdc::kCollectCap;
+    float* hits = win + win_floats;                                     // parked hits of a pass: the rest of the region the obs tiles use
+    const int hit_cap = kWarpsPerBlock * 32 * kTileStride - 2 * sdc::kCollectCap - win_floats;
     unsigned pass_phase = 0;
     const int N = S.n_envs;
     const int n_units = (N + U - 1) / U;
@@ -693,6 +716,31 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         }
         const long long tk2b = clock64();
         const int finished = st.terminal;
+        if (have_unit) {
+            // logger sums (harl/envs/sustaindc/sustaindc_logger.py:86-101): warp reduce, one atomic per metric.  Done while
+            // the step's results are still in registers (after the long observation code they come back from spills).
+            double m[13];
+#pragma unroll
+            for (int k = 0; k < 13; ++k) m[k] = 0.0;
+            if (active) {
+                m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
+                m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
+                m[11] = st.overdue; m[12] = st.total_kw;
+                if (st.hvac_kw > 0.0) {             // fire-and-forget reduction; the logger's p90 comes from these bins
+                    int bin = (int)(st.hvac_kw * (double)a.hvac_bins_per_kw);
+                    bin = bin < 0 ? 0 : (bin >= SDC_HVAC_BINS ? SDC_HVAC_BINS - 1 : bin);
+                    atomicAdd(a.hvac_hist + bin, 1ull);
+                }
+            }
+            constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
+                                      sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
+                                      sdc::M_OVERDUE, sdc::M_TOTAL_KW};
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {
+                const double v = warp_sum(m[k]);
+                if (lane == 0) atomicAdd(a.metrics + slot[k], v);
+            }
+        }
         {
             // Observation rows go through a shared-memory tile (odd row stride: conflict-free) and leave as contiguous
             // 128-bit stores; 107 scattered 4-byte stores per env would keep the LSU busy for ~50 k cycles per unit.
@@ -727,28 +775,6 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                     fin &= fin - 1;
                     for (int k = lane; k < kObsRow; k += 32) a.term_obs[(size_t)(env0 + l) * kObsRow + k] = tile[l * kTileStride + k];
                 }
-                // logger sums (harl/envs/sustaindc/sustaindc_logger.py:86-101): warp reduce, one atomic per metric
-                double m[13];
-#pragma unroll
-                for (int k = 0; k < 13; ++k) m[k] = 0.0;
-                if (active) {
-                    m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
-                    m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
-                    m[11] = st.overdue; m[12] = st.total_kw;
-                    if (st.hvac_kw > 0.0) {             // fire-and-forget reduction; the logger's p90 comes from these bins
-                        int bin = (int)(st.hvac_kw * (double)a.hvac_bins_per_kw);
-                        bin = bin < 0 ? 0 : (bin >= SDC_HVAC_BINS ? SDC_HVAC_BINS - 1 : bin);
-                        atomicAdd(a.hvac_hist + bin, 1ull);
-                    }
-                }
-                constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
-                                          sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
-                                          sdc::M_OVERDUE, sdc::M_TOTAL_KW};
-#pragma unroll
-                for (int k = 0; k < 13; ++k) {
-                    const double v = warp_sum(m[k]);
-                    if (lane == 0) atomicAdd(a.metrics + slot[k], v);
-                }
             }
         }
         const long long tk2c = clock64();
@@ -772,7 +798,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                     J.q_a[0] = Q.a[0]; J.q_a[1] = Q.a[1]; J.q_m[0] = Q.m[0]; J.q_m[1] = Q.m[1];
                 }
                 __syncthreads();
-                window_pass(S, ps, win, scr, pass_phase);
+                window_pass(S, ps, win, scr, hits, hit_cap, pass_phase);
                 pass_phase ^= 1u;
                 if (warp == w && lane == l) rs = ps.job.rs;
                 __syncthreads();              // the owner has its results before the next owner overwrites the slot
@@ -875,7 +901,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                 int* dst = reinterpret_cast<int*>(&ps.job);
                 for (int i = threadIdx.x; i < (int)(sizeof(PassJob) / 4); i += kStepThreads) dst[i] = __ldcg(src + i);
                 __syncthreads();
-                window_pass(S, ps, win, scr, pass_phase);
+                window_pass(S, ps, win, scr, hits, hit_cap, pass_phase);
                 pass_phase ^= 1u;
             } else {
                 pregen_one_env(S, env, runbuf, rsh);
@@ -968,9 +994,7 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     }
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(c.device));
-    if (a.unroll == 4) k_step<4><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas);
-    else if (a.unroll == 16) k_step<16><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas);
-    else k_step<8><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas);
+    k_step<<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas);
     CU(cudaGetLastError());
     return nullptr;
 }
@@ -1003,9 +1027,7 @@ static const char* launch_rebuild(Context&, const sdc::State& S, void* stream) {
 }
 
 static const char* set_kernel_attributes() {
-    CU(cudaFuncSetAttribute(k_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_step<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_step<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_rebuild, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     return nullptr;
 }
