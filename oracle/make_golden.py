@@ -60,8 +60,25 @@ def _reset_record(env, t_ep):
                 ci_max30=float(np.max(cm.carbon_smooth[t0:t0 + 2880])))
 
 
-def record_trajectory(name, cfg, seed, n_steps, compact=False):
-    env = live_ref.fresh_env(dict(cfg))
+def record_trajectory(name, cfg, seed, n_steps, compact=False, dc_geometry=None):
+    """dc_geometry = (rows, racks_per_row, cpus_per_rack): run the reference on the builder-authored geometry of
+    dc_rl_b200.dc_config.synthetic_dc_config (BASELINE config 3: 25 racks x 40 CPUs) instead of utils/dc_config.json.
+    The reference reader joins its utils/ directory with `dc_config_file`, so an absolute path selects our JSON."""
+    live_cfg = dict(cfg)
+    if dc_geometry is not None:
+        import tempfile
+        from dc_rl_b200.dc_config import synthetic_dc_config
+        tmp = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+        # the reference reader wants every key of its own file: start from it and overlay the synthetic geometry
+        with open(os.path.join(live_ref.REFERENCE_ROOT, "utils", "dc_config.json")) as f:
+            full = json.load(f)
+        for section, values in synthetic_dc_config(*dc_geometry).items():
+            full.setdefault(section, {}).update(values)
+        json.dump(full, tmp)
+        tmp.close()
+        live_cfg["dc_config_file"] = tmp.name
+        cfg = dict(cfg, dc_geometry=list(dc_geometry))
+    env = live_ref.fresh_env(live_cfg)
     t_ep = cfg["days_per_episode"] * 96
     random.seed(seed)
     np.random.seed(seed)
@@ -200,6 +217,9 @@ def known_answers():
 
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--geometry-only" in sys.argv:       # adds the non-default geometry trajectory without rewriting the other fixtures
+        record_trajectory("ny_m6_dc25x200", {"location": "ny", "month": 6, "days_per_episode": 2}, seed=5, n_steps=450, dc_geometry=(5, 5, 200))
+        return
     dump_locations()
     known_answers()
     base = {"location": "ny", "month": 0, "days_per_episode": 7}
@@ -209,6 +229,10 @@ def main():
     record_trajectory("wa_m9_s3", dict(base, location="wa", month=9, days_per_episode=2), seed=3, n_steps=500)
     # long run: reward history saturates at 10 000 samples (utils/reward_creator.py:5)
     record_trajectory("ny_m6_long", dict(base, month=6), seed=4, n_steps=11000, compact=True)
+    # non-default geometry: 25 racks (5 x 5) of 200 CPUs, builder-authored JSON.  (BASELINE config 3 names 25 racks x 40
+    # CPUs; the reference itself refuses that geometry: racks that small trip its outlet-temperature guard,
+    # envs/datacenter.py:295-300.)
+    record_trajectory("ny_m6_dc25x200", dict(base, month=6, days_per_episode=2), seed=5, n_steps=450, dc_geometry=(5, 5, 200))
 
 
 if __name__ == "__main__":

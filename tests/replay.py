@@ -24,7 +24,11 @@ def scaled_err(a, b):
 
 def make_engine(g, lib, n_envs=1, **kw):
     cfg = traj_cfg(g)
-    params, _ = size_datacenter(cfg["location"])
+    dc_cfg = None
+    if "dc_geometry" in cfg:                    # builder-authored geometry (dc_config.synthetic_dc_config)
+        from dc_rl_b200.dc_config import synthetic_dc_config
+        dc_cfg = synthetic_dc_config(*cfg["dc_geometry"])
+    params, _ = size_datacenter(cfg["location"], dc_cfg)
     return Engine(n_envs, [location_traces(cfg["location"])], [params], months=cfg["month"],
                   days_per_episode=cfg["days_per_episode"], lib=lib, **kw)
 

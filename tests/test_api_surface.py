@@ -151,6 +151,24 @@ def test_hvac_histogram_matches_sample_percentile(lib):
     v.close()
 
 
+def test_small_rack_geometry_trips_the_outlet_guard(lib):
+    """BASELINE config 3 names 25 racks x 40 CPUs.  The reference refuses that geometry: racks that small heat the air by
+    less than 2 C and `compute_datacenter_IT_load_outlet_temp` raises (envs/datacenter.py:295-300; reproduced with the live
+    reference while minting the goldens).  Here the same condition sets SDC_F_OUTLET_DELTA on the env and the batch goes
+    on; 25 racks x 200 CPUs is the non-default geometry pinned against the live reference (traj_ny_m6_dc25x200)."""
+    from dc_rl_b200.dc_config import size_datacenter, synthetic_dc_config
+    from dc_rl_b200.engine import Engine
+    from replay import location_traces
+    for cpus, flagged in ((40, True), (200, False)):
+        params, _ = size_datacenter("ny", synthetic_dc_config(5, 5, cpus))
+        eng = Engine(4, [location_traces("ny")], [params], months=6, days_per_episode=1, lib=lib)
+        eng.reset_host()
+        for _ in range(3):
+            eng.step_host(np.ones((4, 3), np.int32))
+        assert bool((eng.read_state("err") & 0x4).all()) == flagged
+        eng.close()
+
+
 def test_make_env_month_and_seed_rules(lib):
     """harl/utils/envs_tools.py:56-67,95: month by rank unless pinned; seed + rank*1000 / seed*50000 + rank*10000."""
     from dc_rl_b200.dc_config import start_day_range

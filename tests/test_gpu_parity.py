@@ -18,7 +18,7 @@ def lib():
     return _lib.load()
 
 
-@pytest.mark.parametrize("name", ["ny_m0_s0", "ny_m3_s1", "az_m6_s2", "wa_m9_s3"])
+@pytest.mark.parametrize("name", ["ny_m0_s0", "ny_m3_s1", "az_m6_s2", "wa_m9_s3", "ny_m6_dc25x200"])
 def test_golden_replay_single_env(lib, name):
     from replay import replay
     w = replay(name, lib)

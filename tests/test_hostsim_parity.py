@@ -14,7 +14,7 @@ def lib():
     return hostsim_build.load()
 
 
-@pytest.mark.parametrize("name", ["ny_m0_s0", "ny_m3_s1", "az_m6_s2", "wa_m9_s3"])
+@pytest.mark.parametrize("name", ["ny_m0_s0", "ny_m3_s1", "az_m6_s2", "wa_m9_s3", "ny_m6_dc25x200"])
 def test_replay_matches_live_reference(lib, name):
     w = replay(name, lib)
     assert w["err_flags"] == 0

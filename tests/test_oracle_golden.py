@@ -10,12 +10,17 @@ from dc_rl_b200.info_layout import INFO_COLUMNS, info_dict_to_row
 from helpers import kat, load_traj, oracle_traces, rel_err, traj_cfg
 
 AG = ("agent_ls", "agent_dc", "agent_bat")
-FULL = ["ny_m0_s0", "ny_m3_s1", "az_m6_s2", "wa_m9_s3"]
+FULL = ["ny_m0_s0", "ny_m3_s1", "az_m6_s2", "wa_m9_s3", "ny_m6_dc25x200"]
 
 
 def _make(g):
     cfg = traj_cfg(g)
-    return sdc_oracle.OracleEnv(oracle_traces(cfg["location"]), cfg["location"], cfg["month"], cfg["days_per_episode"])
+    dc_cfg = None
+    if "dc_geometry" in cfg:                    # builder-authored geometry (dc_config.synthetic_dc_config)
+        from dc_rl_b200.dc_config import synthetic_dc_config
+        nested = synthetic_dc_config(*cfg["dc_geometry"])
+        dc_cfg = {k: v for section in nested.values() for k, v in section.items()}     # the oracle takes the flat form
+    return sdc_oracle.OracleEnv(oracle_traces(cfg["location"]), cfg["location"], cfg["month"], cfg["days_per_episode"], dc_cfg=dc_cfg)
 
 
 def _check_reset(g, k, obs):
