@@ -37,11 +37,19 @@ class Buffers:
         return x.cpu().numpy() if self.cuda else x
 
 
-def _oracle_rollout(loc, month, days, seed, n_steps):
+def _flat_dc_cfg(geometry):
+    """Flat (oracle) form of dc_config.synthetic_dc_config(*geometry); None = the default file."""
+    if geometry is None:
+        return None
+    from dc_rl_b200.dc_config import synthetic_dc_config
+    return {k: v for section in synthetic_dc_config(*geometry).values() for k, v in section.items()}
+
+
+def _oracle_rollout(loc, month, days, seed, n_steps, geometry=None):
     """One oracle env under seeded RNGs; returns what is needed to replay it on the device."""
     import sdc_oracle
     from helpers import oracle_traces
-    env = sdc_oracle.OracleEnv(oracle_traces(loc), loc, month, days)
+    env = sdc_oracle.OracleEnv(oracle_traces(loc), loc, month, days, dc_cfg=_flat_dc_cfg(geometry))
     random.seed(seed); np.random.seed(seed)
     rng = np.random.RandomState(seed + 77)
     t_ep = days * 96
@@ -63,18 +71,23 @@ def _oracle_rollout(loc, month, days, seed, n_steps):
 
 
 def batched_mixed_locations_vs_oracle(lib, cuda, N=4096):
-    """N = 4096 envs (BASELINE config 2 scale) over {ny, az, wa} x months, device tensors through sdc_step: env i
-    replays oracle rollout i mod K (K seeded oracle envs stepped on the CPU), with auto-resets."""
+    """N = 4096 envs (BASELINE config 2 scale; the mix of BASELINE config 4) over {ny, az, wa} x months x three data-centre
+    geometries (default 20 x 200, 25 x 200, 12 x 160 -- per-env cfg_id), device tensors through sdc_step: env i replays
+    oracle rollout i mod K (K seeded oracle envs stepped on the CPU), with auto-resets."""
     from dc_rl_b200 import info_layout
-    from dc_rl_b200.dc_config import size_datacenter
+    from dc_rl_b200.dc_config import size_datacenter, synthetic_dc_config
     from dc_rl_b200.engine import Engine
     from replay import location_traces, scaled_err
     locs = ["ny", "az", "wa"]
-    days, n_steps, K = 1, 230, 6
-    rollouts = [_oracle_rollout(locs[k % 3], [0, 6, 9, 3, 7, 11][k], days, 100 + k, n_steps) for k in range(K)]
-    eng = Engine(N, [location_traces(l) for l in locs], [size_datacenter(l)[0] for l in locs],
-                 loc_id=np.arange(N) % K % 3, cfg_id=np.arange(N) % K % 3, months=0, days_per_episode=days, lib=lib)
+    geoms = [None, (5, 5, 200), (3, 4, 160)]
+    days, n_steps, K = 1, 230, 9
+    months = [0, 6, 9, 3, 7, 11, 1, 5, 8]
+    combo = [(k % 3, (k // 3 + k) % 3) for k in range(K)]         # (location, geometry) of rollout k: all nine pairs
+    rollouts = [_oracle_rollout(locs[combo[k][0]], months[k], days, 100 + k, n_steps, geoms[combo[k][1]]) for k in range(K)]
+    params = [size_datacenter(locs[l], None if geoms[g] is None else synthetic_dc_config(*geoms[g]))[0] for l, g in combo]
     which = np.arange(N) % K
+    eng = Engine(N, [location_traces(l) for l in locs], params, loc_id=np.array([c[0] for c in combo])[which], cfg_id=which,
+                 months=0, days_per_episode=days, lib=lib)
     B = Buffers(N, cuda)
     obs, share, rew, done, info, term = B.obs, B.share, B.rew, B.done, B.info, B.term
 
@@ -86,6 +99,7 @@ def batched_mixed_locations_vs_oracle(lib, cuda, N=4096):
                 n = len(ids)
                 eng.stage_episode(ids, [r["day"]] * n, [r["hour"]] * n, np.repeat(r["temp"][None], n, 0),
                                   np.repeat(r["wetb"][None], n, 0), [r["tmin"]] * n, [r["tmax"]] * n)
+    assert len(set(combo)) == 9
     stage(0)
     eng.reset_device(obs, share)
     B.sync()
