@@ -982,16 +982,13 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     // All CTAs must be co-resident (reset workers wait for unit CTAs): never more than the resident capacity.
     const int capacity = c.sm_count * (bps < 2 ? bps : 2);
     const int need = (n_units + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    int reserve = capacity / 8;                       // CTAs that only do resets (they overlap with the scans)
+    int reserve = capacity / 8;                       // at least this many CTAs are workers from the first cycle on
     if (reserve < 1) reserve = 1;
     int n_unit_ctas = need < capacity - reserve ? need : capacity - reserve;
     if (n_unit_ctas < 1) n_unit_ctas = 1;
-    int blocks = n_unit_ctas + reserve;
-    if (need < capacity - reserve && blocks < capacity) {
-        // small batches: spare CTAs cost nothing; cap so that a handful of envs does not launch a whole grid
-        const int want = n_unit_ctas + (S.n_envs < 4096 ? 4 : reserve);
-        blocks = want < capacity ? want : capacity;
-    }
+    // large batches fill the chip (every CTA beyond the unit CTAs is a worker); small ones do not launch a whole grid
+    int blocks = S.n_envs < 4096 ? n_unit_ctas + 4 : capacity;
+    if (blocks > capacity) blocks = capacity;
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(c.device));
     k_step<<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas);
