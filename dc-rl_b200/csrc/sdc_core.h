@@ -36,6 +36,7 @@ constexpr int kWexpMax = 6;           // |log2| range of the adaptive interval w
 constexpr int kTailCap = 128;         // values per tail band
 constexpr int kBandTarget = 40;       // a refresh narrows the bands when one holds more values than this
 constexpr int kAlphaOff = 12;         // narrowest tail band: alpha = 0.5 / 2^12 of the IQR
+constexpr int kHandD = 16, kHandI = 6;  // rows of the physics hand-over arrays (StepArgs::hand_d / hand_i)
 constexpr int kPassJobBytes = 192;     // size of one maintenance-pass record (sdc_kernels.cu PassJob)
 constexpr int kTailRetry = 200;       // steps of plain scans before another attempt at tail sets that did not fit
 constexpr double kSpMin = 15.0, kSpMax = 21.6;   // utils/make_envs_pyenv.py:124-126
@@ -648,51 +649,69 @@ SDC_HD int find_equal(const float* lst, int m, float o) {
     }
     return m;
 }
-// number of elements <= e in the sorted lst[0..m) (insertion point after ties)
-SDC_HD int upper_bound(const float* lst, int m, float e) {
-    int lo = 0, hi = m;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (lst[mid] <= e) lo = mid + 1; else hi = mid; }
-    return lo;
+
+// A structural edit of a bracket is PLANNED by the lane that owns the env and applied afterwards (on the device by the
+// whole warp, coalesced; a lane moving a hundred floats by itself stalls its 31 neighbours):
+//   B (memory) --remove index rm--> R --drop first / last--> R' --insert val at ins--> F (the edited list)
+struct ListEdit { int rm, drop, ins; float val; int m0; };   // rm / ins -1 = none; drop 0 none, 1 first, 2 last; m0 = length of B
+SDC_HD bool edit_trivial(const ListEdit& ed) { return ed.rm < 0 && ed.drop == 0 && ed.ins < 0; }
+SDC_HD int edit_len(const ListEdit& ed) { return ed.m0 - (ed.rm >= 0) - (ed.drop != 0) + (ed.ins >= 0); }
+SDC_HD float edit_at(const float* B, const ListEdit& ed, int j) {       // element j of F
+    if (ed.ins >= 0) { if (j == ed.ins) return ed.val; if (j > ed.ins) j -= 1; }
+    if (ed.drop == 1) j += 1;
+    if (ed.rm >= 0 && j >= ed.rm) j += 1;
+    return B[j];
+}
+SDC_HD float removed_at(const float* B, int rm, int j) { return B[(rm >= 0 && j >= rm) ? j + 1 : j]; }   // element j of R
+// serial application (host build; the CUDA kernel applies edits warp-cooperatively)
+SDC_HD void edit_apply(float* B, const ListEdit& ed) {
+    if (edit_trivial(ed)) return;
+    float tmp[kListCap];
+    const int len = edit_len(ed);
+    for (int j = 0; j < len; ++j) tmp[j] = edit_at(B, ed, j);
+    for (int j = 0; j < len; ++j) B[j] = tmp[j];
 }
 
-SDC_HD void list_remove(float* lst, int& a, int& m, float o, int& err) {
+// first / last: B[0], B[m-1] (cached by the caller)
+SDC_HD void list_remove(const float* B, int& a, int& m, float o, float first, float last, ListEdit& ed, int& err) {
     if (m == 0) { err |= SDC_F_BRACKET; return; }
-    if (o < lst[0]) { a -= 1; return; }
-    if (o > lst[m - 1]) return;
-    const int i = find_equal(lst, m, o);
+    if (o < first) { a -= 1; return; }
+    if (o > last) return;
+    const int i = find_equal(B, m, o);
     if (i == m) { err |= SDC_F_BRACKET; return; }
-    shift_down(lst, i, m - 1);
+    ed.rm = i;
     m -= 1;
 }
 
-// k_after: rank that must stay inside the list (chooses the side to drop from when the list is full)
-SDC_HD void list_insert(float* lst, int& a, int& m, float e, int n_after, int k_after) {
-    if (m > 0 && e < lst[0] && a > 0) { a += 1; return; }
-    if (m > 0 && e > lst[m - 1] && a + m < n_after - 1) return;     // ranks above the list, list not at the top
-    // e belongs inside the list (or extends a list that reaches the end of the window)
-    const int pos = upper_bound(lst, m, e);
+// m: length after the removal; k_after: rank that must stay inside the list (chooses the side to drop from when the list is full)
+SDC_HD void list_insert(const float* B, int& a, int& m, float e, int n_after, int k_after, float first, float last, ListEdit& ed) {
+    if (ed.rm >= 0 && m > 0) { first = removed_at(B, ed.rm, 0); last = removed_at(B, ed.rm, m - 1); }
+    if (m > 0 && e < first && a > 0) { a += 1; return; }
+    if (m > 0 && e > last && a + m < n_after - 1) return;           // ranks above the list, list not at the top
+    // e belongs inside the list (or extends a list that reaches the end of the window): position after ties in R
+    int lo = 0, hi = m;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (removed_at(B, ed.rm, mid) <= e) lo = mid + 1; else hi = mid; }
+    const int pos = lo;
     if (m == kListCap) {
         // full: drop from the side with more spare ranks around the target k_after
         const int r = k_after - a;
         const int margin_lo = r, margin_hi = m - 1 - r;
-        if (margin_lo > margin_hi) {            // drop lst[0]
+        if (margin_lo > margin_hi) {            // drop the first value
             if (pos == 0) { a += 1; return; }   // e itself would be the dropped element
-            shift_down(lst, 0, pos - 1);
-            lst[pos - 1] = e; a += 1; return;
-        } else {                                // drop lst[m-1]
+            ed.drop = 1; ed.ins = pos - 1; ed.val = e; a += 1; return;
+        } else {                                // drop the last value
             if (pos == m) return;
-            shift_up(lst, pos, m - 1);
-            lst[pos] = e; return;
+            ed.drop = 2; ed.ins = pos; ed.val = e; return;
         }
     }
-    shift_up(lst, pos, m);
-    lst[pos] = e;
+    ed.ins = pos; ed.val = e;
     m += 1;
 }
 
 // Appends `energy` to the env's reward window (fp32 ring; `o` = the value it evicts, if any), updates both
 // quartile brackets and derives the fences.  utils/reward_creator.py:16-45.
-SDC_HDN void reward_prepare(const State& S, int env, double energy, int len, int head, float evicted, QView& Q, ScanRequest& rq) {
+SDC_HDN void reward_prepare(const State& S, int env, double energy, int len, int head, float evicted, QView& Q, ScanRequest& rq,
+                            ListEdit* edits) {
     int err = 0;
     float e = (float)energy;
     if (!(fabs(energy) <= 3.0e38)) { err |= SDC_F_NONFINITE; e = 0.f; }
@@ -723,33 +742,32 @@ SDC_HDN void reward_prepare(const State& S, int env, double energy, int len, int
         const int k = num / 4;                                   // np.percentile 'linear': idx = (n-1)*p
         const double frac = (double)(num % 4) * 0.25;
         rq.k[j] = k;
-        bool touched = false;                                    // list contents changed: the cached ends are stale
-        if (evict) {
-            if (m > 0 && o < first[j]) a -= 1;
-            else if (m > 0 && o > last[j]) { }
-            else { list_remove(lst, a, m, o, err); touched = true; }
-        }
-        if (m == 0) { lst[0] = e; a = 0; m = 1; }                // first value ever
-        else if (!touched && e < first[j] && a > 0) a += 1;
-        else if (!touched && e > last[j] && a + m < n - 1) { }   // ranks above the list, list not at the top
-        else list_insert(lst, a, m, e, n, k);
+        ListEdit& ed = edits[j];
+        ed.rm = -1; ed.drop = 0; ed.ins = -1; ed.val = 0.f; ed.m0 = m;
+        if (evict) list_remove(lst, a, m, o, first[j], last[j], ed, err);
+        if (m == 0 && ed.rm < 0) { ed.ins = 0; ed.val = e; a = 0; m = 1; }   // first value ever
+        else list_insert(lst, a, m, e, n, k, first[j], last[j], ed);
+        const bool plain = edit_trivial(ed);                     // contents unchanged: the cached ends are valid
         if (n >= 2) {
             const int r = k - a;
             if (r < 0 || r + 1 >= m) {
                 err |= SDC_F_BRACKET;
             } else {
-                const double lo_v = lst[r], hi_v = lst[r + 1];
+                const double lo_v = edit_at(lst, ed, r), hi_v = edit_at(lst, ed, r + 1);
                 const double d = hi_v - lo_v;                    // numpy _lerp
                 qv[j] = (frac >= 0.5) ? hi_v - d * (1.0 - frac) : lo_v + d * frac;
                 const int margin_lo = (a > 0) ? r : kListCap, margin_hi = (a + m < n) ? m - 2 - r : kListCap;
-                if (margin_lo < kWidenMargin && margin_lo <= margin_hi) { rq.dir[j] = SCAN_BELOW; rq.thr[j] = lst[0]; }
-                else if (margin_hi < kWidenMargin) { rq.dir[j] = SCAN_ABOVE; rq.thr[j] = lst[m - 1]; }
-                if (margin_lo < kRecentreMargin || margin_hi < kRecentreMargin) {
+                const bool short_side = margin_lo < kRecentreMargin || margin_hi < kRecentreMargin;
+                float f0 = first[j], f1 = last[j];
+                if (short_side && !plain) { f0 = edit_at(lst, ed, 0); f1 = edit_at(lst, ed, m - 1); }
+                if (margin_lo < kWidenMargin && margin_lo <= margin_hi) { rq.dir[j] = SCAN_BELOW; rq.thr[j] = f0; }
+                else if (margin_hi < kWidenMargin) { rq.dir[j] = SCAN_ABOVE; rq.thr[j] = f1; }
+                if (short_side) {
                     // all values within ~kCollectAim average list gaps of the quartile pair (width adapts per env and list)
                     const int wexp = (int)(int8_t)(fc >> (16 + 8 * j));
-                    const float gap = (lst[m - 1] - lst[0]) / (float)(m - 1);
+                    const float gap = (f1 - f0) / (float)(m - 1);
                     const float w = ldexpf(gap * (float)kCollectAim, wexp);
-                    rq.rc[j] = 1; rq.ca[j] = lst[r] - w; rq.cb[j] = lst[r + 1] + w;
+                    rq.rc[j] = 1; rq.ca[j] = (float)lo_v - w; rq.cb[j] = (float)hi_v + w;
                 }
             }
         }
@@ -1083,6 +1101,11 @@ struct StepArgs {
     float hvac_bins_per_kw;             // SDC_HVAC_BINS / range
     unsigned long long* phase_clocks;   // optional [16]: summed per-warp clock64 deltas of the k_step phases (diagnostics)
     int32_t unit_envs, blocks_per_sm;
+    // split-phase variant (k_phys -> k_obs -> k_step without physics / observations): what the physics hands over
+    double* hand_d;        // [kHandD][N]  energy, nci_next, ls_penalty, LsStats (oldest, avg, norm_q, hist[5]), soc, norms (cmin, crng, tmin, trng)
+    int32_t* hand_i;       // [kHandI][N]  terminal, step_after, hist_len, hist_head, tn, norms.t0
+    float* hand_f;         // [N]          evicted window sample
+    int32_t split;
 };
 
 // HARL shared observation (harl/envs/sustaindc/harlsustaindc_env.py:78-85): ls[0:26] | dc[11] | dc[13] |

@@ -24,7 +24,6 @@ namespace backend {
 struct Context {
     int device = 0;
     int sm_count = 148;
-    int step_blocks_per_sm = 2;
 };
 using StepArgs = sdc::StepArgs;
 
@@ -80,6 +79,11 @@ static const char* sync(Context& c) { CU(cudaSetDevice(c.device)); CU(cudaDevice
 // device helpers
 // =================================================================================================
 constexpr int kStepThreads = 256;
+#ifndef SDC_SPLIT_CTAS_PER_SM
+#define SDC_SPLIT_CTAS_PER_SM 3
+#endif
+constexpr int kSplitCtasPerSm = SDC_SPLIT_CTAS_PER_SM;   // k_step<false> (no physics / observation code): co-resident CTAs per SM
+constexpr int kSplitHitFloats = 2048;                    // parked-hit list of a window pass in the split-phase variant
 constexpr int kWarpsPerBlock = kStepThreads / 32;
 constexpr int kObsRow = 3 * SDC_OBS_DIM;          // 78 floats per env
 constexpr int kTileStride = kObsRow + 1;          // odd row stride of the shared-memory observation tile
@@ -120,9 +124,10 @@ __device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("pre
 
 // Issues, up front and all at once, the second-level (address-dependent) reads of one env-step so that their
 // DRAM latencies overlap instead of being paid one after another inside the scalar phase.
-// Called by the whole warp (`active` lanes own an env).
-__device__ __forceinline__ void prefetch_env(const sdc::State& S, const sdc::Tables& T, int env, bool active) {
+// Called by the whole warp (`active` lanes own an env).  what: bit 0 the reads of the physics, bit 1 those of the normaliser.
+__device__ __forceinline__ void prefetch_env(const sdc::State& S, const sdc::Tables& T, int env, bool active, int what) {
     if (!active) env = 0;
+    if (what & 1) {
     const int t = S.t[env], t0 = S.t0[env], head = S.ls_head[env], hh = S.hist_head[env];
     const sdc::LocTables& L = T.loc[S.loc_id[env]];
     const double* wt = S.weather + (size_t)env * 2 * S.win_len + (t - t0);
@@ -134,6 +139,8 @@ __device__ __forceinline__ void prefetch_env(const sdc::State& S, const sdc::Tab
     prefetch_line(S.hist + (size_t)env * S.hist_cap + hh);
     prefetch_line(L.ci + t - 16); prefetch_line(L.ci + t); prefetch_line(L.ci + t + 9);
     prefetch_line(L.workload + t); prefetch_line(L.ns + t); prefetch_line(L.sh + t);
+    }
+    if (!(what & 2)) return;
     // reward normaliser: the bracket positions it will look at and the rows of the two tail bands
     const int2 qa = reinterpret_cast<const int2*>(S.q_a)[env], qm = reinterpret_cast<const int2*>(S.q_m)[env];
     const int2 tn = reinterpret_cast<const int2*>(S.tail_n)[env];
@@ -360,24 +367,21 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
                 // ordered by slot, so the ranks are a permutation.
                 float* buf = scr + j * sdc::kCollectCap;
                 float* out = win + j * sdc::kCollectCap;              // the staged window is no longer needed
-                const bool h0 = tid < c, h1 = tid + kStepThreads < c;
-                const float x0 = h0 ? buf[tid] : 0.f;
-                int r0 = 0;
                 if (c <= kStepThreads) {
+                    const bool h0 = tid < c;
+                    const float x0 = h0 ? buf[tid] : 0.f;
+                    int r0 = 0;
 #pragma unroll 4
                     for (int i = 0; i < c; ++i) { const float y = buf[i]; r0 += (y < x0) | ((y == x0) & (i < tid)); }
-                } else {
-                    const float x1 = h1 ? buf[tid + kStepThreads] : 0.f;
-                    int r1 = 0;
-#pragma unroll 2
-                    for (int i = 0; i < c; ++i) {
-                        const float y = buf[i];
-                        r0 += (y < x0) | ((y == x0) & (i < tid));
-                        r1 += (y < x1) | ((y == x1) & (i < tid + kStepThreads));
-                    }
-                    if (h1) out[r1] = x1;
+                    if (h0) out[r0] = x0;
+                } else {                                              // larger collections: bitonic sort in place, then copy
+                    int p2 = 2;
+                    while (p2 < c) p2 <<= 1;
+                    for (int i = c + tid; i < p2; i += kStepThreads) buf[i] = SDC_INF_F;
+                    __syncthreads();
+                    block_bitonic_sort(buf, p2);
+                    for (int i = tid; i < c; i += kStepThreads) out[i] = buf[i];
                 }
-                if (h0) out[r0] = x0;
             }
         }
         __syncthreads();
@@ -577,7 +581,11 @@ __global__ void __launch_bounds__(kResetThreads) k_reset(const sdc::State S, con
 // =================================================================================================
 // k_step
 // =================================================================================================
-__global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, const StepArgs a, const int n_unit_ctas) {
+// FUSED = true: the whole env-step in this kernel.  FUSED = false (split-phase variant): k_phys and k_obs have run, this
+// kernel does the reward normaliser, the window passes and the worker jobs from what k_phys handed over.
+template <bool FUSED>
+__global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_step(const sdc::State S, const StepArgs a, const int n_unit_ctas,
+                                                                                   const int hit_cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int U = a.unit_envs;
@@ -605,7 +613,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
     float* win = scr + 2 * sdc::kCollectCap;                            // [hist_cap] the staged window
     const int win_floats = S.hist_cap > 2 * sdc::kCollectCap ? S.hist_cap : 2 * sdc::kCollectCap;
     float* hits = win + win_floats;                                     // parked hits of a pass: the rest of the region the obs tiles use
-    const int hit_cap = kWarpsPerBlock * 32 * kTileStride - 2 * sdc::kCollectCap - win_floats;
+
     unsigned pass_phase = 0;
     const int N = S.n_envs;
     const int n_units = (N + U - 1) / U;
@@ -638,6 +646,9 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         sdc::ScanResult rs;
         sdc::Moments M;
         sdc::QView Q;
+        sdc::ListEdit edits[2];
+        edits[0].rm = edits[1].rm = -1; edits[0].drop = edits[1].drop = 0; edits[0].ins = edits[1].ins = -1;
+        edits[0].val = edits[1].val = 0.f; edits[0].m0 = edits[1].m0 = 0;
         st.terminal = 0;
         en.energy = 0.0; en.nci_next = 0.0; en.ls_penalty = 0.0;
         rq.kind = sdc::SCAN_SKIP; rq.n = 0; rq.lo = rq.hi = rq.shift = 0.f; rq.tl = rq.th = rq.tl2 = rq.th2 = 0.f; rq.tails = 0;
@@ -649,19 +660,49 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         Q.lst[0] = S.qlist + (size_t)(active ? env : 0) * 2 * sdc::kListCap; Q.lst[1] = Q.lst[0] + sdc::kListCap;
         Q.a[0] = Q.a[1] = Q.m[0] = Q.m[1] = 0;
         long long tk1 = tk0;
-        prefetch_env(S, T, env, active);
+        prefetch_env(S, T, env, active, FUSED ? 3 : 2);
         if (active) {
             const int2 qa = reinterpret_cast<const int2*>(S.q_a)[env], qm = reinterpret_cast<const int2*>(S.q_m)[env];
-            const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
-            GlobalInfoSink info{a.info, N, env};
-            sdc::physics_step(S, T, env, a_ls, a_dc, a_bat, info, st, od);
+            if (FUSED) {
+                const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
+                GlobalInfoSink info{a.info, N, env};
+                sdc::physics_step(S, T, env, a_ls, a_dc, a_bat, info, st, od);
+            } else {
+                st.energy = a.hand_d[env]; st.nci_next = a.hand_d[(size_t)N + env]; st.ls_penalty = a.hand_d[(size_t)2 * N + env];
+                st.terminal = a.hand_i[env]; st.step_after = a.hand_i[(size_t)N + env];
+                st.hist_len = a.hand_i[(size_t)2 * N + env]; st.hist_head = a.hand_i[(size_t)3 * N + env];
+                st.evicted = a.hand_f[env];
+            }
             en.energy = st.energy; en.nci_next = st.nci_next; en.ls_penalty = st.ls_penalty;
             tk1 = clock64();
             Q.a[0] = qa.x; Q.a[1] = qa.y; Q.m[0] = qm.x; Q.m[1] = qm.y;
-            sdc::reward_prepare(S, env, en.energy, st.hist_len, st.hist_head, st.evicted, Q, rq);
+            sdc::reward_prepare(S, env, en.energy, st.hist_len, st.hist_head, st.evicted, Q, rq, edits);
             sdc::reward_plan(S, env, rq, M);
         }
         __syncwarp();
+        // Planned bracket edits (a value entered / left inside a bracket: ~10 % of the env-steps) are applied by the whole
+        // warp, one env at a time: every lane computes its elements of the edited list from the old one, then stores them.
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+            unsigned need = __ballot_sync(0xffffffffu, active && !sdc::edit_trivial(edits[j]));
+            while (need) {
+                const int l = __ffs(need) - 1;
+                need &= need - 1;
+                sdc::ListEdit ed;
+                ed.rm = __shfl_sync(0xffffffffu, edits[j].rm, l); ed.drop = __shfl_sync(0xffffffffu, edits[j].drop, l);
+                ed.ins = __shfl_sync(0xffffffffu, edits[j].ins, l); ed.val = __shfl_sync(0xffffffffu, edits[j].val, l);
+                ed.m0 = __shfl_sync(0xffffffffu, edits[j].m0, l);
+                float* B = S.qlist + ((size_t)(env0 + l) * 2 + j) * sdc::kListCap;
+                const int len = sdc::edit_len(ed);
+                float v[sdc::kListCap / 32];
+#pragma unroll
+                for (int t = 0; t < sdc::kListCap / 32; ++t) { const int i = lane + 32 * t; v[t] = i < len ? sdc::edit_at(B, ed, i) : 0.f; }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < sdc::kListCap / 32; ++t) { const int i = lane + 32 * t; if (i < len) B[i] = v[t]; }
+                __syncwarp();
+            }
+        }
         const long long tk2 = clock64();
         // A pass whose result this step's reward does not need (the brackets still hold the quartile ranks and the tail
         // bands still contain the fences: the refresh only restores slack for FUTURE steps) is a maintenance pass: its
@@ -716,7 +757,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         }
         const long long tk2b = clock64();
         const int finished = st.terminal;
-        if (have_unit) {
+        if (FUSED && have_unit) {
             // logger sums (harl/envs/sustaindc/sustaindc_logger.py:86-101): warp reduce, one atomic per metric.  Done while
             // the step's results are still in registers (after the long observation code they come back from spills).
             double m[13];
@@ -741,7 +782,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                 if (lane == 0) atomicAdd(a.metrics + slot[k], v);
             }
         }
-        {
+        if (FUSED) {
             // Observation rows go through a shared-memory tile (odd row stride: conflict-free) and leave as contiguous
             // 128-bit stores; 107 scattered 4-byte stores per env would keep the LSU busy for ~50 k cycles per unit.
             // The tile shares its memory with the window-pass buffers (used only after the barrier below).
@@ -917,6 +958,126 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
     if (a.phase_clocks && threadIdx.x == 0) atomicMax(a.phase_clocks + 15, gtime_ns());   // timeline: CTA done
 }
 
+
+// =================================================================================================
+// split-phase variant: k_phys -> k_obs -> k_step<false>
+// =================================================================================================
+// The fused kernel is bounded by resident warps x per-unit latency at the register budget of its largest phase.  Here the
+// physics and the observation builder are kernels of their own (one lane per env, 32 envs per warp), handing ~170 B
+// per env over through global memory; the normaliser kernel then runs without their registers and code.
+__device__ __forceinline__ void tables_to_smem(const sdc::State& S, unsigned char* smem, sdc::Tables& T) {
+    const int loc_bytes = S.n_loc * (int)sizeof(sdc::LocTables), dc_bytes = S.n_cfg * (int)sizeof(sdc_dc_params);
+    if (loc_bytes + dc_bytes <= kTableBytes) {
+        int* dst = reinterpret_cast<int*>(smem);
+        const int* src_loc = reinterpret_cast<const int*>(S.loc);
+        const int* src_dc = reinterpret_cast<const int*>(S.dc);
+        for (int i = threadIdx.x; i < loc_bytes / 4; i += blockDim.x) dst[i] = src_loc[i];
+        for (int i = threadIdx.x; i < dc_bytes / 4; i += blockDim.x) dst[loc_bytes / 4 + i] = src_dc[i];
+        T.loc = reinterpret_cast<const sdc::LocTables*>(smem);
+        T.dc = reinterpret_cast<const sdc_dc_params*>(smem + loc_bytes);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kStepThreads, 2) k_phys(const sdc::State S, const StepArgs a) {
+    __shared__ __align__(16) unsigned char tab[kTableBytes];
+    sdc::Tables T{S.loc, S.dc};
+    tables_to_smem(S, tab, T);
+    const int lane = threadIdx.x & 31;
+    const int N = S.n_envs;
+    const int env = blockIdx.x * kStepThreads + threadIdx.x;
+    const bool active = env < N;
+    prefetch_env(S, T, env, active, 1);
+    sdc::StepResult st;
+    sdc::ObsDeferred od;
+    double m[13];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) m[k] = 0.0;
+    if (active) {
+        const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
+        GlobalInfoSink info{a.info, N, env};
+        sdc::physics_step(S, T, env, a_ls, a_dc, a_bat, info, st, od);
+        double* d = a.hand_d + env;
+        d[0] = st.energy; d[(size_t)N] = st.nci_next; d[(size_t)2 * N] = st.ls_penalty;
+        d[(size_t)3 * N] = od.ls.oldest; d[(size_t)4 * N] = od.ls.avg; d[(size_t)5 * N] = od.ls.norm_q;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) d[(size_t)(6 + k) * N] = od.ls.hist[k];
+        d[(size_t)11 * N] = od.soc; d[(size_t)12 * N] = od.nm.cmin; d[(size_t)13 * N] = od.nm.crng;
+        d[(size_t)14 * N] = od.nm.tmin; d[(size_t)15 * N] = od.nm.trng;
+        int32_t* q = a.hand_i + env;
+        q[0] = st.terminal; q[(size_t)N] = st.step_after; q[(size_t)2 * N] = st.hist_len; q[(size_t)3 * N] = st.hist_head;
+        q[(size_t)4 * N] = od.tn; q[(size_t)5 * N] = od.nm.t0;
+        a.hand_f[env] = st.evicted;
+        m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
+        m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
+        m[11] = st.overdue; m[12] = st.total_kw;
+        if (st.hvac_kw > 0.0) {
+            int bin = (int)(st.hvac_kw * (double)a.hvac_bins_per_kw);
+            bin = bin < 0 ? 0 : (bin >= SDC_HVAC_BINS ? SDC_HVAC_BINS - 1 : bin);
+            atomicAdd(a.hvac_hist + bin, 1ull);
+        }
+    }
+    constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
+                              sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
+                              sdc::M_OVERDUE, sdc::M_TOTAL_KW};
+#pragma unroll
+    for (int k = 0; k < 13; ++k) {
+        const double v = warp_sum(m[k]);
+        if (lane == 0 && v != 0.0) atomicAdd(a.metrics + slot[k], v);
+    }
+}
+
+__global__ void __launch_bounds__(kStepThreads, 2) k_obs(const sdc::State S, const StepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    sdc::Tables T{S.loc, S.dc};
+    tables_to_smem(S, smem_raw, T);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = S.n_envs;
+    const int env0 = (blockIdx.x * kWarpsPerBlock + warp) * 32;
+    if (env0 >= N) return;
+    const int env = env0 + lane;
+    const bool active = env < N;
+    float* tile = reinterpret_cast<float*>(smem_raw + kTableBytes) + (size_t)warp * 32 * kTileStride;
+    int finished = 0;
+    if (active) {
+        sdc::ObsDeferred od;
+        const double* d = a.hand_d + env;
+        od.ls.oldest = d[(size_t)3 * N]; od.ls.avg = d[(size_t)4 * N]; od.ls.norm_q = d[(size_t)5 * N];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) od.ls.hist[k] = d[(size_t)(6 + k) * N];
+        od.soc = d[(size_t)11 * N]; od.nm.cmin = d[(size_t)12 * N]; od.nm.crng = d[(size_t)13 * N];
+        od.nm.tmin = d[(size_t)14 * N]; od.nm.trng = d[(size_t)15 * N];
+        const int32_t* q = a.hand_i + env;
+        finished = q[0]; od.tn = q[(size_t)4 * N]; od.nm.t0 = q[(size_t)5 * N];
+        RowSink sink{tile + lane * kTileStride};
+        sdc::emit_obs(S, T, env, od, sink);
+        a.done[env] = (uint8_t)finished;
+    }
+    __syncwarp();
+    const int n_here = min(32, N - env0);
+    const int total = n_here * kObsRow;
+    float4* dst4 = reinterpret_cast<float4*>(a.obs + (size_t)env0 * kObsRow);
+    for (int i = lane; i < total / 4; i += 32) {
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int f = 4 * i + q; const int e = f / kObsRow; v[q] = tile[e * kTileStride + (f - e * kObsRow)]; }
+        dst4[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    for (int f = (total & ~3) + lane; f < total; f += 32) { const int e = f / kObsRow; a.obs[(size_t)env0 * kObsRow + f] = tile[e * kTileStride + (f - e * kObsRow)]; }
+    float* dsh = a.share + (size_t)env0 * SDC_SHARE_DIM;
+    for (int f = lane; f < n_here * SDC_SHARE_DIM; f += 32) {
+        const int e = f / SDC_SHARE_DIM, k = f - e * SDC_SHARE_DIM;
+        const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
+        dsh[f] = tile[e * kTileStride + src];
+    }
+    unsigned fin = __ballot_sync(0xffffffffu, finished != 0);
+    while (fin && a.term_obs) {
+        const int l = __ffs(fin) - 1;
+        fin &= fin - 1;
+        for (int k = lane; k < kObsRow; k += 32) a.term_obs[(size_t)(env0 + l) * kObsRow + k] = tile[l * kTileStride + k];
+    }
+}
+
 __global__ void k_build_reset_list(int n_envs, const uint8_t* __restrict__ mask, int32_t* list, int32_t* count) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= n_envs) return;
@@ -972,15 +1133,21 @@ __global__ void __launch_bounds__(kSortThreads) k_rebuild(const sdc::State S) {
 // =================================================================================================
 static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& a, void* stream) {
     const int U = a.unit_envs;
-    // collect scratch + the staged window (which also receives the sorted collections: at least 2 x kCollectCap floats)
-    size_t smem = (size_t)(2 * sdc::kCollectCap + (S.hist_cap > 2 * sdc::kCollectCap ? S.hist_cap : 2 * sdc::kCollectCap)) * sizeof(float);
-    if (smem < (size_t)kWarpsPerBlock * 32 * kTileStride * sizeof(float)) smem = (size_t)kWarpsPerBlock * 32 * kTileStride * sizeof(float);   // obs tiles (same region)
+    // Dynamic shared memory of k_step after the tables: collect scratch + the staged window (which also receives the sorted
+    // collections: at least 2 x kCollectCap floats) + the parked-hit list.  The fused kernel shares the region with its
+    // observation tiles (whatever they leave beyond scratch + window is the hit list); the split-phase variant has no tiles.
+    const size_t pass_floats = (size_t)2 * sdc::kCollectCap + (S.hist_cap > 2 * sdc::kCollectCap ? S.hist_cap : 2 * sdc::kCollectCap);
+    const size_t tile_floats = (size_t)kWarpsPerBlock * 32 * kTileStride;
+    size_t smem_floats = a.split ? pass_floats + kSplitHitFloats : (pass_floats > tile_floats ? pass_floats : tile_floats);
+    const int hit_cap = (int)(smem_floats - pass_floats);
+    size_t smem = smem_floats * sizeof(float);
     if (smem < kNormWindow * sizeof(double)) smem = kNormWindow * sizeof(double);      // reset workers reuse the region
     smem += kTableBytes;
     const int n_units = (S.n_envs + U - 1) / U;
-    const int bps = a.blocks_per_sm > 0 ? a.blocks_per_sm : c.step_blocks_per_sm;
-    // All CTAs must be co-resident (reset workers wait for unit CTAs): never more than the resident capacity.
-    const int capacity = c.sm_count * (bps < 2 ? bps : 2);
+    const int per_sm = a.split ? kSplitCtasPerSm : 2;
+    const int bps = a.blocks_per_sm > 0 ? a.blocks_per_sm : per_sm;
+    // All CTAs must be co-resident (workers wait for unit CTAs): never more than the resident capacity.
+    const int capacity = c.sm_count * (bps < per_sm ? bps : per_sm);
     const int need = (n_units + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int reserve = capacity / 8;                       // at least this many CTAs are workers from the first cycle on
     if (reserve < 1) reserve = 1;
@@ -991,7 +1158,14 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     if (blocks > capacity) blocks = capacity;
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(c.device));
-    k_step<<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas);
+    if (a.split) {
+        const int nb = (S.n_envs + kStepThreads - 1) / kStepThreads;
+        k_phys<<<nb, kStepThreads, 0, st>>>(S, a);
+        k_obs<<<nb, kStepThreads, kTableBytes + tile_floats * sizeof(float), st>>>(S, a);
+        k_step<false><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas, hit_cap);
+    } else {
+        k_step<true><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas, hit_cap);
+    }
     CU(cudaGetLastError());
     return nullptr;
 }
@@ -1024,7 +1198,9 @@ static const char* launch_rebuild(Context&, const sdc::State& S, void* stream) {
 }
 
 static const char* set_kernel_attributes() {
-    CU(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_rebuild, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     return nullptr;
 }

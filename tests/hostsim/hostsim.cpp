@@ -123,7 +123,9 @@ static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs&
         for (int j = 0; j < 2; ++j) {
             Q.lst[j] = S.qlist + ((size_t)env * 2 + j) * sdc::kListCap; Q.a[j] = S.q_a[env * 2 + j]; Q.m[j] = S.q_m[env * 2 + j];
         }
-        sdc::reward_prepare(S, env, st.energy, st.hist_len, st.hist_head, st.evicted, Q, rq);
+        sdc::ListEdit edits[2];
+        sdc::reward_prepare(S, env, st.energy, st.hist_len, st.hist_head, st.evicted, Q, rq, edits);
+        for (int j = 0; j < 2; ++j) sdc::edit_apply(Q.lst[j], edits[j]);          // the CUDA kernel does this warp-cooperatively
         sdc::reward_plan(S, env, rq, mo);
         if (rq.kind == sdc::SCAN_PLAIN) {
             scan_plain(S, env, rq, rs);
