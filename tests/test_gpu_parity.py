@@ -117,3 +117,40 @@ def test_split_phase_variant_is_bit_identical(lib):
             assert np.array_equal(xa, xb)
     assert np.allclose(outs[0][1], outs[1][1], rtol=1e-12) and np.array_equal(outs[0][2], outs[1][2])
     assert not outs[0][3].any() and not outs[1][3].any()
+
+
+def test_host_buffer_modes_agree(lib):
+    """sdc_step_host on the handle's pinned buffers: kernel stores straight into host memory (direct_host = 3, default),
+    staged device buffers + D2H (0), and caller-owned pageable arrays all return the same step results."""
+    import ctypes as C
+    from dc_rl_b200.dc_config import size_datacenter
+    from dc_rl_b200.engine import Engine, _ptr
+    from replay import location_traces
+    N = 700
+    outs = []
+    for mode in (3, 0, "own"):
+        eng = Engine(N, [location_traces("az")], [size_datacenter("az")[0]], months=np.arange(N) % 12,
+                     seeds=np.arange(N, dtype=np.uint64) + 3, days_per_episode=1, lib=lib)
+        if mode != "own":
+            eng.set_tuning(direct_host=mode)
+        eng.reset_host()
+        rng = np.random.RandomState(9)
+        rec = []
+        own = dict(obs=np.full((N, 3, 26), 7.0, np.float32), share=np.zeros((N, 29), np.float32), rew=np.zeros((N, 3), np.float32),
+                   done=np.zeros(N, np.uint8))
+        for s in range(100):
+            a = rng.randint(0, 3, size=(N, 3)).astype(np.int32)
+            if mode == "own":
+                rc = lib.sdc_step_host(eng._h, _ptr(a), _ptr(own["obs"]), _ptr(own["share"]), _ptr(own["rew"]), _ptr(own["done"]), None, None)
+                assert rc == 0
+                o, sh, r, d = own["obs"], own["share"], own["rew"], own["done"]
+            else:
+                o, sh, r, d, _, _ = eng.step_host(a, want_info=False, want_term=False)
+            if s % 9 == 0 or s > 95:
+                rec.append([x.copy() for x in (o, sh, r, d)])
+        outs.append(rec)
+        eng.close()
+    for other in outs[1:]:
+        for ra, rb in zip(outs[0], other):
+            for xa, xb in zip(ra, rb):
+                assert np.array_equal(xa, xb)
