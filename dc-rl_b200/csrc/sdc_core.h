@@ -296,11 +296,11 @@ struct StepResult {
     float evicted;
 };
 
-// What the observation builder needs from the scalar phase: k_step publishes the env's window-scan job first and
-// builds the observations afterwards, off the critical path of the scan queue.
+// What the observation builder needs from the scalar phase (the observations are built after the normaliser; in the
+// split-phase variant by a kernel of their own).
 struct ObsDeferred { LsStats ls; double soc; Norms nm; int tn; };
 
-// The part of StepResult that has to survive the window scan (kept small: it lives in registers).
+// The part of StepResult the reward needs (kept small: it lives in registers across the window passes).
 struct RewardInputs { double energy, nci_next, ls_penalty; };
 
 // One env-step of the three sub-envs + managers + observations + info (everything except the

@@ -167,22 +167,6 @@ struct GlobalInfoSink {
     __device__ __forceinline__ void operator()(int col, float v) { if (info) info[(size_t)col * n + env] = v; }
 };
 
-// Streaming 128-bit load of the reward window.  Deliberately a WEAK load (no `volatile`, evict-first hint): the
-// CUDA intrinsics (__ldcg/__ldcs) are `asm volatile` and ld.global.cg compiles to LDG...STRONG.GPU, which ptxas
-// keeps in order and interleaves with the arithmetic -- only ~3 loads in flight when the warp first stalls.  Weak
-// loads let it issue the whole batch up front.  Coherence: a window line is read once per launch, after its new
-// sample was stored (ordering via the tagged queue words), and L1 is invalidated at kernel boundaries.
-__device__ __forceinline__ float4 ld_stream(const float4* p) {
-    float4 v;
-    asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ld_stream(const float* p) {
-    float v;
-    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-
 // ---- window pass: the whole CTA processes one env's window, staged in shared memory by the TMA engine -------
 // Parameters and results of the pass in flight (one at a time per CTA).
 struct PassJob {
