@@ -886,7 +886,15 @@ SDC_HDN void reward_plan(const State& S, int env, ScanRequest& rq, Moments& M) {
         if (retry > 0) { retry -= 1; fc = (fc & ~0xff00u) | ((uint32_t)retry << 8); S.fast_cfg[env] = fc; }
         else want_tails = true;
     }
-    if (lists || want_tails) {
+    // A fence that has drifted into the outer twelfth of its band gets the band re-centred NOW, by a maintenance pass,
+    // while the step can still be priced incrementally; once the fence is outside, the pass is on the step's critical path.
+    bool near_edge = false;
+    if (moments_needed && M.ok) {
+        const double lo = rq.lo64, hi = rq.hi64;
+        const double ql = 0.08 * ((double)tl - (double)tl2), qh = 0.08 * ((double)th2 - (double)th);
+        near_edge = (lo - (double)tl2) < ql || ((double)tl - lo) < ql || (hi - (double)th) < qh || ((double)th2 - hi) < qh;
+    }
+    if (lists || want_tails || near_edge) {
         rq.kind = SCAN_REFRESH;
         if (moments_needed && retry == 0) {
             const int aexp = (int)(fc & 0xffu);
