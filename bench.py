@@ -40,7 +40,7 @@ B_ALG_STEADY = 4 * 10000 + 1024      # bytes per env-step at H = 10 000 (SURVEY.
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch at N = 65 536 (launch 151 of the bench workload, ~390
 # window refreshes in flight) from the round-1 `ncu --set full` capture (profiles/r01_kstep_ncu_raw.csv); only
 # meaningful for the default --envs
-TRAFFIC_BYTES_PER_LAUNCH = 240.246272e6 + 77.325568e6
+TRAFFIC_BYTES_PER_LAUNCH = 236.845312e6 + 76.829440e6
 METRIC = "env-steps/sec at N=65536 parallel envs, 1/2/4/8xB200; HBM GB/s fraction"
 
 
