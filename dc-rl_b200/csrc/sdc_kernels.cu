@@ -347,25 +347,16 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
         for (int j = 0; j < 2; ++j) {                                    // uniform across the CTA
             const int c = raw.c[j];
             if (c >= 1 && c <= sdc::kCollectCap) {
-                // rank sort: every thread places up to two of the collected values (broadcast reads, one barrier).  Ties are
-                // ordered by slot, so the ranks are a permutation.
+                // bitonic sort in place (padded to a power of two), then copied out: ~350 instructions and 36-45 barriers per
+                // thread; a rank sort (one pass over the c values per thread) was the single most executed line of the kernel
                 float* buf = scr + j * sdc::kCollectCap;
                 float* out = win + j * sdc::kCollectCap;              // the staged window is no longer needed
-                if (c <= kStepThreads) {
-                    const bool h0 = tid < c;
-                    const float x0 = h0 ? buf[tid] : 0.f;
-                    int r0 = 0;
-#pragma unroll 4
-                    for (int i = 0; i < c; ++i) { const float y = buf[i]; r0 += (y < x0) | ((y == x0) & (i < tid)); }
-                    if (h0) out[r0] = x0;
-                } else {                                              // larger collections: bitonic sort in place, then copy
-                    int p2 = 2;
-                    while (p2 < c) p2 <<= 1;
-                    for (int i = c + tid; i < p2; i += kStepThreads) buf[i] = SDC_INF_F;
-                    __syncthreads();
-                    block_bitonic_sort(buf, p2);
-                    for (int i = tid; i < c; i += kStepThreads) out[i] = buf[i];
-                }
+                int p2 = 2;
+                while (p2 < c) p2 <<= 1;
+                for (int i = c + tid; i < p2; i += kStepThreads) buf[i] = SDC_INF_F;
+                __syncthreads();
+                block_bitonic_sort(buf, p2);
+                for (int i = tid; i < c; i += kStepThreads) out[i] = buf[i];
             }
         }
         __syncthreads();
