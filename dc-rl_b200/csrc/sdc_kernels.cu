@@ -892,12 +892,13 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
                     if (all_done) __threadfence();
                     const int e = list[my_reset];
                     if (e >= 0) { list[my_reset] = -1; my_reset = -1; kind = 1; env = e; break; }
-                    if (my_pass < N && ready[my_pass] == a.seq) { __threadfence(); env = my_pass; my_pass = -1; kind = 2; break; }
+                    // longest jobs first: a generation (44 us) started late would be the tail of the launch
                     if (pre_left) {
                         const int idx = atomicAdd(a.ctr + 9, 1);
                         if (idx < n_pre) { kind = 3; env = a.pre_list_prev[idx]; break; }
                         pre_left = false;
                     }
+                    if (my_pass < N && ready[my_pass] == a.seq) { __threadfence(); env = my_pass; my_pass = -1; kind = 2; break; }
                     if (all_done) { kind = 0; break; }
                     __nanosleep(200);
                 }
