@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(kResetThreads) k_reset(const sdc::State S, con
 // kernel does the reward normaliser, the window passes and the worker jobs from what k_phys handed over.
 template <bool FUSED>
 __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_step(const sdc::State S, const StepArgs a, const int n_unit_ctas,
-                                                                                   const int hit_cap) {
+                                                                                   const int hit_cap, const int table_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int U = a.unit_envs;
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
     __shared__ PassShared ps;
     {
         const int loc_bytes = S.n_loc * (int)sizeof(sdc::LocTables), dc_bytes = S.n_cfg * (int)sizeof(sdc_dc_params);
-        if (loc_bytes + dc_bytes <= kTableBytes) {
+        if (loc_bytes + dc_bytes <= table_bytes) {
             int* dst = reinterpret_cast<int*>(smem_raw);
             const int* src_loc = reinterpret_cast<const int*>(S.loc);
             const int* src_dc = reinterpret_cast<const int*>(S.dc);
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
         }
         __syncthreads();
     }
-    float* scr = reinterpret_cast<float*>(smem_raw + kTableBytes);      // [2][kCollectCap] collect scratch of the window pass
+    float* scr = reinterpret_cast<float*>(smem_raw + table_bytes);      // [2][kCollectCap] collect scratch of the window pass
     float* win = scr + 2 * sdc::kCollectCap;                            // [hist_cap] the staged window
     const int win_floats = S.hist_cap > 2 * sdc::kCollectCap ? S.hist_cap : 2 * sdc::kCollectCap;
     float* hits = win + win_floats;                                     // parked hits of a pass: the rest of the region the obs tiles use
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
             // Observation rows go through a shared-memory tile (odd row stride: conflict-free) and leave as contiguous
             // 128-bit stores; 107 scattered 4-byte stores per env would keep the LSU busy for ~50 k cycles per unit.
             // The tile shares its memory with the window-pass buffers (used only after the barrier below).
-            float* tile = reinterpret_cast<float*>(smem_raw + kTableBytes) + (size_t)warp * 32 * kTileStride;
+            float* tile = reinterpret_cast<float*>(smem_raw + table_bytes) + (size_t)warp * 32 * kTileStride;
             if (active) {
                 RowSink sink{tile + lane * kTileStride};
                 sdc::emit_obs(S, T, env, od, sink);
@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
     __shared__ ResetShared rsh;
     __shared__ int s_env;
     __syncthreads();
-    double* runbuf = reinterpret_cast<double*>(smem_raw + kTableBytes);   // the window-pass buffers are free by now
+    double* runbuf = reinterpret_cast<double*>(smem_raw + table_bytes);   // the window-pass buffers are free by now
     // A worker always holds one ticket of the reset queue and one of the maintenance-pass queue (a ticket is a slot
     // index; it is served as soon as the slot is filled) and takes look-ahead generation jobs -- which were published by
     // the PREVIOUS launch and are therefore available from the first cycle on -- when neither is ready.  It leaves when
@@ -1118,7 +1118,10 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     const int hit_cap = (int)(smem_floats - pass_floats);
     size_t smem = smem_floats * sizeof(float);
     if (smem < kNormWindow * sizeof(double)) smem = kNormWindow * sizeof(double);      // reset workers reuse the region
-    smem += kTableBytes;
+    // shared-memory copy of the location / dc parameter tables: only what this handle needs
+    int table_bytes = (int)(S.n_loc * sizeof(sdc::LocTables) + S.n_cfg * sizeof(sdc_dc_params));
+    table_bytes = table_bytes <= kTableBytes ? (table_bytes + 127) & ~127 : 0;
+    smem += table_bytes;
     const int n_units = (S.n_envs + U - 1) / U;
     const int per_sm = a.split ? kSplitCtasPerSm : 2;
     const int bps = a.blocks_per_sm > 0 ? a.blocks_per_sm : per_sm;
@@ -1138,9 +1141,9 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
         const int nb = (S.n_envs + kStepThreads - 1) / kStepThreads;
         k_phys<<<nb, kStepThreads, 0, st>>>(S, a);
         k_obs<<<nb, kStepThreads, kTableBytes + tile_floats * sizeof(float), st>>>(S, a);
-        k_step<false><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas, hit_cap);
+        k_step<false><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas, hit_cap, table_bytes);
     } else {
-        k_step<true><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas, hit_cap);
+        k_step<true><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas, hit_cap, table_bytes);
     }
     CU(cudaGetLastError());
     return nullptr;
