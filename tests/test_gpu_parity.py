@@ -154,3 +154,48 @@ def test_host_buffer_modes_agree(lib):
         for ra, rb in zip(outs[0], other):
             for xa, xb in zip(ra, rb):
                 assert np.array_equal(xa, xb)
+
+
+def test_full_size_properties(lib):
+    """BASELINE size (N = 65 536, H = 10 000 pre-filled) through size-independent properties: envs j and j + N/2 are given
+    the same seed, month, window and actions, so they must produce bit-identical outputs although different warps / CTAs /
+    worker CTAs handle them; the device-side logger sums equal the sums of the per-env outputs; the incremental normaliser
+    state of a sample of envs equals what their windows say."""
+    import torch
+    from helpers import check_incremental_state
+    from dc_rl_b200.dc_config import size_datacenter
+    from dc_rl_b200.engine import Engine
+    from dc_rl_b200.traces import LocationTraces
+    N, H, steps = 65536, 10000, 40
+    half = N // 2
+    ids = np.arange(N) % half
+    eng = Engine(N, [LocationTraces.synthetic("ny", 1234)], [size_datacenter("ny")[0]], months=ids % 12,
+                 seeds=ids.astype(np.uint64) * 1000 + 17, days_per_episode=1, lib=lib)
+    rng = np.random.default_rng(5)
+    pool = (330.0 + 40.0 * rng.standard_normal((128, H), dtype=np.float32)).astype(np.float32)
+    hist = pool[rng.integers(0, 128, half)] + rng.standard_normal((half, 1), dtype=np.float32)
+    eng.prefill_history(np.concatenate([hist, hist]))
+    del hist
+    dev = torch.device("cuda:0")
+    obs = torch.zeros(N, 3, 26, device=dev); share = torch.zeros(N, 29, device=dev); rew = torch.zeros(N, 3, device=dev)
+    done = torch.zeros(N, dtype=torch.uint8, device=dev)
+    eng.reset_device(obs, share)
+    phase = np.tile(rng.integers(0, 90, half).astype(np.int32), 2)            # de-synchronised episodes: resets in every step
+    eng.write_state("step_in_ep", phase)
+    eng.write_state("t", eng.read_state("t0").astype(np.int32) + phase)
+    eng.metrics(clear=True)
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    rew_sum, n_done = 0.0, 0
+    for s in range(steps):
+        a = torch.randint(0, 3, (half, 3), dtype=torch.int32, device=dev, generator=g).repeat(2, 1).contiguous()
+        eng.step_device(a, obs, share, rew, done)
+        torch.cuda.synchronize()
+        assert torch.equal(obs[:half], obs[half:]) and torch.equal(rew[:half], rew[half:]) and torch.equal(done[:half], done[half:])
+        assert torch.equal(share[:half], share[half:])
+        rew_sum += float(rew.double().sum()); n_done += int(done.sum())
+    m = eng.metrics()
+    assert m[9] == N * steps and m[11] == n_done and n_done > 0
+    assert abs(m[10] - rew_sum) <= 1e-9 * max(1.0, abs(rew_sum))
+    assert not eng.read_state("err").any()
+    valid, checked = check_incremental_state(eng, envs=list(range(0, N, 4099)), tag="full size")
+    assert valid == checked
