@@ -1,9 +1,22 @@
-"""Importable alias for the package directory `dc-rl_b200/` (a hyphen cannot appear in a Python
-module name). All code lives in `dc-rl_b200/`; this file only points the import system at it."""
-import os as _os
+"""dc_rl_b200: B200-native vectorised SustainDC per-timestep simulation (`sustaindc_env.step`).
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "dc-rl_b200")
-__path__.insert(0, _real)
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
-del _f
+Submodules are imported lazily so that host-only helpers (config, sizing, traces) work without torch or the
+CUDA library.
+"""
+__version__ = "0.1.0"
+
+_LAZY = {
+    "CudaShareVecEnv": "vec_env",
+    "InfoBatch": "vec_env",
+    "SustainDC": "sustaindc_env",
+    "HARLSustainDCEnv": "harl_env",
+    "make_train_env": "harl_env",
+    "make_eval_env": "harl_env",
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+        return getattr(importlib.import_module(__name__ + "." + _LAZY[name]), name)
+    raise AttributeError(name)

@@ -41,7 +41,7 @@ constexpr int kPassJobBytes = 192;     // size of one maintenance-pass record (s
 constexpr int kTailRetry = 200;       // steps of plain scans before another attempt at tail sets that did not fit
 constexpr double kSpMin = 15.0, kSpMax = 21.6;   // utils/make_envs_pyenv.py:124-126
 
-// ---- info table columns: keep in sync with dc-rl_b200/info_layout.py -------------------------
+// ---- info table columns: keep in sync with dc_rl_b200/info_layout.py -------------------------
 enum InfoCol {
     I_BAT_ACTION = 0, I_BAT_SOC, I_BAT_CO2, I_BAT_AVG_CI, I_BAT_E_WITHOUT, I_BAT_E_WITH, I_BAT_MAX_CAP,
     I_BAT_DCLOAD_MIN, I_BAT_DCLOAD_MAX,

@@ -6,7 +6,7 @@ reference sources cited below.  Only tests/, __graft_entry__.smoke() and bench.p
 PARITY PIN: tests/test_oracle_golden.py checks this restatement against tests/golden/traj_*.npz and
 kat.json, which oracle/make_golden.py minted by running the live reference in the build container
 (observations bit-identical after the fp32 cast, rewards / info to <= 1e-12 relative).  The one unpinned
-input is the wet-bulb trace (psychrolib is absent everywhere; see dc-rl_b200/psychro.py).
+input is the wet-bulb trace (psychrolib is absent everywhere; see dc_rl_b200/psychro.py).
 
 Reference map (all paths relative to the reference root):
   traces / managers   utils/managers.py:66-88,116-147,183-185,220-244,247-314,401-483,581-666

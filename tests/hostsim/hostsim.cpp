@@ -1,10 +1,10 @@
 // TEST INFRASTRUCTURE ONLY -- serial host build of the device logic.
 //
-// Compiles dc-rl_b200/csrc/sdc_core.h (the scalar per-env functions the CUDA kernels call) and
-// dc-rl_b200/csrc/sdc_api.inc (the C-ABI host layer) with g++ against a trivial in-memory backend, so
+// Compiles dc_rl_b200/csrc/sdc_core.h (the scalar per-env functions the CUDA kernels call) and
+// dc_rl_b200/csrc/sdc_api.inc (the C-ABI host layer) with g++ against a trivial in-memory backend, so
 // that the step logic, the rolling-quartile brackets and the reset/auto-reset sequencing can be
 // unit-tested against the oracle on machines without a GPU.  It is built by tests/ into
-// tests/hostsim/_build/libsdc_hostsim.so and is never loaded by the dc-rl_b200 package: the product
+// tests/hostsim/_build/libsdc_hostsim.so and is never loaded by the dc_rl_b200 package: the product
 // path is libsdc_b200.so (CUDA) only and fails loudly without it.
 //
 // The "kernels" below are plain loops; the full-window scan is a scalar loop (the CUDA kernel does
@@ -16,7 +16,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../dc-rl_b200/csrc/sdc_core.h"
+#include "../../dc_rl_b200/csrc/sdc_core.h"
 
 namespace backend {
 struct Context { int unused = 0; };
@@ -260,4 +260,4 @@ static const char* launch_rebuild(Context&, const sdc::State& S, void*) {
 }
 }  // namespace backend
 
-#include "../../dc-rl_b200/csrc/sdc_api.inc"
+#include "../../dc_rl_b200/csrc/sdc_api.inc"

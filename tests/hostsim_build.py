@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "hostsim", "hostsim.cpp")
 OUT = os.path.join(HERE, "hostsim", "_build", "libsdc_hostsim.so")
-DEPS = [SRC] + [os.path.join(REPO, "dc-rl_b200", "csrc", f) for f in ("sdc_core.h", "sdc_api.inc")] + [
+DEPS = [SRC] + [os.path.join(REPO, "dc_rl_b200", "csrc", f) for f in ("sdc_core.h", "sdc_api.inc")] + [
     os.path.join(REPO, "include", "sdc_b200.h")]
 
 

@@ -43,7 +43,7 @@ def test_missing_library_fails_loudly(tmp_path):
 
 
 def test_product_package_never_imports_oracle_or_hostsim():
-    pkg = os.path.join(REPO, "dc-rl_b200")
+    pkg = os.path.join(REPO, "dc_rl_b200")
     for root, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".h", ".inc")):

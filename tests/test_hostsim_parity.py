@@ -1,4 +1,4 @@
-"""CPU tests of the device logic (dc-rl_b200/csrc/sdc_core.h + sdc_api.inc) through the serial hostsim
+"""CPU tests of the device logic (dc_rl_b200/csrc/sdc_core.h + sdc_api.inc) through the serial hostsim
 build: the same golden live-reference trajectories that pin the oracle, replayed through the C ABI.
 Tolerance: |a-b| <= tol*max(1,|b|); observations 1e-6 (fp64 physics, fp32 outputs), info 1e-6,
 rewards 1e-4 (north_star bar; the reward window is fp32)."""
