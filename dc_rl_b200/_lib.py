@@ -14,8 +14,11 @@ LIST_CAP, TAIL_CAP = 128, 128
 HVAC_BINS = 4096          # sdc_core.h kListCap / kTailCap (state inspection only)
 ABI_VERSION = 1
 
-F_WORKLOAD_RANGE, F_CPU_LOAD_RANGE, F_OUTLET_DELTA, F_TRACE_DOMAIN, F_BRACKET, F_NONFINITE, F_BATTERY = (
-    0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40)
+F_WORKLOAD_RANGE, F_CPU_LOAD_RANGE, F_OUTLET_DELTA, F_TRACE_DOMAIN, F_BRACKET, F_NONFINITE, F_BATTERY, F_REWARD_DOMAIN = (
+    0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40, 0x80)
+# reward method ids (SDC_R_*), keyed by the reference's names (utils/reward_creator.py:322-334)
+REWARD_METHOD_IDS = {"default_ls_reward": 0, "default_dc_reward": 1, "default_bat_reward": 1, "custom_agent_reward": 2, "tou_reward": 3,
+                     "energy_efficiency_reward": 4, "energy_PUE_reward": 5, "water_usage_efficiency_reward": 6}
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libsdc_b200.so")
 
@@ -56,6 +59,7 @@ _PROTOS = {
     "sdc_set_dc_params": (C.c_int, [_P, C.c_int32, C.POINTER(DcParams)]),
     "sdc_set_hour_table": (C.c_int, [_P, _P, _P]),
     "sdc_assign": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "sdc_set_reward_methods": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "sdc_stage_episode": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "sdc_window_len": (C.c_int, [_P]),
     "sdc_reset": (C.c_int, [_P, _P, _P, _P, _P]),

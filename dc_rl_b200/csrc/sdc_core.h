@@ -71,6 +71,8 @@ struct LocTables {
 
 struct State {
     int32_t n_envs, ep_len, hist_cap, ls_mask, win_len, n_loc, n_cfg, pad0;
+    int32_t reward_kind[3];        // SDC_R_* per agent (ls, dc, bat)
+    int32_t append_history;        // agent_ls uses default_ls_reward: the step's energy enters the reward window
     const LocTables* loc;          // [n_loc]
     const sdc_dc_params* dc;       // [n_cfg]
     const double* hour_cos;        // [96]
@@ -97,7 +99,8 @@ struct State {
     // battery
     double* bat_load;
     // reward window + quartile brackets
-    float* hist;                   // [N][hist_cap]
+    float* hist;                   // [N][hist_cap] window samples RELATIVE to hist_ref (fp32)
+    double* hist_ref;              // [N] the env's first sample (fp64): what the fp32 window values are measured from
     int32_t* hist_len; int32_t* hist_head;
     float* qlist;                  // [N][2][kListCap] sorted order statistics around the quartile ranks
     int32_t* q_a;                  // [N][2] rank of qlist[.][0]
@@ -306,6 +309,33 @@ struct ObsDeferred { LsStats ls; double soc; Norms nm; int tn; };
 
 // The part of StepResult the reward needs (kept small: it lives in registers across the window passes).
 struct RewardInputs { double energy, nci_next, ls_penalty; };
+// What the alternate reward methods read from the step (utils/reward_creator.py:133-318).
+struct AltInputs { double ite_kw, total_kw, water; int hour_q; };      // hour_q: quarter-hours since midnight at the new time
+
+SDC_HD bool any_alt_reward(const State& S) { return (S.reward_kind[0] | S.reward_kind[1] | S.reward_kind[2]) > SDC_R_DEFAULT_DC; }
+// Alternate (stateless) reward methods.  tou_reward indexes its price table with the float hour and raises KeyError
+// off the full hour (three steps out of four): flagged here, priced at the hour's tariff.
+SDC_HD double alt_reward(int kind, double energy, const AltInputs& ai, int& err) {
+    switch (kind) {
+        case SDC_R_TOU: {
+            const int h = ai.hour_q >> 2;
+            if (ai.hour_q & 3) err |= SDC_F_REWARD_DOMAIN;
+            const double price = (h < 6 || h >= 22) ? 0.25 : (h < 11 ? 0.41 : (h < 16 ? 0.30 : 0.27));   // :169-192
+            return -1.0 * energy * price;
+        }
+        case SDC_R_ENERGY_EFFICIENCY: return ai.ite_kw / ai.total_kw;
+        case SDC_R_PUE: return ai.ite_kw != 0.0 ? -fabs(ai.total_kw / ai.ite_kw - 1.0) : -INFINITY;
+        case SDC_R_WATER: return -0.01 * ai.water;
+        default: return 0.0;                                             // SDC_R_CUSTOM
+    }
+}
+// The three agents' alternate rewards of one step (entries of default-method agents are unused).
+SDC_HD void alt_rewards(const State& S, int env, double energy, const AltInputs& ai, float* alt3) {
+    int err = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) alt3[a] = S.reward_kind[a] > SDC_R_DEFAULT_DC ? (float)alt_reward(S.reward_kind[a], energy, ai, err) : 0.f;
+    if (err) flag_error(S, env, err);
+}
 
 // One env-step of the three sub-envs + managers + observations + info (everything except the
 // reward normaliser).  InfoSink: void operator()(int col, float v).
@@ -716,11 +746,18 @@ SDC_HD void list_insert(const float* B, int& a, int& m, float e, int n_after, in
 
 // Appends `energy` to the env's reward window (fp32 ring; `o` = the value it evicts, if any), updates both
 // quartile brackets and derives the fences.  utils/reward_creator.py:16-45.
-SDC_HDN void reward_prepare(const State& S, int env, double energy, int len, int head, float evicted, QView& Q, ScanRequest& rq,
+// The window holds fp32 values measured from the env's first sample (hist_ref, fp64): the normaliser is translation
+// invariant, and a fresh window -- whose spread is a tiny fraction of the energy itself, so that z = (E - mean) / std
+// amplifies the storage rounding of absolute values -- is represented (nearly) exactly.  On return `energy` is the
+// relative value, which is what reward_finish prices.
+SDC_HDN void reward_prepare(const State& S, int env, double& energy, int len, int head, float evicted, QView& Q, ScanRequest& rq,
                             ListEdit* edits) {
     int err = 0;
+    double ref = S.hist_ref[env];
+    if (len == 0) { ref = (fabs(energy) <= 3.0e38) ? energy : 0.0; S.hist_ref[env] = ref; }
+    energy -= ref;
     float e = (float)energy;
-    if (!(fabs(energy) <= 3.0e38)) { err |= SDC_F_NONFINITE; e = 0.f; }
+    if (!(fabs(energy) <= 3.0e38)) { err |= SDC_F_NONFINITE; e = 0.f; energy = 0.0; }
     const int cap = S.hist_cap;
     float* h = S.hist + (size_t)env * cap;
     float o = 0.f; bool evict = false;
@@ -997,7 +1034,7 @@ SDC_HDN void refresh_commit(const State& S, int env, const ScanRequest& rq, cons
 // Applies the scan's results to the brackets (re-centred lists are taken over, the others extended by the one exact
 // rank the scan found) and turns the clipped moments into the three rewards.
 SDC_HDN void reward_finish(const State& S, int env, const ScanRequest& rq, const ScanResult& rs, const Moments& M,
-                           const RewardInputs& st, QView& Q, float* rew3) {
+                           const RewardInputs& st, const float* alt3, QView& Q, float* rew3) {
     int err = 0;
     const int n = rq.n;
     if (rq.kind == SCAN_REFRESH) {
@@ -1042,6 +1079,14 @@ SDC_HDN void reward_finish(const State& S, int env, const ScanRequest& rq, const
     double r_ls = foot + st.ls_penalty;
     r_ls = fmin(fmax(r_ls, -10.0), 10.0);                        // :82
     rew3[0] = (float)r_ls; rew3[1] = (float)foot; rew3[2] = (float)foot;
+    if (any_alt_reward(S)) {                                     // uniform across the batch
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int kind = S.reward_kind[a];
+            if (kind > SDC_R_DEFAULT_DC) rew3[a] = alt3[a];
+            else if (kind == SDC_R_DEFAULT_DC) rew3[a] = (float)foot;
+        }
+    }
     if (err) flag_error(S, env, err);
 }
 

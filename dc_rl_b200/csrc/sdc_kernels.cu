@@ -16,6 +16,7 @@
 //
 // No tensor cores: there is no dense contraction on this path (per-env scalar state machines + streaming passes).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include "sdc_core.h"
 
@@ -24,6 +25,9 @@ namespace backend {
 struct Context {
     int device = 0;
     int sm_count = 148;
+    bool cooperative = true;      // cudaLaunchCooperativeKernel for k_step (co-residency guaranteed by the driver)
+    int occ_per_sm[2] = {0, 0};   // cached occupancy query of k_step<true> / k_step<false> ...
+    size_t occ_smem[2] = {0, 0};  // ... at this much dynamic shared memory
 };
 using StepArgs = sdc::StepArgs;
 
@@ -44,6 +48,9 @@ static const char* init(Context& c, int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return "libsdc_b200 requires an sm_100a (B200) device";
     c.sm_count = prop.multiProcessorCount;
+    int coop = 0;
+    CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop) return "libsdc_b200 needs cooperative kernel launch (worker CTAs wait on unit CTAs of the same grid)";
     return set_kernel_attributes();
 }
 static void shutdown(Context&) {}
@@ -74,6 +81,8 @@ static const char* event_elapsed_ms(Context&, void* a, void* b, double* ms) {
 static void event_destroy(Context&, void* ev) { cudaEventDestroy((cudaEvent_t)ev); }
 static const char* dev_fill_bytes(Context&, void* p, int v, size_t bytes) { CU(cudaMemset(p, v, bytes)); return nullptr; }
 static const char* sync(Context& c) { CU(cudaSetDevice(c.device)); CU(cudaDeviceSynchronize()); return nullptr; }
+static void range_push(const char* name) { nvtxRangePushA(name); }      // NVTX ranges around the C-ABI calls (nsys / ncu --nvtx)
+static void range_pop() { nvtxRangePop(); }
 
 // =================================================================================================
 // device helpers
@@ -240,7 +249,10 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
     const bool refresh = J.kind == sdc::SCAN_REFRESH;
     if (tid == 0) {
         const unsigned bytes = ((unsigned)n * 4u + 15u) & ~15u;          // rows are 16-byte multiples (hist_cap % 4 == 0)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of `win` are done
+        // Generic-proxy accesses that the bulk copy (async proxy) must observe: this CTA's earlier use of `win` in shared
+        // memory, and -- for a maintenance pass -- the window's newest sample, a generic store to GLOBAL memory by another CTA
+        // of this launch that reached us through __threadfence + the job's ready tag.  fence.proxy.async covers both spaces.
+        asm volatile("fence.proxy.async;" ::: "memory");
         mbar_expect_tx(&ps.bar, bytes);
         tma_load_1d(win, S.hist + (size_t)env * S.hist_cap, bytes, &ps.bar);
     }
@@ -424,12 +436,12 @@ struct ResetShared {
 
 constexpr int kNormWindow = 2880;                 // 30 days of quarter-hours (utils/managers.py:435,606)
 
-// Episode reset of one env by one CTA.  `runbuf` = kNormWindow doubles of shared memory.
+// Episode reset of one env by one CTA.  `runbuf` = max(kNormWindow, win_len) doubles of shared memory (run_buf_doubles).
 // Weather noise (utils/managers.py:35-48,596-613): the year-long random walk is generated ONCE (Philox, 140 samples per
 // thread); its mean / variance come from per-thread partial sums combined with the segment offsets, and only the walk
-// values that land in the 30-day window after the start are kept (in shared memory).  The emit pass then runs over
-// window positions, so its trace reads are coalesced and independent.  No global scratch: a dependent global access
-// costs ~2 us while the other CTAs saturate HBM with window scans.
+// values that land in the episode window or in the 30-day normalisation slice after the start are kept (in shared
+// memory).  The emit pass then runs over window positions, so its trace reads are coalesced and independent.  No global
+// scratch: a dependent global access costs ~2 us while the other CTAs saturate HBM with window scans.
 // Generates the next episode of `env` (start day / hour, realised weather window, 30-day temperature range) from the
 // env's counter-based RNG stream into (wt, ww, *tmin_out, *tmax_out, sh.start).  All threads of the CTA.
 __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, double* wt, double* ww, double* tmin_out, double* tmax_out,
@@ -442,7 +454,9 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
     if (tid == 0) sdc::draw_episode_start(seed, ep, S.day_lo[env], S.day_hi[env], &sh.start[0], &sh.start[1], &sh.start[2]);
     __syncthreads();
     const int t0 = sh.start[0] * 96 + sh.start[1] * 4, roll = sh.start[2];
-    const int k_max = min(kNormWindow, n - t0);            // the reference's slice is truncated at the year end
+    const int k_norm = min(kNormWindow, n - t0);           // the reference's 30-day slice is truncated at the year end
+    const int k_win = min(S.win_len, n - t0);              // episode window (a 30-day episode is 2898 samples: longer than the slice)
+    const int k_keep = max(k_norm, k_win);
     // pass 1: this thread's segment of the walk (utils/managers.py:45-46)
     double run = 0.0, sum_run = 0.0, sum_run2 = 0.0;
     int cnt = 0;
@@ -458,7 +472,7 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
                 sum_run += run; sum_run2 += run * run; cnt += 1;
                 int t = j + 96 * roll; if (t >= n) t -= n;
                 const int k = t - t0;
-                if (k >= 0 && k < k_max) runbuf[k] = run;
+                if (k >= 0 && k < k_keep) runbuf[k] = run;
             }
         }
     }
@@ -478,16 +492,15 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
     // emit: roll, clip, window, 30-day min/max (managers.py:598-608), one window position per thread and trip
     const sdc::LocTables& L = S.loc[S.loc_id[env]];
     double tmin = INFINITY, tmax = -INFINITY;
-    for (int k = tid; k < max(k_max, S.win_len); k += kResetThreads) {
-        if (k < k_max) {
+    for (int k = tid; k < max(k_keep, S.win_len); k += kResetThreads) {
+        if (k < k_keep) {
             int j = t0 + k - 96 * roll; if (j < 0) j += n;
             const double noise = (sh.seg_off[j / sdc::kNoiseSeg] + runbuf[k]) * scale;
             const double vt = fmin(fmax(L.temp_base[j] + noise, 0.0), 45.0);
-            tmin = fmin(tmin, vt); tmax = fmax(tmax, vt);
-            if (k < S.win_len) { wt[k] = vt; ww[k] = fmin(fmax(L.wetb_base[j] + noise, 0.0), 45.0); }
-        } else if (k < S.win_len) {
-            wt[k] = 0.0; ww[k] = 0.0;                                      // beyond the year end (flagged domain)
+            if (k < k_norm) { tmin = fmin(tmin, vt); tmax = fmax(tmax, vt); }
+            if (k < k_win) { wt[k] = vt; ww[k] = fmin(fmax(L.wetb_base[j] + noise, 0.0), 45.0); }
         }
+        if (k >= k_win && k < S.win_len) { wt[k] = 0.0; ww[k] = 0.0; }    // beyond the year end (flagged domain) / padding
     }
     tmin = block_minmax(tmin, true, sh.red);
     tmax = block_minmax(tmax, false, sh.red);
@@ -508,7 +521,7 @@ __device__ __forceinline__ void pregen_one_env(const sdc::State& S, int env, dou
     }
 }
 
-// Episode reset of one env by one CTA.  `runbuf` = kNormWindow doubles of shared memory.
+// Episode reset of one env by one CTA.  `runbuf` = run_buf_doubles(S) doubles of shared memory.
 __device__ __forceinline__ void reset_one_env(const sdc::State& S, int env, float* obs, float* share, double* runbuf, ResetShared& sh) {
     const int tid = threadIdx.x;
     double* wt = S.weather + (size_t)env * 2 * S.win_len;
@@ -547,7 +560,7 @@ __device__ __forceinline__ void reset_one_env(const sdc::State& S, int env, floa
 // =================================================================================================
 __global__ void __launch_bounds__(kResetThreads) k_reset(const sdc::State S, const int32_t* __restrict__ list,
                                                          const int32_t* __restrict__ count, float* obs, float* share) {
-    extern __shared__ double runbuf[];              // [kNormWindow] walk values inside the 30-day window
+    extern __shared__ double runbuf[];              // [run_buf_doubles] walk values inside the episode window / 30-day slice
     __shared__ ResetShared sh;
     const int total = *count;
     for (int i = blockIdx.x; i < total; i += gridDim.x) reset_one_env(S, list[i], obs, share, runbuf, sh);
@@ -635,6 +648,7 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
         Q.lst[0] = S.qlist + (size_t)(active ? env : 0) * 2 * sdc::kListCap; Q.lst[1] = Q.lst[0] + sdc::kListCap;
         Q.a[0] = Q.a[1] = Q.m[0] = Q.m[1] = 0;
         long long tk1 = tk0;
+        float alt3[3] = {0.f, 0.f, 0.f};
         prefetch_env(S, T, env, active, FUSED ? 3 : 2);
         if (active) {
             const int2 qa = reinterpret_cast<const int2*>(S.q_a)[env], qm = reinterpret_cast<const int2*>(S.q_m)[env];
@@ -649,10 +663,16 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
                 st.evicted = a.hand_f[env];
             }
             en.energy = st.energy; en.nci_next = st.nci_next; en.ls_penalty = st.ls_penalty;
+            if (FUSED && sdc::any_alt_reward(S)) {
+                const sdc::AltInputs ai{st.ite_kw, st.total_kw, st.water, od.tn % 96};
+                sdc::alt_rewards(S, env, st.energy, ai, alt3);
+            }
             tk1 = clock64();
             Q.a[0] = qa.x; Q.a[1] = qa.y; Q.m[0] = qm.x; Q.m[1] = qm.y;
-            sdc::reward_prepare(S, env, en.energy, st.hist_len, st.hist_head, st.evicted, Q, rq, edits);
-            sdc::reward_plan(S, env, rq, M);
+            if (S.append_history) {                    // utils/reward_creator.py:62-63: only default_ls_reward grows the window
+                sdc::reward_prepare(S, env, en.energy, st.hist_len, st.hist_head, st.evicted, Q, rq, edits);   // en.energy -> relative
+                sdc::reward_plan(S, env, rq, M);
+            }
         }
         __syncwarp();
         // Planned bracket edits (a value entered / left inside a bracket: ~10 % of the env-steps) are applied by the whole
@@ -709,7 +729,7 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
         if (active && !slow_lane) {
             const int kind = rq.kind;
             rq.kind = sdc::SCAN_SKIP;              // no pass results to apply: price the step from the incremental state
-            sdc::reward_finish(S, env, rq, rs, M, en, Q, r3);
+            sdc::reward_finish(S, env, rq, rs, M, en, alt3, Q, r3);
             reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
             reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
             a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
@@ -823,7 +843,7 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
         const long long tk3 = clock64();
         // ---- rewards of the envs that had a pass; reward sums ----
         if (slow_lane) {
-            sdc::reward_finish(S, env, rq, rs, M, en, Q, r3);
+            sdc::reward_finish(S, env, rq, rs, M, en, alt3, Q, r3);
             reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
             reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
             a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
@@ -1107,6 +1127,11 @@ __global__ void __launch_bounds__(kSortThreads) k_rebuild(const sdc::State S) {
 // =================================================================================================
 // launches
 // =================================================================================================
+constexpr int kMaxDynSmem = 100 * 1024;           // opt-in dynamic shared memory of k_step / k_obs / k_reset
+constexpr int kMaxWinLen = (kMaxDynSmem - kTableBytes) / (int)sizeof(double);   // walk buffer of the longest supported episode
+static int max_window_len() { return kMaxWinLen; }
+static size_t run_buf_bytes(const sdc::State& S) { return (size_t)(S.win_len > kNormWindow ? S.win_len : kNormWindow) * sizeof(double); }
+
 static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& a, void* stream) {
     const int U = a.unit_envs;
     // Dynamic shared memory of k_step after the tables: collect scratch + the staged window (which also receives the sorted
@@ -1117,15 +1142,30 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     size_t smem_floats = a.split ? pass_floats + kSplitHitFloats : (pass_floats > tile_floats ? pass_floats : tile_floats);
     const int hit_cap = (int)(smem_floats - pass_floats);
     size_t smem = smem_floats * sizeof(float);
-    if (smem < kNormWindow * sizeof(double)) smem = kNormWindow * sizeof(double);      // reset workers reuse the region
+    if (smem < run_buf_bytes(S)) smem = run_buf_bytes(S);                              // reset workers reuse the region
     // shared-memory copy of the location / dc parameter tables: only what this handle needs
     int table_bytes = (int)(S.n_loc * sizeof(sdc::LocTables) + S.n_cfg * sizeof(sdc_dc_params));
     table_bytes = table_bytes <= kTableBytes ? (table_bytes + 127) & ~127 : 0;
     smem += table_bytes;
+    if (smem > (size_t)kMaxDynSmem) return "k_step: shared memory budget exceeded";
     const int n_units = (S.n_envs + U - 1) / U;
-    const int per_sm = a.split ? kSplitCtasPerSm : 2;
+    // All CTAs must be co-resident: workers spin on counters that unit CTAs advance.  The grid is sized from the occupancy
+    // the runtime reports for this kernel / block size / shared memory, and the launch is COOPERATIVE: the driver then
+    // gang-schedules the grid (or refuses the launch), also when other kernels -- an NCCL collective, a policy forward on
+    // another stream -- hold part of the device.
+    const void* fn = a.split ? (const void*)k_step<false> : (const void*)k_step<true>;
+    CU(cudaSetDevice(c.device));
+    const int which = a.split ? 1 : 0;
+    if (c.occ_per_sm[which] == 0 || c.occ_smem[which] != smem) {
+        int q = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, fn, kStepThreads, smem));
+        c.occ_per_sm[which] = q; c.occ_smem[which] = smem;
+    }
+    int per_sm = c.occ_per_sm[which];
+    if (per_sm < 1) return "k_step: no resident CTA fits on an SM";
+    const int design = a.split ? kSplitCtasPerSm : 2;  // __launch_bounds__ of the kernel
+    if (per_sm > design) per_sm = design;
     const int bps = a.blocks_per_sm > 0 ? a.blocks_per_sm : per_sm;
-    // All CTAs must be co-resident (workers wait for unit CTAs): never more than the resident capacity.
     const int capacity = c.sm_count * (bps < per_sm ? bps : per_sm);
     const int need = (n_units + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int reserve = capacity / 8;                       // at least this many CTAs are workers from the first cycle on
@@ -1136,22 +1176,22 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     int blocks = S.n_envs < 4096 ? n_unit_ctas + 4 : capacity;
     if (blocks > capacity) blocks = capacity;
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(c.device));
     if (a.split) {
         const int nb = (S.n_envs + kStepThreads - 1) / kStepThreads;
         k_phys<<<nb, kStepThreads, 0, st>>>(S, a);
         k_obs<<<nb, kStepThreads, kTableBytes + tile_floats * sizeof(float), st>>>(S, a);
-        k_step<false><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas, hit_cap, table_bytes);
-    } else {
-        k_step<true><<<blocks, kStepThreads, smem, st>>>(S, a, n_unit_ctas, hit_cap, table_bytes);
     }
+    int hc = hit_cap, tb = table_bytes, nuc = n_unit_ctas;
+    void* args[] = {(void*)&S, (void*)&a, (void*)&nuc, (void*)&hc, (void*)&tb};
+    if (c.cooperative) CU(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kStepThreads), args, smem, st));
+    else CU(cudaLaunchKernel(fn, dim3(blocks), dim3(kStepThreads), args, smem, st));
     CU(cudaGetLastError());
     return nullptr;
 }
 
 static const char* launch_reset(Context& c, const sdc::State& S, const int32_t* list, const int32_t* count, float* obs, float* share,
                                 void* stream) {
-    const size_t smem = kNormWindow * sizeof(double);
+    const size_t smem = run_buf_bytes(S);
     CU(cudaSetDevice(c.device));
     int blocks = c.sm_count;
     if (blocks > S.n_envs) blocks = S.n_envs;
@@ -1177,9 +1217,10 @@ static const char* launch_rebuild(Context&, const sdc::State& S, void* stream) {
 }
 
 static const char* set_kernel_attributes() {
-    CU(cudaFuncSetAttribute(k_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    CU(cudaFuncSetAttribute(k_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    CU(cudaFuncSetAttribute(k_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    CU(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     CU(cudaFuncSetAttribute(k_rebuild, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     return nullptr;
 }

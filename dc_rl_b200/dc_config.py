@@ -75,6 +75,17 @@ def _cycled(values, n):
     return [values[i % len(values)] for i in range(n)]
 
 
+def tolerant_flat_config(path_or_dict=None):
+    """The flat dc_config this loader actually simulates: missing keys defaulted, per-rack lists cycled to
+    NUM_ROWS * NUM_RACKS_PER_ROW entries.  The shipped reader rejects utils/dc_config_dc{1,2,3}.json (missing
+    CHILLER_COP_BASE, list lengths != NUM_RACKS); parity tests feed the oracle this same dict."""
+    c = dict(load_dc_config(path_or_dict))
+    n = int(c["NUM_ROWS"]) * int(c["NUM_RACKS_PER_ROW"])
+    for key in ("RACK_SUPPLY_APPROACH_TEMP_LIST", "RACK_RETURN_APPROACH_TEMP_LIST", "DEFAULT_SERVER_POWER_CHARACTERISTICS"):
+        c[key] = _cycled(c[key], n)
+    return c
+
+
 class RackModel:
     """Per-rack closed form of the reference's per-CPU vectorised model (all CPUs of a rack are identical)."""
 

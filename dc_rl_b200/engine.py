@@ -19,11 +19,11 @@ _STATE_DTYPES = {
     "episode": np.uint32, "t": np.int32, "t0": np.int32, "step_in_ep": np.int32, "ci_min": np.float64, "ci_max": np.float64,
     "t_min": np.float64, "t_max": np.float64, "weather": np.float64, "ls_head": np.int32, "ls_len": np.int32,
     "ls_sum": np.int32, "ls_bins": np.uint16, "ls_ring": np.uint8, "setpoint": np.float64, "dc_run": np.int32,
-    "dc_scale": np.int32, "dc_last": np.int8, "bat_load": np.float64, "hist": np.float32, "hist_len": np.int32,
+    "dc_scale": np.int32, "dc_last": np.int8, "bat_load": np.float64, "hist": np.float32, "hist_ref": np.float64, "hist_len": np.int32,
     "hist_head": np.int32, "phase_clocks": np.uint64, "qlist": np.float32, "q_a": np.int32, "q_m": np.int32, "err": np.int32,
     "mom_s1": np.float64, "mom_s2": np.float64, "mom_c0": np.float64, "tails": np.float32, "tail_n": np.int32,
     "tail_thr": np.float32, "agg_n": np.int32, "agg_s": np.float64, "fast_cfg": np.uint32, "counters": np.int32, "pass_stats": np.int32,
-    "pend_valid": np.uint8,
+    "pend_valid": np.uint8, "metrics": np.float64, "hvac_hist": np.uint64,
 }
 
 _default_lib = None
@@ -114,6 +114,18 @@ class Engine:
         for k, v in kw.items():
             self._check(self.lib.sdc_set_tuning(self._h, k.encode(), int(v)))
 
+    def set_reward_methods(self, ls="default_ls_reward", dc="default_dc_reward", bat="default_bat_reward"):
+        """Reward method per agent by the reference's names (utils/reward_creator.py:322-334)."""
+        ids = []
+        for name in (ls, dc, bat):
+            if name in ("renewable_energy_reward", "temperature_efficiency_reward"):
+                raise AssertionError("%s needs keys the reference env never provides (utils/reward_creator.py:217,283)" % name)
+            if name not in _lib.REWARD_METHOD_IDS:
+                raise AssertionError("Specified Reward Method %s not in REWARD_METHOD_MAP" % name)       # reward_creator.py:346
+            ids.append(_lib.REWARD_METHOD_IDS[name])
+        self._check(self.lib.sdc_set_reward_methods(self._h, *ids))
+        self.reward_methods = (ls, dc, bat)
+
     # ---- episodes ------------------------------------------------------------------------------
     def stage_episode(self, env_ids, day, hour, temp_win, wetb_win, t_min30, t_max30):
         """Replay mode: the next reset of `env_ids` uses these starts / realised weather windows
@@ -192,6 +204,8 @@ class Engine:
 
     def prefill_history(self, values):
         """values: fp32 [count] (shared by all envs) or [N, count]."""
+        if getattr(self, "reward_methods", ("default_ls_reward",))[0] != "default_ls_reward":
+            raise NotImplementedError("a pre-filled reward window with a non-default ls_reward (the window never changes) is not supported")
         v = np.ascontiguousarray(values, np.float32)
         per_env = int(v.ndim == 2)
         count = v.shape[-1]
@@ -211,6 +225,8 @@ class Engine:
             out = np.zeros(64, dt)
         elif name == "pass_stats":
             out = np.zeros(4, dt)
+        elif name in ("metrics", "hvac_hist"):
+            out = np.zeros(_lib.HVAC_BINS if name == "hvac_hist" else N_METRICS, dt)
         elif name == "tails":
             out = np.zeros(((n + 31) // 32) * 2 * _lib.TAIL_CAP * 32, dt)
         elif name == "ls_ring":
@@ -219,7 +235,7 @@ class Engine:
             out = np.zeros(n * per_env, dt)
         got = self._check(self.lib.sdc_read_state(self._h, name.encode(), _ptr(out), out.nbytes))
         out = out[:got // dt.itemsize]
-        if name in ("phase_clocks", "counters", "pass_stats"):
+        if name in ("phase_clocks", "counters", "pass_stats", "metrics", "hvac_hist"):
             return out
         if name == "tails":
             return out.reshape(-1, 2, _lib.TAIL_CAP, 32)         # [env // 32][side][slot][env % 32]

@@ -57,18 +57,22 @@ def hour_table():
 class LocationTraces:
     """Device-ready tables of one location (all length YEAR_STEPS + TRACE_PAD)."""
 
-    def __init__(self, cpu_load, avg_ci, dry_bulb, wet_bulb, name="custom"):
+    def __init__(self, cpu_load, avg_ci, dry_bulb, wet_bulb, name="custom", timezone_shift=0):
+        """timezone_shift (hours): every 15-min trace is rolled by -4*shift samples right after the interpolation, as the
+        reference managers do (managers.py:188,377,557-558)."""
         self.name = name
-        cpu = interp15(np.asarray(cpu_load, np.float64)[:HOURS])
+        self.timezone_shift = int(timezone_shift)
+        sh = -4 * self.timezone_shift
+        cpu = np.roll(interp15(np.asarray(cpu_load, np.float64)[:HOURS]), sh)
         p5, p95 = np.percentile(cpu, 5), np.percentile(cpu, 95)
         scaled = np.clip(0.2 + ((cpu - p5) * (0.8 - 0.2) / (p95 - p5)), 0, 1)
         workload = np.convolve(scaled, np.ones(16) / 16, mode="same")
         ci_h = np.asarray(avg_ci, np.float64)[:HOURS]
         if np.isnan(ci_h).any():
             ci_h = np.nan_to_num(ci_h, nan=np.nanmean(ci_h))
-        ci = np.clip(interp15(ci_h), 0, None)
-        temp = interp15(np.asarray(dry_bulb, np.float64)[:HOURS])
-        wetb = interp15(np.asarray(wet_bulb, np.float64)[:HOURS])
+        ci = np.clip(np.roll(interp15(ci_h), sh), 0, None)
+        temp = np.roll(interp15(np.asarray(dry_bulb, np.float64)[:HOURS]), sh)
+        wetb = np.roll(interp15(np.asarray(wet_bulb, np.float64)[:HOURS]), sh)
         for arr in (workload, ci, temp, wetb):
             if len(arr) != YEAR_STEPS:
                 raise ValueError("traces must cover 8760 hours")
@@ -84,44 +88,53 @@ class LocationTraces:
         self.wetb_base = _pad(wetb, np.float64)
 
     @classmethod
-    def from_hourly_columns(cls, cpu_load, avg_ci, dry_bulb, rel_hum_pct, pressure_pa, name="custom"):
+    def from_hourly_columns(cls, cpu_load, avg_ci, dry_bulb, rel_hum_pct, pressure_pa, name="custom", timezone_shift=0):
         """Wet bulb from (dry bulb, RH %, station pressure) like managers.py:521-530."""
         wet = [psychro.wet_bulb_from_rel_hum(t, rh / 100, p) for t, rh, p in zip(dry_bulb, rel_hum_pct, pressure_pa)]
-        return cls(cpu_load, avg_ci, dry_bulb, wet, name)
+        return cls(cpu_load, avg_ci, dry_bulb, wet, name, timezone_shift)
 
     @classmethod
-    def from_npz(cls, path, name=None):
+    def from_npz(cls, path, name=None, timezone_shift=0):
         """Hourly columns saved as npz (keys cpu_load, avg_ci, dry_bulb, rel_hum, pressure)."""
         z = np.load(path, allow_pickle=False)
         return cls.from_hourly_columns(z["cpu_load"], z["avg_ci"], z["dry_bulb"], z["rel_hum"], z["pressure"],
-                                       name or os.path.basename(path))
+                                       name or os.path.basename(path), timezone_shift)
 
     @classmethod
-    def from_reference_data(cls, data_root, location, workload_file="Alibaba_CPU_Data_Hourly_1.csv"):
+    def from_reference_data(cls, data_root, location, workload_file="Alibaba_CPU_Data_Hourly_1.csv", timezone_shift=0):
         """Reads the reference's data/ tree: Workload/*.csv (cpu_load), CarbonIntensity/<loc>_NG_&_avgCI.csv
         (avg_CI), Weather/*.epw (columns 6, 8, 9 after 8 header rows) -- managers.py:168-174,345-351,521-528;
         file choice per location as utils/utils_cf.py:11-40."""
         ci_loc, epw = LOCATION_FILES[location_key(location)]
+        wl_path = os.path.join(data_root, "Workload", workload_file)
+        ci_path = os.path.join(data_root, "CarbonIntensity", "%s_NG_&_avgCI.csv" % ci_loc)
+        epw_path = os.path.join(data_root, "Weather", epw)
+        try:
+            # The reference parses with pandas.read_csv, whose default float parser is NOT correctly rounded (it can differ
+            # from float() in the last bit): use the same parser when pandas is there, so the tables are bit-identical.
+            import pandas as pd
+            cpu = pd.read_csv(wl_path)["cpu_load"].values[:HOURS].astype(np.float64)
+            ci = pd.read_csv(ci_path)["avg_CI"].values[:HOURS].astype(np.float64)
+            wea = pd.read_csv(epw_path, skiprows=8, header=None).values[:, [6, 8, 9]].astype(np.float64)
+        except ImportError:
+            def column(path, name):
+                with open(path) as f:
+                    header = f.readline().strip().split(",")
+                    idx = header.index(name)
+                    return np.array([float(line.split(",")[idx] or "nan") for line in f if line.strip()])
 
-        def column(path, name):
-            with open(path) as f:
-                header = f.readline().strip().split(",")
-                idx = header.index(name)
-                return np.array([float(line.split(",")[idx] or "nan") for line in f if line.strip()])
-
-        cpu = column(os.path.join(data_root, "Workload", workload_file), "cpu_load")
-        ci = column(os.path.join(data_root, "CarbonIntensity", "%s_NG_&_avgCI.csv" % ci_loc), "avg_CI")
-        rows = []
-        with open(os.path.join(data_root, "Weather", epw)) as f:
-            for i, line in enumerate(f):
-                if i >= 8 and line.strip():
-                    parts = line.split(",")
-                    rows.append((float(parts[6]), float(parts[8]), float(parts[9])))
-        wea = np.array(rows)
-        return cls.from_hourly_columns(cpu, ci, wea[:, 0], wea[:, 1], wea[:, 2], location)
+            cpu, ci = column(wl_path, "cpu_load"), column(ci_path, "avg_CI")
+            rows = []
+            with open(epw_path) as f:
+                for i, line in enumerate(f):
+                    if i >= 8 and line.strip():
+                        parts = line.split(",")
+                        rows.append((float(parts[6]), float(parts[8]), float(parts[9])))
+            wea = np.array(rows)
+        return cls.from_hourly_columns(cpu, ci, wea[:, 0], wea[:, 1], wea[:, 2], location, timezone_shift)
 
     @classmethod
-    def synthetic(cls, location="ny", seed=1234):
+    def synthetic(cls, location="ny", seed=1234, timezone_shift=0):
         """Seeded synthetic 1-year traces with the moments of the shipped files (SURVEY.md section 8d,
         config 3): used by bench.py, where the reference's data files are not available."""
         rng = np.random.default_rng(seed + {"ny": 0, "az": 1, "wa": 2}.get(location.lower(), 3))
@@ -144,7 +157,7 @@ class LocationTraces:
             front[i] = acc
         dry = mean_t - 11.5 * np.cos(year) + 4.0 * np.sin(day - 2.4) + np.clip(front, -9, 9)
         wet = dry - rng.uniform(1.0, 5.0, HOURS)
-        return cls(cpu, ci, dry, wet, "synthetic-" + location)
+        return cls(cpu, ci, dry, wet, "synthetic-" + location, timezone_shift)
 
 
 # location -> (carbon-intensity region, EPW file), reference utils/utils_cf.py:11-40

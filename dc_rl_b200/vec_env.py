@@ -6,6 +6,7 @@ shapes and dtypes, same auto-reset contract (when an env finishes, the returned 
 ones and ``infos[i][0]`` carries ``original_obs`` / ``original_state`` / ``original_avail_actions``,
 env_wrappers.py:173-192), so ``harl.runners`` drive it unchanged.  One process, one CUDA library handle, no pipes.
 """
+import json
 import os
 
 import numpy as np
@@ -62,22 +63,25 @@ def make_spaces(nonoverlapping_shared_obs_space=True):
     return obs, share, act
 
 
-def resolve_traces(location, workload_file="Alibaba_CPU_Data_Hourly_1.csv", data_root=None, traces=None):
-    """Traces for a location: an explicit LocationTraces, the reference's data/ tree (``data_root`` or
-    $SDC_DATA_ROOT), or -- only when asked for with traces='synthetic' -- the seeded synthetic year."""
+def resolve_traces(location, workload_file="Alibaba_CPU_Data_Hourly_1.csv", data_root=None, traces=None, timezone_shift=0):
+    """Traces for a location: an explicit LocationTraces (or a {location key: LocationTraces} dict), the reference's
+    data/ tree (``data_root`` or $SDC_DATA_ROOT), or -- only when asked for with traces='synthetic' -- the seeded
+    synthetic year.  timezone_shift rolls the traces like the reference managers (managers.py:188,377,557-558)."""
+    if isinstance(traces, dict):
+        traces = traces[location_key(location)]
     if isinstance(traces, LocationTraces):
+        if int(timezone_shift) != traces.timezone_shift:
+            raise ValueError("explicit LocationTraces were built with timezone_shift=%d, env_args asks for %d" % (
+                traces.timezone_shift, int(timezone_shift)))
         return traces
     if traces == "synthetic":
-        return LocationTraces.synthetic(location_key(location))
+        return LocationTraces.synthetic(location_key(location), timezone_shift=timezone_shift)
     root = data_root or os.environ.get("SDC_DATA_ROOT")
     if root and os.path.isdir(root):
-        return LocationTraces.from_reference_data(root, location, workload_file)
+        return LocationTraces.from_reference_data(root, location, workload_file, timezone_shift)
     raise FileNotFoundError(
         "no trace data for location %r: pass env_args['data_root'] (the reference's data/ directory), set SDC_DATA_ROOT, "
         "or request env_args['traces']='synthetic'" % location)
-
-
-_UNSUPPORTED_REWARDS = "only the default reward methods (default_{ls,dc,bat}_reward) run on the device"
 
 
 class InfoRow:
@@ -172,26 +176,55 @@ class InfoBatch:
         return self.table[info_layout.COL[key]]
 
 
+def _cyclic(value, index):
+    """Per-env value of an env_args entry: scalars apply to every env, lists / tuples are cycled by `index`."""
+    if isinstance(value, (list, tuple)):
+        return [value[int(i) % len(value)] for i in index]
+    return [value] * len(index)
+
+
 class CudaShareVecEnv:
-    """harl ``ShareVecEnv`` surface over one `Engine` (see module docstring)."""
+    """harl ``ShareVecEnv`` surface over one `Engine` (see module docstring).
+
+    env_args are the reference's (sustaindc_env.py:38-80; harl/configs/envs_cfgs/sustaindc.yaml) plus additive keys:
+    ``traces`` / ``data_root`` (where the year traces come from), ``device``.  ``location`` and ``dc_config_file`` may be
+    LISTS: env with global id i then gets ``location[i % len(location)]`` and ``dc_config_file[(i // len(location)) %
+    len(dc_config_file)]`` (BASELINE config 4: {az, ny, wa} x {dc1, dc2, dc3}); every distinct (dc_config, location) pair is
+    sized once (utils/make_envs_pyenv.py:149-218 uses the location's design ambient) and selected per env on the device.
+    Dead keys of the reference (weather_file, cintensity_file, flexible_load, individual_reward_weight, max_bat_cap_Mw,
+    evaluation) are accepted and ignored, as there."""
 
     def __init__(self, env_args, n_envs, seed=0, months=None, seeds=None, device=0, lib=None, first_env_id=0):
         args = dict(env_args)
-        for key in ("ls_reward", "dc_reward", "bat_reward"):
-            if args.get(key, "default_%s" % key) != "default_%s" % key:
-                raise NotImplementedError(_UNSUPPORTED_REWARDS)
         self.env_args = args
         self.num_envs = int(n_envs)
         self.n_agents = N_AGENTS
         self.nonoverlapping = bool(args.get("nonoverlapping_shared_obs_space", False))
         self.observation_space, self.share_observation_space, self.action_space = make_spaces(self.nonoverlapping)
-        location = args.get("location", "ny")
-        traces = resolve_traces(location, args.get("workload_file", "Alibaba_CPU_Data_Hourly_1.csv"), args.get("data_root"),
-                                args.get("traces"))
-        cfg_file = args.get("dc_config_file", "dc_config.json")
-        cfg = cfg_file if isinstance(cfg_file, dict) else _find_dc_config(cfg_file, args.get("data_root"))
-        params, self.derived = size_datacenter(location, cfg, args.get("datacenter_capacity_mw", 1))
         ids = np.arange(first_env_id, first_env_id + self.num_envs)
+        location = args.get("location", "ny")
+        n_loc_cycle = len(location) if isinstance(location, (list, tuple)) else 1
+        env_loc = [location_key(x) for x in _cyclic(location, ids)]
+        env_cfg = _cyclic(args.get("dc_config_file", "dc_config.json"), ids // n_loc_cycle)
+        tz = int(args.get("timezone_shift", 0))
+        loc_keys, traces = [], []
+        cfg_keys, params, self.derived_all = [], [], []
+        loc_id, cfg_id = np.zeros(self.num_envs, np.uint8), np.zeros(self.num_envs, np.uint8)
+        flat_cache = {}
+        for i, (lk, cf) in enumerate(zip(env_loc, env_cfg)):
+            if lk not in loc_keys:
+                loc_keys.append(lk)
+                traces.append(resolve_traces(lk, args.get("workload_file", "Alibaba_CPU_Data_Hourly_1.csv"), args.get("data_root"),
+                                             args.get("traces"), tz))
+            ck = (json.dumps(cf, sort_keys=True) if isinstance(cf, dict) else str(cf), lk)
+            if ck not in cfg_keys:
+                if ck[0] not in flat_cache:
+                    flat_cache[ck[0]] = cf if isinstance(cf, dict) else _find_dc_config(cf, args.get("data_root"))
+                p, d = size_datacenter(lk, flat_cache[ck[0]], args.get("datacenter_capacity_mw", 1))
+                cfg_keys.append(ck); params.append(p); self.derived_all.append(d)
+            loc_id[i], cfg_id[i] = loc_keys.index(lk), cfg_keys.index(ck)
+        self.derived = self.derived_all[0]
+        self.env_location, self.env_dc_config = env_loc, [k[0] for k in (cfg_keys[c] for c in cfg_id)]
         if months is None:
             if "month" in args:                                   # harl/utils/envs_tools.py:56-62
                 months = np.full(self.num_envs, int(args["month"]))
@@ -199,8 +232,11 @@ class CudaShareVecEnv:
                 months = np.where(ids < 12, ids % 12, ids % 3 + 5)
         if seeds is None:
             seeds = (int(seed) + ids * 1000).astype(np.uint64)   # envs_tools.py:67
-        self.engine = Engine(self.num_envs, [traces], [params], months=months, seeds=seeds,
+        self.engine = Engine(self.num_envs, traces, params, loc_id=loc_id, cfg_id=cfg_id, months=months, seeds=seeds,
                              days_per_episode=int(args.get("days_per_episode", 7)), device=device, lib=lib)
+        rewards = [args.get(key, "default_%s" % key) for key in ("ls_reward", "dc_reward", "bat_reward")]
+        if rewards != ["default_ls_reward", "default_dc_reward", "default_bat_reward"]:
+            self.engine.set_reward_methods(*rewards)              # sustaindc_env.py:137-144
         self.closed = False
         self._avail = np.ones((self.num_envs, N_AGENTS, 3), np.float32)
 

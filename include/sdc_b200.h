@@ -50,6 +50,16 @@ extern "C" {
 #define SDC_F_BRACKET 0x10         /* internal: quartile bracket invariant broken (bug guard)      */
 #define SDC_F_NONFINITE 0x20       /* non-finite energy value                                      */
 #define SDC_F_BATTERY 0x40         /* envs/bat_env_fwd_view.py:237 discharge > DC energy           */
+#define SDC_F_REWARD_DOMAIN 0x80   /* utils/reward_creator.py:191 tou_reward off the full hour (KeyError there) */
+
+/* reward methods (utils/reward_creator.py:322-334, selected per agent at sustaindc_env.py:137-144) */
+#define SDC_R_DEFAULT_LS 0         /* default_ls_reward  :48-82   (agent_ls only: it alone appends to the window, :62-63) */
+#define SDC_R_DEFAULT_DC 1         /* default_dc_reward / default_bat_reward :85-130 (the same function)  */
+#define SDC_R_CUSTOM 2             /* custom_agent_reward :133-146 -> 0.0                                 */
+#define SDC_R_TOU 3                /* tou_reward :154-202                                                  */
+#define SDC_R_ENERGY_EFFICIENCY 4  /* energy_efficiency_reward :227-243                                    */
+#define SDC_R_PUE 5                /* energy_PUE_reward :246-268                                           */
+#define SDC_R_WATER 6              /* water_usage_efficiency_reward :297-318                               */
 
 typedef struct sdc_env sdc_env;
 
@@ -117,6 +127,11 @@ int sdc_set_hour_table(sdc_env* env, const double* cos96, const double* sin96);
  * (make_train_env month/seed rules, harl/utils/envs_tools.py:56-67; sustaindc_env.py:197-198). */
 int sdc_assign(sdc_env* env, const uint8_t* loc_id, const uint8_t* cfg_id, const int16_t* day_lo,
                const int16_t* day_hi, const uint64_t* seed);
+
+/* Reward method of each agent (SDC_R_*; default: DEFAULT_LS, DEFAULT_DC, DEFAULT_DC).  Replaces get_reward_method
+ * (utils/reward_creator.py:336-349).  When agent_ls does not use default_ls_reward nothing appends to the reward window
+ * (utils/reward_creator.py:62-63): the default dc / bat rewards are then computed against the empty window, i.e. 0. */
+int sdc_set_reward_methods(sdc_env* env, int32_t ls, int32_t dc, int32_t bat);
 
 /* ---- episodes ------------------------------------------------------------------------------ */
 /* Replay ("injection") mode: stage the NEXT episode of `count` envs: start (day, hour), the realised

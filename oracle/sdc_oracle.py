@@ -204,8 +204,9 @@ def interp15(hourly):
 class Traces:
     """Per-location traces at 15-min resolution built from the hourly input columns."""
 
-    def __init__(self, cpu_load, avg_ci, dry_bulb, wet_bulb_hourly):
-        cpu = interp15(cpu_load[:8760])
+    def __init__(self, cpu_load, avg_ci, dry_bulb, wet_bulb_hourly, timezone_shift=0):
+        roll = lambda x: np.roll(x, -1 * timezone_shift * 4)              # noqa: E731  managers.py:188,377,557-558
+        cpu = roll(interp15(cpu_load[:8760]))
         # workload: percentile rescale + 16-tap smoothing at every reset, deterministic (managers.py:220-244,268-271)
         p5, p95 = np.percentile(cpu, 5), np.percentile(cpu, 95)
         scaled = np.clip(0.2 + ((cpu - p5) * (0.8 - 0.2) / (p95 - p5)), 0, 1)
@@ -213,14 +214,14 @@ class Traces:
         ci = np.asarray(avg_ci[:8760], dtype=float)
         if np.isnan(ci).any():
             ci = np.nan_to_num(ci, nan=np.nanmean(ci))                     # managers.py:359-361
-        self.ci = np.clip(interp15(ci), 0, None)                            # managers.py:417
-        self.temp_base = interp15(dry_bulb)                                 # managers.py:550
-        self.wetb_base = interp15(wet_bulb_hourly)                          # managers.py:547
+        self.ci = np.clip(roll(interp15(ci)), 0, None)                      # managers.py:417
+        self.temp_base = roll(interp15(dry_bulb))                           # managers.py:550
+        self.wetb_base = roll(interp15(wet_bulb_hourly))                    # managers.py:547
 
     @staticmethod
-    def from_golden(npz, wet_bulb_fn):
+    def from_golden(npz, wet_bulb_fn, timezone_shift=0):
         wb = [wet_bulb_fn(t, rh / 100, p) for t, rh, p in zip(npz["dry_bulb"], npz["rel_hum"], npz["pressure"])]
-        return Traces(npz["cpu_load"], npz["avg_ci"], npz["dry_bulb"], wb)
+        return Traces(npz["cpu_load"], npz["avg_ci"], npz["dry_bulb"], wb, timezone_shift)
 
 
 def weather_reset(traces, t0, np_rng=np.random):
@@ -281,7 +282,7 @@ class OracleEnv:
     """One SustainDC env. `history` is private to the instance (the reference keeps one per process)."""
 
     def __init__(self, traces, location="ny", month=0, days_per_episode=7, dc_cfg=None,
-                 py_rng=_pyrandom, np_rng=np.random):
+                 py_rng=_pyrandom, np_rng=np.random, reward_methods=None):
         self.tr = traces
         self.dc, self.consts = size_datacenter(location, dc_cfg)
         self.cap = self.consts["bat_capacity"]
@@ -292,6 +293,8 @@ class OracleEnv:
         self.history = deque(maxlen=HIST_MAX)
         self.setpoint = SP_INIT                                              # dc_gym.py:77, survives reset()
         self.injected = None
+        # (ls, dc, bat) reward method names, sustaindc_env.py:137-144 / utils/reward_creator.py:322-334
+        self.reward_methods = tuple(reward_methods or ("default_ls_reward", "default_dc_reward", "default_bat_reward"))
 
     # -- reset ---------------------------------------------------------------------------------
     def inject_episode(self, day, hour, temp_window, wetb_window, t_min30, t_max30):
@@ -471,14 +474,36 @@ class OracleEnv:
         obs = self._observe(soc=b / cap_b)
         # ---- rewards (reward_creator.py:16-130; ls first: it alone appends to the history)
         norm_ci_next = self.norm_ci[self.t + 1]
-        self.history.append(energy)
-        z = normalize_energy(self.history, energy)
-        foot = -1.0 * (norm_ci_next * z / 0.50)
-        r_ls = np.clip(foot + (-0.3 * np.sqrt(over) + 0.3) + (-0.1 * (oldest / 24)), -10, 10)
-        rewards = (r_ls, foot, foot)
         info.update(outside_temp=self.temp[self.t], day=self.day, hour=self.hour, norm_CI=norm_ci_next,
                     forecast_CI=self.norm_ci[self.t + 1:self.t + 9], isterminal=terminal)
+        # sustaindc_env.py:721-737: the three methods are called in the order ls, dc, bat on the same params
+        rewards = tuple(self._reward(name, info) for name in self.reward_methods)
         return obs, rewards, terminal, info
+
+    def _reward(self, name, p):
+        """utils/reward_creator.py:48-318 (the methods usable as shipped)."""
+        if name in ("default_ls_reward", "default_dc_reward", "default_bat_reward"):
+            energy = p["bat_total_energy_with_battery_KWh"]
+            if name == "default_ls_reward":
+                self.history.append(energy)                                 # :62-63 -- the only place the window grows
+            foot = -1.0 * (p["norm_CI"] * normalize_energy(self.history, energy) / 0.50)
+            if name != "default_ls_reward":
+                return foot
+            return np.clip(foot + (-0.3 * np.sqrt(p["ls_overdue_penalty"]) + 0.3) + (-0.1 * p["ls_oldest_task_age"]), -10, 10)
+        if name == "custom_agent_reward":
+            return 0.0                                                      # :133-146
+        if name == "tou_reward":                                            # :154-202 (KeyError off the full hour)
+            tou = {h: v for hs, v in (((0, 1, 2, 3, 4, 5, 22, 23), 0.25), ((6, 7, 8, 9, 10), 0.41), ((11, 12, 13, 14, 15), 0.30),
+                                      ((16, 17, 18, 19, 20, 21), 0.27)) for h in hs}
+            return -1.0 * p["bat_total_energy_with_battery_KWh"] * tou[p["hour"]]
+        if name == "energy_efficiency_reward":
+            return p["dc_ITE_total_power_kW"] / p["dc_total_power_kW"]      # :227-243
+        if name == "energy_PUE_reward":                                     # :246-268
+            pue = p["dc_total_power_kW"] / p["dc_ITE_total_power_kW"] if p["dc_ITE_total_power_kW"] != 0 else float("inf")
+            return -abs(pue - 1)
+        if name == "water_usage_efficiency_reward":
+            return -0.01 * p["dc_water_usage"]                              # :297-318
+        raise AssertionError("%s needs keys the env never provides (reward_creator.py:217,283)" % name)
 
 
 def normalize_energy(history, value):

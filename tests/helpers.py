@@ -15,11 +15,23 @@ def load_traj(name):
 
 
 @functools.lru_cache(maxsize=None)
-def oracle_traces(loc):
+def oracle_traces(loc, timezone_shift=0):
     import sdc_oracle
     from dc_rl_b200 import psychro
     z = np.load(os.path.join(GOLDEN, f"loc_{loc}.npz"), allow_pickle=False)
-    return sdc_oracle.Traces.from_golden(z, psychro.wet_bulb_from_rel_hum)
+    return sdc_oracle.Traces.from_golden(z, psychro.wet_bulb_from_rel_hum, timezone_shift)
+
+
+def reward_methods_of(cfg):
+    """(ls, dc, bat) reward method names of a trajectory config (defaults as sustaindc_env.py:63-65)."""
+    return tuple(cfg.get(k, "default_%s" % k) for k in ("ls_reward", "dc_reward", "bat_reward"))
+
+
+@functools.lru_cache(maxsize=None)
+def dc_configs():
+    """utils/dc_config_dc{1,2,3}.json of the reference (fixture minted by oracle/make_golden_r2.py)."""
+    with open(os.path.join(GOLDEN, "dc_configs.json")) as f:
+        return json.load(f)
 
 
 @functools.lru_cache(maxsize=None)

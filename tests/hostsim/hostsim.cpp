@@ -41,6 +41,9 @@ static const char* event_create(Context&, void** ev) { *ev = nullptr; return nul
 static const char* event_record(Context&, void*, void*) { return nullptr; }
 static const char* event_elapsed_ms(Context&, void*, void*, double* ms) { *ms = 0.0; return nullptr; }
 static void event_destroy(Context&, void*) {}
+static void range_push(const char*) {}
+static void range_pop() {}
+static int max_window_len() { return SDC_YEAR_STEPS; }
 
 struct ObsRow {
     float* row;   // [3][26]
@@ -124,9 +127,13 @@ static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs&
             Q.lst[j] = S.qlist + ((size_t)env * 2 + j) * sdc::kListCap; Q.a[j] = S.q_a[env * 2 + j]; Q.m[j] = S.q_m[env * 2 + j];
         }
         sdc::ListEdit edits[2];
-        sdc::reward_prepare(S, env, st.energy, st.hist_len, st.hist_head, st.evicted, Q, rq, edits);
-        for (int j = 0; j < 2; ++j) sdc::edit_apply(Q.lst[j], edits[j]);          // the CUDA kernel does this warp-cooperatively
-        sdc::reward_plan(S, env, rq, mo);
+        rq.kind = sdc::SCAN_SKIP; rq.n = 0; rq.degenerate = 0; rq.dir[0] = rq.dir[1] = 0; mo.ok = 0;
+        double e_rel = st.energy;                                                  // becomes relative to the env's hist_ref
+        if (S.append_history) {
+            sdc::reward_prepare(S, env, e_rel, st.hist_len, st.hist_head, st.evicted, Q, rq, edits);
+            for (int j = 0; j < 2; ++j) sdc::edit_apply(Q.lst[j], edits[j]);      // the CUDA kernel does this warp-cooperatively
+            sdc::reward_plan(S, env, rq, mo);
+        }
         if (rq.kind == sdc::SCAN_PLAIN) {
             scan_plain(S, env, rq, rs);
             a.ctr[4] += 1;
@@ -138,8 +145,13 @@ static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs&
             sdc::refresh_commit(S, env, rq, raw, sorted, Q, rs, 0, 1);
             a.ctr[5] += 1;
         }
-        sdc::RewardInputs en{st.energy, st.nci_next, st.ls_penalty};
-        sdc::reward_finish(S, env, rq, rs, mo, en, Q, a.rew + (size_t)env * 3);
+        sdc::RewardInputs en{e_rel, st.nci_next, st.ls_penalty};
+        float alt3[3] = {0.f, 0.f, 0.f};
+        if (sdc::any_alt_reward(S)) {
+            const sdc::AltInputs ai{st.ite_kw, st.total_kw, st.water, od.tn % 96};
+            sdc::alt_rewards(S, env, st.energy, ai, alt3);
+        }
+        sdc::reward_finish(S, env, rq, rs, mo, en, alt3, Q, a.rew + (size_t)env * 3);
         for (int j = 0; j < 2; ++j) { S.q_a[env * 2 + j] = Q.a[j]; S.q_m[env * 2 + j] = Q.m[j]; }
         a.done[env] = (uint8_t)st.terminal;
         if (st.terminal) {

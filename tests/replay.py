@@ -6,15 +6,15 @@ from dc_rl_b200 import info_layout
 from dc_rl_b200.dc_config import size_datacenter
 from dc_rl_b200.engine import Engine
 from dc_rl_b200.traces import LocationTraces
-from helpers import GOLDEN, load_traj, traj_cfg
+from helpers import GOLDEN, load_traj, reward_methods_of, traj_cfg
 
 import functools
 import os
 
 
 @functools.lru_cache(maxsize=None)
-def location_traces(loc):
-    return LocationTraces.from_npz(os.path.join(GOLDEN, "loc_%s.npz" % loc), loc)
+def location_traces(loc, timezone_shift=0):
+    return LocationTraces.from_npz(os.path.join(GOLDEN, "loc_%s.npz" % loc), loc, timezone_shift)
 
 
 def scaled_err(a, b):
@@ -29,8 +29,12 @@ def make_engine(g, lib, n_envs=1, **kw):
         from dc_rl_b200.dc_config import synthetic_dc_config
         dc_cfg = synthetic_dc_config(*cfg["dc_geometry"])
     params, _ = size_datacenter(cfg["location"], dc_cfg)
-    return Engine(n_envs, [location_traces(cfg["location"])], [params], months=cfg["month"],
-                  days_per_episode=cfg["days_per_episode"], lib=lib, **kw)
+    eng = Engine(n_envs, [location_traces(cfg["location"], cfg.get("timezone_shift", 0))], [params], months=cfg["month"],
+                 days_per_episode=cfg["days_per_episode"], lib=lib, **kw)
+    methods = reward_methods_of(cfg)
+    if methods != ("default_ls_reward", "default_dc_reward", "default_bat_reward"):
+        eng.set_reward_methods(*methods)
+    return eng
 
 
 def stage(eng, g, k, env_ids):

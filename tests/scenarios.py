@@ -213,7 +213,7 @@ def incremental_normaliser_under_drift(lib, steps=1300, N=48):
             scans += eng.read_state("pass_stats")[:2]
             if s % 61 == 0 or s >= steps - 3:
                 check_incremental_state(eng, tag=(name, s))
-                hist = eng.read_state("hist").astype(np.float64)
+                hist = eng.read_state("hist").astype(np.float64) + eng.read_state("hist_ref").reshape(-1, 1)   # window values are stored relative to the env's first sample
                 e, nci = info[col_e].astype(np.float64), info[col_ci].astype(np.float64)
                 for i in range(N):
                     w = hist[i]

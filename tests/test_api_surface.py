@@ -1,6 +1,7 @@
-"""CPU tests of the reference-facing Python surface (CudaShareVecEnv / InfoBatch / SustainDC / make_*_env /
-multi-process sharding) with the engine bound to the serial hostsim build of the device logic, plus the check
-that the product library loads and exports every symbol include/sdc_b200.h declares."""
+"""Tests of the reference-facing Python surface (CudaShareVecEnv / InfoBatch / SustainDC / make_*_env / multi-process
+sharding).  Every test that takes `lib` runs twice: on the serial hostsim build of the device logic (CPU suite) and, marked
+`gpu`, on libsdc_b200.so itself.  Plus the check that the product library loads and exports every symbol
+include/sdc_b200.h declares."""
 import os
 import re
 import subprocess
@@ -9,16 +10,17 @@ import sys
 import numpy as np
 import pytest
 
-import hostsim_build
 import sdc_oracle
+from conftest import lib_params, resolve_lib
 from helpers import load_traj, oracle_traces, traj_cfg
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def lib():
-    return hostsim_build.load()
+@pytest.fixture(scope="module", params=lib_params())
+def lib(request):
+    request.module._LIB_KIND = request.param
+    return resolve_lib(request.param)
 
 
 def test_library_exports_every_declared_symbol():
@@ -219,20 +221,22 @@ def test_requires_data_or_explicit_synthetic(lib):
     finally:
         if old:
             os.environ["SDC_DATA_ROOT"] = old
-    with pytest.raises(NotImplementedError):
-        CudaShareVecEnv({"location": "ny", "traces": "synthetic", "ls_reward": "tou_reward"}, 1, lib=lib)
+    with pytest.raises(AssertionError):       # utils/reward_creator.py:346 asserts on unknown names
+        CudaShareVecEnv({"location": "ny", "traces": "synthetic", "ls_reward": "no_such_reward"}, 1, lib=lib)
+    with pytest.raises(AssertionError):       # :217 -- needs a key the env never provides
+        CudaShareVecEnv({"location": "ny", "traces": "synthetic", "dc_reward": "renewable_energy_reward"}, 1, lib=lib)
 
 
 _WORKER = r"""
 import os, sys
 sys.path[:0] = [{repo!r}, {repo!r} + "/tests"]
 import numpy as np, torch.distributed as dist
-import hostsim_build
+from conftest import resolve_lib
 from dc_rl_b200.distributed import gather_metrics, make_sharded_env, reduce_hvac_histogram, shard_range
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 rank = dist.get_rank()
-args = {{"location": "ny", "traces": "synthetic", "days_per_episode": 1, "nonoverlapping_shared_obs_space": True}}
-env = make_sharded_env(args, 13, seed=5, device=0, lib=hostsim_build.load())
+args = {{"location": ["ny", "az"], "traces": "synthetic", "days_per_episode": 1, "nonoverlapping_shared_obs_space": True}}
+env = make_sharded_env(args, 13, seed=5, device=0, lib=resolve_lib({kind!r}))
 lo, hi = shard_range(13, rank, 2)
 obs, _, _ = env.reset()
 rng = np.random.RandomState(0)
@@ -251,7 +255,8 @@ dist.destroy_process_group()
 
 def test_two_rank_sharding_is_equivalent_to_one_process(lib, tmp_path):
     """N envs on one handle == the same env ids split over 2 ranks (gloo): bit-identical per env, and the one
-    collective (metric all-gather) sums to the single-process metrics."""
+    collective (metric all-gather) sums to the single-process metrics.  Locations alternate per GLOBAL env id, so the
+    shards must pick up the right (location, sizing) per env."""
     from dc_rl_b200.distributed import shard_range
     from dc_rl_b200.vec_env import CudaShareVecEnv
     import socket
@@ -259,11 +264,11 @@ def test_two_rank_sharding_is_equivalent_to_one_process(lib, tmp_path):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     script = tmp_path / "worker.py"
-    script.write_text(_WORKER.format(repo=REPO, port=port, out=str(tmp_path)))
+    script.write_text(_WORKER.format(repo=REPO, port=port, out=str(tmp_path), kind=_LIB_KIND))
     procs = [subprocess.Popen([sys.executable, str(script), str(r)]) for r in range(2)]
     for p in procs:
         assert p.wait(timeout=300) == 0
-    args = {"location": "ny", "traces": "synthetic", "days_per_episode": 1, "nonoverlapping_shared_obs_space": True}
+    args = {"location": ["ny", "az"], "traces": "synthetic", "days_per_episode": 1, "nonoverlapping_shared_obs_space": True}
     env = CudaShareVecEnv(args, 13, seed=5, lib=lib)
     env.reset()
     rng = np.random.RandomState(0)

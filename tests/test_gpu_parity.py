@@ -12,13 +12,12 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def lib():
-    import torch
-    assert torch.cuda.is_available()
-    from dc_rl_b200 import _lib
-    return _lib.load()
+    from conftest import cuda_lib_or_skip
+    return cuda_lib_or_skip()
 
 
-@pytest.mark.parametrize("name", ["ny_m0_s0", "ny_m3_s1", "az_m6_s2", "wa_m9_s3", "ny_m6_dc25x200"])
+@pytest.mark.parametrize("name", ["ny_m0_s0", "ny_m3_s1", "az_m6_s2", "wa_m9_s3", "ny_m6_dc25x200",
+                                  "ny_m6_tz5", "ny_m2_altA", "az_m8_altB", "wa_m4_altC"])
 def test_golden_replay_single_env(lib, name):
     from replay import replay
     w = replay(name, lib)

@@ -14,7 +14,9 @@ def lib():
     return hostsim_build.load()
 
 
-@pytest.mark.parametrize("name", ["ny_m0_s0", "ny_m3_s1", "az_m6_s2", "wa_m9_s3", "ny_m6_dc25x200"])
+@pytest.mark.parametrize("name", ["ny_m0_s0", "ny_m3_s1", "az_m6_s2", "wa_m9_s3", "ny_m6_dc25x200",
+                                  "ny_m6_tz5",                                   # timezone_shift = 5
+                                  "ny_m2_altA", "az_m8_altB", "wa_m4_altC"])     # alternate reward methods
 def test_replay_matches_live_reference(lib, name):
     w = replay(name, lib)
     assert w["err_flags"] == 0

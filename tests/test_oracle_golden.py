@@ -7,10 +7,12 @@ import pytest
 
 import sdc_oracle
 from dc_rl_b200.info_layout import INFO_COLUMNS, info_dict_to_row
-from helpers import kat, load_traj, oracle_traces, rel_err, traj_cfg
+from helpers import kat, load_traj, oracle_traces, rel_err, reward_methods_of, traj_cfg
 
 AG = ("agent_ls", "agent_dc", "agent_bat")
-FULL = ["ny_m0_s0", "ny_m3_s1", "az_m6_s2", "wa_m9_s3", "ny_m6_dc25x200"]
+FULL = ["ny_m0_s0", "ny_m3_s1", "az_m6_s2", "wa_m9_s3", "ny_m6_dc25x200",
+        "ny_m6_tz5",                                    # timezone_shift = 5
+        "ny_m2_altA", "az_m8_altB", "wa_m4_altC"]       # alternate reward methods (utils/reward_creator.py:133-318)
 
 
 def _make(g):
@@ -20,7 +22,8 @@ def _make(g):
         from dc_rl_b200.dc_config import synthetic_dc_config
         nested = synthetic_dc_config(*cfg["dc_geometry"])
         dc_cfg = {k: v for section in nested.values() for k, v in section.items()}     # the oracle takes the flat form
-    return sdc_oracle.OracleEnv(oracle_traces(cfg["location"]), cfg["location"], cfg["month"], cfg["days_per_episode"], dc_cfg=dc_cfg)
+    return sdc_oracle.OracleEnv(oracle_traces(cfg["location"], cfg.get("timezone_shift", 0)), cfg["location"], cfg["month"],
+                                cfg["days_per_episode"], dc_cfg=dc_cfg, reward_methods=reward_methods_of(cfg))
 
 
 def _check_reset(g, k, obs):
