@@ -36,7 +36,6 @@ constexpr int kWexpMax = 6;           // |log2| range of the adaptive interval w
 constexpr int kTailCap = 128;         // values per tail band
 constexpr int kBandTarget = 40;       // a refresh narrows the bands when one holds more values than this
 constexpr int kAlphaOff = 12;         // narrowest tail band: alpha = 0.5 / 2^12 of the IQR
-constexpr int kHandD = 16, kHandI = 6;  // rows of the physics hand-over arrays (StepArgs::hand_d / hand_i)
 constexpr int kPassJobBytes = 192;     // size of one maintenance-pass record (sdc_kernels.cu PassJob)
 constexpr int kTailRetry = 200;       // steps of plain scans before another attempt at tail sets that did not fit
 constexpr double kSpMin = 15.0, kSpMax = 21.6;   // utils/make_envs_pyenv.py:124-126
@@ -89,7 +88,8 @@ struct State {
     int32_t* step_in_ep;
     double* ci_min; double* ci_max;          // CI_Manager 30-day normalisation    managers.py:435-437
     double* t_min; double* t_max;            // Weather_Manager normalisation      managers.py:606-608
-    double* weather;               // [N][2][win_len]: realised dry bulb, wet bulb of the episode
+    double* weather;               // [N][2 buffers][2][win_len]: realised dry bulb, wet bulb of the current and the staged episode
+    uint8_t* cur_buf;              // [N] which buffer holds the current episode (a reset flips it instead of copying 11 KB)
     // load shifting queue as a ring of per-quarter-hour task counts
     int32_t* ls_head; int32_t* ls_len; int32_t* ls_sum;
     uint16_t* ls_bins;             // [N][4] tasks aged [0,6) [6,12) [12,18) [18,24) hours
@@ -113,10 +113,17 @@ struct State {
     int32_t* agg_n; double* agg_s; // [N][2] count, [N][2][2] sum / sum of squares about c0 of the values beyond TL2 / TH2
     uint32_t* fast_cfg;            // [N] byte 0 tail slack exponent, 1 retry countdown, 2/3 interval width exponents (int8)
     int32_t* err;                  // [N] SDC_F_* bits
-    // staged ("injected") next episodes; null until sdc_stage_episode is used
-    uint8_t* pend_valid; int32_t* pend_day; int32_t* pend_hour; double* pend_tmin; double* pend_tmax;
-    double* pend_weather;          // [N][2][win_len]
+    // staged next episodes: written by the look-ahead generation (with the reset observation) or by sdc_stage_episode
+    uint8_t* pend_valid;           // [N] bit 0: the other weather buffer + pend_day / hour / tmin / tmax hold the next episode;
+                                   //     bit 1: pend_obs holds its reset observation
+    int32_t* pend_day; int32_t* pend_hour; double* pend_tmin; double* pend_tmax;
+    float* pend_obs;               // [N][3][26]
 };
+
+// The env's current / staged weather window: [0, win_len) dry bulb, [win_len, 2 win_len) wet bulb.
+SDC_HD double* weather_buf(const State& S, int env, int which) { return S.weather + ((size_t)env * 2 + which) * 2 * S.win_len; }
+SDC_HD double* weather_cur(const State& S, int env) { return weather_buf(S, env, S.cur_buf[env]); }
+SDC_HD double* weather_pend(const State& S, int env) { return weather_buf(S, env, S.cur_buf[env] ^ 1); }
 
 // Where the shared tables are read from (k_step points these at a shared-memory copy).
 struct Tables { const LocTables* loc; const sdc_dc_params* dc; };
@@ -178,8 +185,9 @@ SDC_HD void trend_features(double cur, const double* v, double* out5) {
 
 struct LsStats { double oldest, avg, norm_q, hist[5]; };
 
-// Per-episode normalisation constants of an env (CI_Manager / Weather_Manager 30-day min-max).
-struct Norms { double cmin, crng, tmin, trng; int t0; };
+// Per-episode normalisation constants of an env (CI_Manager / Weather_Manager 30-day min-max) and its weather window,
+// addressed by trace index: wrel[t] = dry bulb, wrel[win_len + t] = wet bulb at index t (wrel = window start - t0).
+struct Norms { double cmin, crng, tmin, trng; const double* wrel; };
 
 // Builds the three observations at trace index t. Sink: void operator()(int agent, int idx, float v).
 // Layouts: SURVEY.md A.6 / sustaindc_env.py:302-433.
@@ -188,7 +196,7 @@ struct Norms { double cmin, crng, tmin, trng; int t0; };
 template <class Sink>
 SDC_HDN void build_obs(const State& S, const Tables& T, int env, int t, const LsStats& ls, double soc, const Norms& nm, Sink& sink) {
     const LocTables& L = T.loc[S.loc_id[env]];
-    const double* wtemp = S.weather + (size_t)env * 2 * S.win_len + (t - nm.t0);
+    const double* wtemp = nm.wrel + t;
     const int tp = t >= 16 ? t - 16 : 0;              // start of the 16-sample past window (empty before t = 16)
 #ifndef SDC_LAZY_OBS_LOADS
     double ci_raw[25], wt_raw[17];
@@ -303,8 +311,7 @@ struct StepResult {
     float evicted;
 };
 
-// What the observation builder needs from the scalar phase (the observations are built after the normaliser; in the
-// split-phase variant by a kernel of their own).
+// What the observation builder needs from the scalar phase (the observations are built after the normaliser).
 struct ObsDeferred { LsStats ls; double soc; Norms nm; int tn; };
 
 // The part of StepResult the reward needs (kept small: it lives in registers across the window passes).
@@ -352,7 +359,7 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
     double b = S.bat_load[env];
     Norms nm;
     nm.cmin = S.ci_min[env]; nm.crng = S.ci_max[env] - nm.cmin;
-    nm.tmin = S.t_min[env]; nm.trng = S.t_max[env] - nm.tmin; nm.t0 = t0;
+    nm.tmin = S.t_min[env]; nm.trng = S.t_max[env] - nm.tmin; nm.wrel = weather_cur(S, env) - t0;
     const int h_len = S.hist_len[env], h_head = S.hist_head[env];
     const LocTables& L = T.loc[S.loc_id[env]];
     const sdc_dc_params& P = T.dc[S.cfg_id[env]];
@@ -363,10 +370,7 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
     const int m1 = ring[(q - 24) & mask], m2 = ring[(q - 48) & mask], m3 = ring[(q - 72) & mask], m4r = ring[(q - 96) & mask];
     const double w = L.workload[t];
     const int ns = L.ns[t], sh = L.sh[t];
-    const double* wtemp = S.weather + (size_t)env * 2 * S.win_len;
-    const double* wwetb = wtemp + S.win_len;
-    const int wi = t - t0;
-    const double ambient = wtemp[wi], wet_bulb = wwetb[wi], outside_next = wtemp[wi + 1];
+    const double ambient = nm.wrel[t], wet_bulb = nm.wrel[S.win_len + t], outside_next = nm.wrel[t + 1];
     const double ci_now = L.ci[t];
     double ci_fut[8];
 #pragma unroll
@@ -1113,18 +1117,39 @@ SDC_HD U4 env_random(uint64_t seed, uint32_t episode, uint32_t stream, uint32_t 
     U4 c; c.x = idx; c.y = episode; c.z = stream; c.w = 0x5DCB200u;
     return philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
-// Four N(0,1) samples (indices 4*idx4 .. 4*idx4+3 of the env's noise stream), Box-Muller in fp32.
-SDC_HD void noise_normals4(uint64_t seed, uint32_t episode, uint32_t idx4, float* z4) {
-    const U4 r = env_random(seed, episode, RS_NOISE, idx4);
-    const float k = 2.3283064365386963e-10f;             // 2^-32
-    const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = (float)r.y * k;
-    const float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u4 = (float)r.w * k;
-    const float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
-    float s, c;
-    sincosf(6.283185307179586f * u2, &s, &c);
-    z4[0] = ra * c; z4[1] = ra * s;
-    sincosf(6.283185307179586f * u4, &s, &c);
-    z4[2] = rb * c; z4[3] = rb * s;
+// Weather noise: the year-long random walk is cut into kNoiseThreads segments of kNoiseSeg samples; segment i draws its
+// normals from its own PCG32 stream (O'Neill 2014, XSH-RR 64/32), seeded by one Philox block keyed by (env seed, episode,
+// segment).  ~10 integer instructions per 32-bit draw instead of ~23 for Philox: the walk is 35 040 normals per episode,
+// a fifth of all instructions of a step when it ran on Philox alone.
+struct Pcg32 { uint64_t state, inc; };
+SDC_HD uint32_t pcg32_next(Pcg32& g) {
+    const uint64_t old = g.state;
+    g.state = old * 6364136223846793005ULL + g.inc;
+    const uint32_t xs = (uint32_t)(((old >> 18) ^ old) >> 27), rot = (uint32_t)(old >> 59);
+    return (xs >> rot) | (xs << ((32u - rot) & 31u));
+}
+SDC_HD Pcg32 noise_stream(uint64_t seed, uint32_t episode, uint32_t segment) {
+    const U4 r = env_random(seed, episode, RS_NOISE, segment);
+    Pcg32 g;
+    g.state = (uint64_t)r.x | ((uint64_t)r.y << 32);
+    g.inc = ((uint64_t)r.z | ((uint64_t)r.w << 32)) | 1ull;
+    return g;
+}
+// Two N(0,1) samples from two 32-bit draws (Box-Muller, fp32): radius from the top 24 bits of `a`, angle in [-pi, pi)
+// from `b` read as a signed integer.  On the device the logarithm, square root and sine / cosine are the hardware
+// approximations (MUFU; absolute error ~2^-21 in the range used): ~12 instructions per pair instead of ~150, and a
+// difference from the host statement below the 1e-5 level in z (tests compare the realised weather at 1e-4 C).
+SDC_HD void noise_normals2(uint32_t a, uint32_t b, float* z2) {
+    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float th = (float)(int32_t)b * 1.4629180792671596e-9f;           // pi / 2^31
+#if defined(__CUDA_ARCH__)
+    float r, s, c;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+    __sincosf(th, &s, &c);
+#else
+    const float r = sqrtf(-2.0f * logf(u1)), s = sinf(th), c = cosf(th);
+#endif
+    z2[0] = r * c; z2[1] = r * s;
 }
 // Episode start (day, hour) and weather day-roll: random.randint(lo, hi), random.randint(0, 23),
 // np.random.randint(0, 14).
@@ -1135,7 +1160,7 @@ SDC_HD void draw_episode_start(uint64_t seed, uint32_t episode, int day_lo, int 
     *roll = (int)(r.z % 14u);
 }
 constexpr int kNoiseThreads = 256;                        // segments of the year-long random walk
-constexpr int kNoiseSeg = 140;                            // 4-aligned segment length, 256*140 >= 35040
+constexpr int kNoiseSeg = 140;                            // even segment length, 256*140 >= 35040
 
 // Buffers and knobs of one step launch (all device pointers; see sdc_step in include/sdc_b200.h).
 struct StepArgs {
@@ -1160,11 +1185,6 @@ struct StepArgs {
     float hvac_bins_per_kw;             // SDC_HVAC_BINS / range
     unsigned long long* phase_clocks;   // optional [16]: summed per-warp clock64 deltas of the k_step phases (diagnostics)
     int32_t unit_envs, blocks_per_sm;
-    // split-phase variant (k_phys -> k_obs -> k_step without physics / observations): what the physics hands over
-    double* hand_d;        // [kHandD][N]  energy, nci_next, ls_penalty, LsStats (oldest, avg, norm_q, hist[5]), soc, norms (cmin, crng, tmin, trng)
-    int32_t* hand_i;       // [kHandI][N]  terminal, step_after, hist_len, hist_head, tn, norms.t0
-    float* hand_f;         // [N]          evicted window sample
-    int32_t split;
 };
 
 // HARL shared observation (harl/envs/sustaindc/harlsustaindc_env.py:78-85): ls[0:26] | dc[11] | dc[13] |
@@ -1177,9 +1197,8 @@ SDC_HD void share_from_obs(const float* obs78, float* share29) {
 }
 
 // ---- reset of the scalar sub-env state (sustaindc_env.py:436-531) ----------------------------
-// The weather window / norms / t0 must already be in place. Set-point and reward window survive.
-template <class ObsSink>
-SDC_HDN void reset_scalar_state(const State& S, int env, int t0, ObsSink& obs) {
+// The weather window / norms must already be in place. Set-point and reward window survive.
+SDC_HD void reset_scalars(const State& S, int env, int t0) {
     const LocTables& L = S.loc[S.loc_id[env]];
     S.t[env] = t0; S.t0[env] = t0; S.step_in_ep[env] = 0;
     S.ci_min[env] = L.ci_min30[t0]; S.ci_max[env] = L.ci_max30[t0];
@@ -1188,13 +1207,18 @@ SDC_HDN void reset_scalar_state(const State& S, int env, int t0, ObsSink& obs) {
     S.dc_run[env] = 0; S.dc_scale[env] = 1; S.dc_last[env] = 2;              // dc_gym.py:114-116
     S.bat_load[env] = 0.0;                                                    // battery_model.py:90-91
     if (t0 + S.ep_len + 18 > SDC_YEAR_STEPS) flag_error(S, env, SDC_F_TRACE_DOMAIN);
+}
+// The observation SustainDC.reset returns (:488-494, 531): empty queue, SoC 0, trace index t0, the given window / range.
+template <class ObsSink>
+SDC_HDN void reset_observation(const State& S, int env, int t0, const double* window, double tmin, double tmax, ObsSink& obs) {
+    const LocTables& L = S.loc[S.loc_id[env]];
     LsStats ls;
     ls.oldest = 0.0; ls.avg = 0.0; ls.norm_q = 0.0;
     for (int i = 0; i < 5; ++i) ls.hist[i] = 0.0;
     const Tables T{S.loc, S.dc};
     Norms nm;
-    nm.cmin = S.ci_min[env]; nm.crng = S.ci_max[env] - nm.cmin;
-    nm.tmin = S.t_min[env]; nm.trng = S.t_max[env] - nm.tmin; nm.t0 = t0;
+    nm.cmin = L.ci_min30[t0]; nm.crng = L.ci_max30[t0] - nm.cmin;
+    nm.tmin = tmin; nm.trng = tmax - tmin; nm.wrel = window - t0;
     build_obs(S, T, env, t0, ls, 0.0, nm, obs);
 }
 

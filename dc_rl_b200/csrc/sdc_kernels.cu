@@ -26,8 +26,8 @@ struct Context {
     int device = 0;
     int sm_count = 148;
     bool cooperative = true;      // cudaLaunchCooperativeKernel for k_step (co-residency guaranteed by the driver)
-    int occ_per_sm[2] = {0, 0};   // cached occupancy query of k_step<true> / k_step<false> ...
-    size_t occ_smem[2] = {0, 0};  // ... at this much dynamic shared memory
+    int occ_per_sm[1] = {0};      // cached occupancy query of k_step ...
+    size_t occ_smem[1] = {0};     // ... at this much dynamic shared memory
 };
 using StepArgs = sdc::StepArgs;
 
@@ -88,11 +88,6 @@ static void range_pop() { nvtxRangePop(); }
 // device helpers
 // =================================================================================================
 constexpr int kStepThreads = 256;
-#ifndef SDC_SPLIT_CTAS_PER_SM
-#define SDC_SPLIT_CTAS_PER_SM 3
-#endif
-constexpr int kSplitCtasPerSm = SDC_SPLIT_CTAS_PER_SM;   // k_step<false> (no physics / observation code): co-resident CTAs per SM
-constexpr int kSplitHitFloats = 2048;                    // parked-hit list of a window pass in the split-phase variant
 constexpr int kWarpsPerBlock = kStepThreads / 32;
 constexpr int kObsRow = 3 * SDC_OBS_DIM;          // 78 floats per env
 constexpr int kTileStride = kObsRow + 1;          // odd row stride of the shared-memory observation tile
@@ -139,7 +134,7 @@ __device__ __forceinline__ void prefetch_env(const sdc::State& S, const sdc::Tab
     if (what & 1) {
     const int t = S.t[env], t0 = S.t0[env], head = S.ls_head[env], hh = S.hist_head[env];
     const sdc::LocTables& L = T.loc[S.loc_id[env]];
-    const double* wt = S.weather + (size_t)env * 2 * S.win_len + (t - t0);
+    const double* wt = sdc::weather_cur(S, env) + (t - t0);
     prefetch_line(wt); prefetch_line(wt + 16); prefetch_line(wt + S.win_len);
     const uint8_t* ring = S.ls_ring + (size_t)env * (S.ls_mask + 1);
     prefetch_line(ring + ((t - 24) & S.ls_mask)); prefetch_line(ring + ((t - 48) & S.ls_mask));
@@ -457,23 +452,25 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
     const int k_norm = min(kNormWindow, n - t0);           // the reference's 30-day slice is truncated at the year end
     const int k_win = min(S.win_len, n - t0);              // episode window (a 30-day episode is 2898 samples: longer than the slice)
     const int k_keep = max(k_norm, k_win);
-    // pass 1: this thread's segment of the walk (utils/managers.py:45-46)
+    // pass 1: this thread's segment of the walk (utils/managers.py:45-46), normals from the segment's own PCG32 stream.
+    // Walk sample j lands at trace index (j + 96 roll) mod n, i.e. at window position k = j + c_lo (c_hi past the wrap).
     double run = 0.0, sum_run = 0.0, sum_run2 = 0.0;
-    int cnt = 0;
-    for (int q = 0; q < sdc::kNoiseSeg / 4; ++q) {
-        float z[4];
-        const int j0 = tid * sdc::kNoiseSeg + q * 4;
-        sdc::noise_normals4(seed, ep, (uint32_t)(j0 >> 2), z);
+    const int j0 = tid * sdc::kNoiseSeg;
+    const int cnt = max(0, min(sdc::kNoiseSeg, n - j0));    // even for every thread (n and the segment length are even)
+    const int jw = n - 96 * roll, c_lo = 96 * roll - t0, c_hi = c_lo - n;
+    sdc::Pcg32 g = sdc::noise_stream(seed, ep, (uint32_t)tid);
+#pragma unroll 2
+    for (int q = 0; q < cnt; q += 2) {
+        float z[2];
+        const uint32_t a = sdc::pcg32_next(g), b = sdc::pcg32_next(g);
+        sdc::noise_normals2(a, b, z);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + u;
-            if (j < n) {
-                run += (double)(0.02f * z[u]);
-                sum_run += run; sum_run2 += run * run; cnt += 1;
-                int t = j + 96 * roll; if (t >= n) t -= n;
-                const int k = t - t0;
-                if (k >= 0 && k < k_keep) runbuf[k] = run;
-            }
+        for (int u = 0; u < 2; ++u) {
+            const int j = j0 + q + u;
+            run += (double)(0.02f * z[u]);
+            sum_run += run; sum_run2 = fma(run, run, sum_run2);
+            const int k = j + (j >= jw ? c_hi : c_lo);
+            if ((unsigned)k < (unsigned)k_keep) runbuf[k] = run;
         }
     }
     sh.seg_off[tid] = run;
@@ -485,8 +482,8 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
     __syncthreads();
     const double off = sh.seg_off[tid];
     // walk_j = off + run_j  ->  sums of w and w^2 from the partial sums
-    const double sw = block_sum(cnt * off + sum_run, sh.red);
-    const double sw2 = block_sum(cnt * off * off + 2.0 * off * sum_run + sum_run2, sh.red);
+    const double sw = block_sum((double)cnt * off + sum_run, sh.red);
+    const double sw2 = block_sum((double)cnt * off * off + 2.0 * off * sum_run + sum_run2, sh.red);
     const double mean = sw / n;
     const double scale = 0.75 / sqrt(sw2 / n - mean * mean);              // managers.py:46-48
     // emit: roll, clip, window, 30-day min/max (managers.py:598-608), one window position per thread and trip
@@ -507,44 +504,53 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
     if (tid == 0) { *tmin_out = tmin; *tmax_out = tmax; }
 }
 
-// Look-ahead: an env that will finish two steps from now gets its next episode generated into the staging buffers
-// (the ones sdc_stage_episode fills in replay mode) while the other CTAs step, so that the reset itself is a copy.
+// Look-ahead: an env that will finish two steps from now gets its next episode generated into its staging buffers (the
+// other weather buffer; the ones sdc_stage_episode fills in replay mode) TOGETHER WITH the observation its reset will
+// return, while the other CTAs step -- so that the reset itself is a buffer flip and a 428-byte copy that the env's own
+// warp does at the end of its step (k_step), not a job.
 __device__ __forceinline__ void pregen_one_env(const sdc::State& S, int env, double* runbuf, ResetShared& sh) {
     if (S.pend_valid[env]) return;                      // uniform: a host-staged (or already generated) episode is waiting
-    double* wt = S.pend_weather + (size_t)env * 2 * S.win_len;
+    double* wt = sdc::weather_pend(S, env);
     generate_episode(S, env, wt, wt + S.win_len, S.pend_tmin + env, S.pend_tmax + env, runbuf, sh);
-    __syncthreads();
+    __syncthreads();                                    // window, range and start are in place (global / shared memory)
     if (threadIdx.x == 0) {
         S.pend_day[env] = sh.start[0]; S.pend_hour[env] = sh.start[1];
+        RowSink sink{S.pend_obs + (size_t)env * kObsRow};
+        sdc::reset_observation(S, env, sh.start[0] * 96 + sh.start[1] * 4, wt, S.pend_tmin[env], S.pend_tmax[env], sink);
         __threadfence();
-        S.pend_valid[env] = 1;
+        S.pend_valid[env] = 3;
     }
 }
 
-// Episode reset of one env by one CTA.  `runbuf` = run_buf_doubles(S) doubles of shared memory.
+// Episode reset of one env by one CTA (k_reset, and the worker jobs of k_step for envs whose next episode was not staged
+// with its observation: first resets, host-staged replays).  `runbuf` = run_buf_bytes(S) of shared memory.
 __device__ __forceinline__ void reset_one_env(const sdc::State& S, int env, float* obs, float* share, double* runbuf, ResetShared& sh) {
     const int tid = threadIdx.x;
-    double* wt = S.weather + (size_t)env * 2 * S.win_len;
-    double* ww = wt + S.win_len;
-    const bool staged = S.pend_valid[env] != 0;
+    const int staged = S.pend_valid[env];
+    double* wt = sdc::weather_pend(S, env);             // the next episode's window: staged, or generated right here
     __syncthreads();
-    if (staged) {
+    if (staged & 1) {
         if (tid == 0) { sh.start[0] = S.pend_day[env]; sh.start[1] = S.pend_hour[env]; sh.start[2] = 0; }
-        const double2* src = reinterpret_cast<const double2*>(S.pend_weather + (size_t)env * 2 * S.win_len);
-        double2* dst = reinterpret_cast<double2*>(wt);                    // win_len is even, rows are 16-byte aligned
-        for (int k = tid; k < S.win_len; k += kResetThreads) dst[k] = src[k];
-        if (tid == 0) { S.t_min[env] = S.pend_tmin[env]; S.t_max[env] = S.pend_tmax[env]; }
     } else {
-        generate_episode(S, env, wt, ww, S.t_min + env, S.t_max + env, runbuf, sh);
+        generate_episode(S, env, wt, wt + S.win_len, S.pend_tmin + env, S.pend_tmax + env, runbuf, sh);
     }
     uint32_t* ring = reinterpret_cast<uint32_t*>(S.ls_ring + (size_t)env * (S.ls_mask + 1));
     for (int k = tid; k < (S.ls_mask + 1) / 4; k += kResetThreads) ring[k] = 0u;
-    __syncthreads();                               // weather window + norms visible to thread 0
+    __syncthreads();                               // weather window + range visible to thread 0
     if (tid == 0) {
-        if (staged) S.pend_valid[env] = 0;
+        const int t0 = sh.start[0] * 96 + sh.start[1] * 4;
+        const double tmin = S.pend_tmin[env], tmax = S.pend_tmax[env];
+        S.t_min[env] = tmin; S.t_max[env] = tmax;
+        S.cur_buf[env] ^= 1;                       // the staged window becomes the current one
+        S.pend_valid[env] = 0;
         S.episode[env] += 1;
-        RowSink sink{sh.row};
-        sdc::reset_scalar_state(S, env, sh.start[0] * 96 + sh.start[1] * 4, sink);
+        sdc::reset_scalars(S, env, t0);
+        if (staged & 2) {
+            for (int k = 0; k < kObsRow; ++k) sh.row[k] = S.pend_obs[(size_t)env * kObsRow + k];
+        } else {
+            RowSink sink{sh.row};
+            sdc::reset_observation(S, env, t0, wt, tmin, tmax, sink);
+        }
     }
     __syncthreads();
     for (int k = tid; k < kObsRow; k += kResetThreads) obs[(size_t)env * kObsRow + k] = sh.row[k];
@@ -569,11 +575,8 @@ __global__ void __launch_bounds__(kResetThreads) k_reset(const sdc::State S, con
 // =================================================================================================
 // k_step
 // =================================================================================================
-// FUSED = true: the whole env-step in this kernel.  FUSED = false (split-phase variant): k_phys and k_obs have run, this
-// kernel does the reward normaliser, the window passes and the worker jobs from what k_phys handed over.
-template <bool FUSED>
-__global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_step(const sdc::State S, const StepArgs a, const int n_unit_ctas,
-                                                                                   const int hit_cap, const int table_bytes) {
+__global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, const StepArgs a, const int n_unit_ctas, const int hit_cap,
+                                                          const int table_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int U = a.unit_envs;
@@ -649,21 +652,16 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
         Q.a[0] = Q.a[1] = Q.m[0] = Q.m[1] = 0;
         long long tk1 = tk0;
         float alt3[3] = {0.f, 0.f, 0.f};
-        prefetch_env(S, T, env, active, FUSED ? 3 : 2);
+        prefetch_env(S, T, env, active, 3);
         if (active) {
             const int2 qa = reinterpret_cast<const int2*>(S.q_a)[env], qm = reinterpret_cast<const int2*>(S.q_m)[env];
-            if (FUSED) {
+            {
                 const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
                 GlobalInfoSink info{a.info, N, env};
                 sdc::physics_step(S, T, env, a_ls, a_dc, a_bat, info, st, od);
-            } else {
-                st.energy = a.hand_d[env]; st.nci_next = a.hand_d[(size_t)N + env]; st.ls_penalty = a.hand_d[(size_t)2 * N + env];
-                st.terminal = a.hand_i[env]; st.step_after = a.hand_i[(size_t)N + env];
-                st.hist_len = a.hand_i[(size_t)2 * N + env]; st.hist_head = a.hand_i[(size_t)3 * N + env];
-                st.evicted = a.hand_f[env];
             }
             en.energy = st.energy; en.nci_next = st.nci_next; en.ls_penalty = st.ls_penalty;
-            if (FUSED && sdc::any_alt_reward(S)) {
+            if (sdc::any_alt_reward(S)) {
                 const sdc::AltInputs ai{st.ite_kw, st.total_kw, st.water, od.tn % 96};
                 sdc::alt_rewards(S, env, st.energy, ai, alt3);
             }
@@ -752,7 +750,7 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
         }
         const long long tk2b = clock64();
         const int finished = st.terminal;
-        if (FUSED && have_unit) {
+        if (have_unit) {
             // logger sums (harl/envs/sustaindc/sustaindc_logger.py:86-101): warp reduce, one atomic per metric.  Done while
             // the step's results are still in registers (after the long observation code they come back from spills).
             double m[13];
@@ -777,7 +775,7 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
                 if (lane == 0) atomicAdd(a.metrics + slot[k], v);
             }
         }
-        if (FUSED) {
+        {
             // Observation rows go through a shared-memory tile (odd row stride: conflict-free) and leave as contiguous
             // 128-bit stores; 107 scattered 4-byte stores per env would keep the LSU busy for ~50 k cycles per unit.
             // The tile shares its memory with the window-pass buffers (used only after the barrier below).
@@ -855,13 +853,41 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
                 atomicAdd(a.metrics + sdc::M_REWARD_DC, m_dc);
             }
         }
-        // Finished envs go to the reset workers (other CTAs of this launch).  Order matters: the terminal observation
-        // is in global memory before the env is published, because the worker overwrites obs/share with the reset
-        // ones.  Only the ~5 % of units that contain a finished env pay the gpu-scope fences.
+        // Finished envs.  The normal case: the look-ahead generation of the previous launch staged the next episode WITH its
+        // reset observation, and the reset is done right here by the env's own warp -- flip the weather buffer, clear the
+        // queue ring, copy the staged observation over the terminal one (which already went to term_obs), reset the
+        // scalars.  Everything else (first resets, episodes staged by the host without an observation) goes to the reset
+        // workers (other CTAs of this launch); there order matters: the terminal observation is in global memory before the
+        // env is published, because the worker overwrites obs/share.  Only the ~5 % of units with a finished env get here.
         if (__any_sync(0xffffffffu, finished)) {
-            __threadfence();
-            if (finished) a.reset_list[atomicAdd(a.ctr + 1, 1)] = env;
-            __threadfence();
+            const bool fast = finished && S.pend_valid[env] == 3;
+            unsigned todo = __ballot_sync(0xffffffffu, fast);
+            __syncwarp();                               // the owner lanes' state stores of this step precede the reset's
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int e = env0 + l;
+                uint4* ring = reinterpret_cast<uint4*>(S.ls_ring + (size_t)e * (S.ls_mask + 1));
+                for (int k = lane; k < (S.ls_mask + 1) / 16; k += 32) ring[k] = make_uint4(0u, 0u, 0u, 0u);
+                const float* po = S.pend_obs + (size_t)e * kObsRow;
+                for (int k = lane; k < kObsRow; k += 32) a.obs[(size_t)e * kObsRow + k] = po[k];
+                if (lane < SDC_SHARE_DIM) {
+                    const int src = lane < 26 ? lane : (lane == 26 ? SDC_OBS_DIM + 11 : (lane == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
+                    a.share[(size_t)e * SDC_SHARE_DIM + lane] = po[src];
+                }
+                if (lane == 0) {
+                    S.t_min[e] = S.pend_tmin[e]; S.t_max[e] = S.pend_tmax[e];
+                    S.cur_buf[e] ^= 1;
+                    S.pend_valid[e] = 0;
+                    S.episode[e] += 1;
+                    sdc::reset_scalars(S, e, S.pend_day[e] * 96 + S.pend_hour[e] * 4);
+                }
+            }
+            if (__any_sync(0xffffffffu, finished && !fast)) {
+                __threadfence();
+                if (finished && !fast) a.reset_list[atomicAdd(a.ctr + 1, 1)] = env;
+                __threadfence();
+            }
             __syncwarp();
         }
         // look-ahead: envs that will finish two steps from now -> pre-generation list consumed by the next launch
@@ -955,125 +981,6 @@ __global__ void __launch_bounds__(kStepThreads, FUSED ? 2 : kSplitCtasPerSm) k_s
 }
 
 
-// =================================================================================================
-// split-phase variant: k_phys -> k_obs -> k_step<false>
-// =================================================================================================
-// The fused kernel is bounded by resident warps x per-unit latency at the register budget of its largest phase.  Here the
-// physics and the observation builder are kernels of their own (one lane per env, 32 envs per warp), handing ~170 B
-// per env over through global memory; the normaliser kernel then runs without their registers and code.
-__device__ __forceinline__ void tables_to_smem(const sdc::State& S, unsigned char* smem, sdc::Tables& T) {
-    const int loc_bytes = S.n_loc * (int)sizeof(sdc::LocTables), dc_bytes = S.n_cfg * (int)sizeof(sdc_dc_params);
-    if (loc_bytes + dc_bytes <= kTableBytes) {
-        int* dst = reinterpret_cast<int*>(smem);
-        const int* src_loc = reinterpret_cast<const int*>(S.loc);
-        const int* src_dc = reinterpret_cast<const int*>(S.dc);
-        for (int i = threadIdx.x; i < loc_bytes / 4; i += blockDim.x) dst[i] = src_loc[i];
-        for (int i = threadIdx.x; i < dc_bytes / 4; i += blockDim.x) dst[loc_bytes / 4 + i] = src_dc[i];
-        T.loc = reinterpret_cast<const sdc::LocTables*>(smem);
-        T.dc = reinterpret_cast<const sdc_dc_params*>(smem + loc_bytes);
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(kStepThreads, 2) k_phys(const sdc::State S, const StepArgs a) {
-    __shared__ __align__(16) unsigned char tab[kTableBytes];
-    sdc::Tables T{S.loc, S.dc};
-    tables_to_smem(S, tab, T);
-    const int lane = threadIdx.x & 31;
-    const int N = S.n_envs;
-    const int env = blockIdx.x * kStepThreads + threadIdx.x;
-    const bool active = env < N;
-    prefetch_env(S, T, env, active, 1);
-    sdc::StepResult st;
-    sdc::ObsDeferred od;
-    double m[13];
-#pragma unroll
-    for (int k = 0; k < 13; ++k) m[k] = 0.0;
-    if (active) {
-        const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
-        GlobalInfoSink info{a.info, N, env};
-        sdc::physics_step(S, T, env, a_ls, a_dc, a_bat, info, st, od);
-        double* d = a.hand_d + env;
-        d[0] = st.energy; d[(size_t)N] = st.nci_next; d[(size_t)2 * N] = st.ls_penalty;
-        d[(size_t)3 * N] = od.ls.oldest; d[(size_t)4 * N] = od.ls.avg; d[(size_t)5 * N] = od.ls.norm_q;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) d[(size_t)(6 + k) * N] = od.ls.hist[k];
-        d[(size_t)11 * N] = od.soc; d[(size_t)12 * N] = od.nm.cmin; d[(size_t)13 * N] = od.nm.crng;
-        d[(size_t)14 * N] = od.nm.tmin; d[(size_t)15 * N] = od.nm.trng;
-        int32_t* q = a.hand_i + env;
-        q[0] = st.terminal; q[(size_t)N] = st.step_after; q[(size_t)2 * N] = st.hist_len; q[(size_t)3 * N] = st.hist_head;
-        q[(size_t)4 * N] = od.tn; q[(size_t)5 * N] = od.nm.t0;
-        a.hand_f[env] = st.evicted;
-        m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
-        m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
-        m[11] = st.overdue; m[12] = st.total_kw;
-        if (st.hvac_kw > 0.0) {
-            int bin = (int)(st.hvac_kw * (double)a.hvac_bins_per_kw);
-            bin = bin < 0 ? 0 : (bin >= SDC_HVAC_BINS ? SDC_HVAC_BINS - 1 : bin);
-            atomicAdd(a.hvac_hist + bin, 1ull);
-        }
-    }
-    constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
-                              sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
-                              sdc::M_OVERDUE, sdc::M_TOTAL_KW};
-#pragma unroll
-    for (int k = 0; k < 13; ++k) {
-        const double v = warp_sum(m[k]);
-        if (lane == 0 && v != 0.0) atomicAdd(a.metrics + slot[k], v);
-    }
-}
-
-__global__ void __launch_bounds__(kStepThreads, 2) k_obs(const sdc::State S, const StepArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    sdc::Tables T{S.loc, S.dc};
-    tables_to_smem(S, smem_raw, T);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int N = S.n_envs;
-    const int env0 = (blockIdx.x * kWarpsPerBlock + warp) * 32;
-    if (env0 >= N) return;
-    const int env = env0 + lane;
-    const bool active = env < N;
-    float* tile = reinterpret_cast<float*>(smem_raw + kTableBytes) + (size_t)warp * 32 * kTileStride;
-    int finished = 0;
-    if (active) {
-        sdc::ObsDeferred od;
-        const double* d = a.hand_d + env;
-        od.ls.oldest = d[(size_t)3 * N]; od.ls.avg = d[(size_t)4 * N]; od.ls.norm_q = d[(size_t)5 * N];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) od.ls.hist[k] = d[(size_t)(6 + k) * N];
-        od.soc = d[(size_t)11 * N]; od.nm.cmin = d[(size_t)12 * N]; od.nm.crng = d[(size_t)13 * N];
-        od.nm.tmin = d[(size_t)14 * N]; od.nm.trng = d[(size_t)15 * N];
-        const int32_t* q = a.hand_i + env;
-        finished = q[0]; od.tn = q[(size_t)4 * N]; od.nm.t0 = q[(size_t)5 * N];
-        RowSink sink{tile + lane * kTileStride};
-        sdc::emit_obs(S, T, env, od, sink);
-        a.done[env] = (uint8_t)finished;
-    }
-    __syncwarp();
-    const int n_here = min(32, N - env0);
-    const int total = n_here * kObsRow;
-    float4* dst4 = reinterpret_cast<float4*>(a.obs + (size_t)env0 * kObsRow);
-    for (int i = lane; i < total / 4; i += 32) {
-        float v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const int f = 4 * i + q; const int e = f / kObsRow; v[q] = tile[e * kTileStride + (f - e * kObsRow)]; }
-        dst4[i] = make_float4(v[0], v[1], v[2], v[3]);
-    }
-    for (int f = (total & ~3) + lane; f < total; f += 32) { const int e = f / kObsRow; a.obs[(size_t)env0 * kObsRow + f] = tile[e * kTileStride + (f - e * kObsRow)]; }
-    float* dsh = a.share + (size_t)env0 * SDC_SHARE_DIM;
-    for (int f = lane; f < n_here * SDC_SHARE_DIM; f += 32) {
-        const int e = f / SDC_SHARE_DIM, k = f - e * SDC_SHARE_DIM;
-        const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
-        dsh[f] = tile[e * kTileStride + src];
-    }
-    unsigned fin = __ballot_sync(0xffffffffu, finished != 0);
-    while (fin && a.term_obs) {
-        const int l = __ffs(fin) - 1;
-        fin &= fin - 1;
-        for (int k = lane; k < kObsRow; k += 32) a.term_obs[(size_t)(env0 + l) * kObsRow + k] = tile[l * kTileStride + k];
-    }
-}
-
 __global__ void k_build_reset_list(int n_envs, const uint8_t* __restrict__ mask, int32_t* list, int32_t* count) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= n_envs) return;
@@ -1136,10 +1043,10 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     const int U = a.unit_envs;
     // Dynamic shared memory of k_step after the tables: collect scratch + the staged window (which also receives the sorted
     // collections: at least 2 x kCollectCap floats) + the parked-hit list.  The fused kernel shares the region with its
-    // observation tiles (whatever they leave beyond scratch + window is the hit list); the split-phase variant has no tiles.
+    // observation tiles (whatever they leave beyond scratch + window is the hit list).
     const size_t pass_floats = (size_t)2 * sdc::kCollectCap + (S.hist_cap > 2 * sdc::kCollectCap ? S.hist_cap : 2 * sdc::kCollectCap);
     const size_t tile_floats = (size_t)kWarpsPerBlock * 32 * kTileStride;
-    size_t smem_floats = a.split ? pass_floats + kSplitHitFloats : (pass_floats > tile_floats ? pass_floats : tile_floats);
+    size_t smem_floats = pass_floats > tile_floats ? pass_floats : tile_floats;
     const int hit_cap = (int)(smem_floats - pass_floats);
     size_t smem = smem_floats * sizeof(float);
     if (smem < run_buf_bytes(S)) smem = run_buf_bytes(S);                              // reset workers reuse the region
@@ -1153,9 +1060,9 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     // the runtime reports for this kernel / block size / shared memory, and the launch is COOPERATIVE: the driver then
     // gang-schedules the grid (or refuses the launch), also when other kernels -- an NCCL collective, a policy forward on
     // another stream -- hold part of the device.
-    const void* fn = a.split ? (const void*)k_step<false> : (const void*)k_step<true>;
+    const void* fn = (const void*)k_step;
     CU(cudaSetDevice(c.device));
-    const int which = a.split ? 1 : 0;
+    const int which = 0;
     if (c.occ_per_sm[which] == 0 || c.occ_smem[which] != smem) {
         int q = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, fn, kStepThreads, smem));
@@ -1163,7 +1070,7 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     }
     int per_sm = c.occ_per_sm[which];
     if (per_sm < 1) return "k_step: no resident CTA fits on an SM";
-    const int design = a.split ? kSplitCtasPerSm : 2;  // __launch_bounds__ of the kernel
+    const int design = 2;                             // __launch_bounds__ of the kernel
     if (per_sm > design) per_sm = design;
     const int bps = a.blocks_per_sm > 0 ? a.blocks_per_sm : per_sm;
     const int capacity = c.sm_count * (bps < per_sm ? bps : per_sm);
@@ -1176,11 +1083,6 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     int blocks = S.n_envs < 4096 ? n_unit_ctas + 4 : capacity;
     if (blocks > capacity) blocks = capacity;
     cudaStream_t st = (cudaStream_t)stream;
-    if (a.split) {
-        const int nb = (S.n_envs + kStepThreads - 1) / kStepThreads;
-        k_phys<<<nb, kStepThreads, 0, st>>>(S, a);
-        k_obs<<<nb, kStepThreads, kTableBytes + tile_floats * sizeof(float), st>>>(S, a);
-    }
     int hc = hit_cap, tb = table_bytes, nuc = n_unit_ctas;
     void* args[] = {(void*)&S, (void*)&a, (void*)&nuc, (void*)&hc, (void*)&tb};
     if (c.cooperative) CU(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kStepThreads), args, smem, st));
@@ -1217,9 +1119,7 @@ static const char* launch_rebuild(Context&, const sdc::State& S, void* stream) {
 }
 
 static const char* set_kernel_attributes() {
-    CU(cudaFuncSetAttribute(k_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    CU(cudaFuncSetAttribute(k_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    CU(cudaFuncSetAttribute(k_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    CU(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     CU(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     CU(cudaFuncSetAttribute(k_rebuild, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     return nullptr;

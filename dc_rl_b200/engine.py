@@ -23,7 +23,7 @@ _STATE_DTYPES = {
     "hist_head": np.int32, "phase_clocks": np.uint64, "qlist": np.float32, "q_a": np.int32, "q_m": np.int32, "err": np.int32,
     "mom_s1": np.float64, "mom_s2": np.float64, "mom_c0": np.float64, "tails": np.float32, "tail_n": np.int32,
     "tail_thr": np.float32, "agg_n": np.int32, "agg_s": np.float64, "fast_cfg": np.uint32, "counters": np.int32, "pass_stats": np.int32,
-    "pend_valid": np.uint8, "metrics": np.float64, "hvac_hist": np.uint64,
+    "pend_valid": np.uint8, "pend_weather": np.float64, "cur_buf": np.uint8, "pend_obs": np.float32, "metrics": np.float64, "hvac_hist": np.uint64,
 }
 
 _default_lib = None
@@ -217,7 +217,7 @@ class Engine:
     def read_state(self, name):
         dt = np.dtype(_STATE_DTYPES[name])
         n = self.n_envs
-        per_env = {"weather": 2 * self.win_len, "ls_bins": 4, "hist": self.hist_cap, "qlist": 2 * _lib.LIST_CAP, "q_a": 2, "q_m": 2,
+        per_env = {"weather": 2 * self.win_len, "pend_weather": 2 * self.win_len, "pend_obs": N_AGENTS * OBS_DIM, "ls_bins": 4, "hist": self.hist_cap, "qlist": 2 * _lib.LIST_CAP, "q_a": 2, "q_m": 2,
                    "tail_n": 2, "tail_thr": 4, "agg_n": 2, "agg_s": 4}.get(name, 1)
         if name == "phase_clocks":
             out = np.zeros(16, dt)

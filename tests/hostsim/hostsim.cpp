@@ -191,10 +191,14 @@ static void generate_weather(const sdc::State& S, int env, int t0, int roll, uin
     const int n = SDC_YEAR_STEPS;
     const uint64_t seed = S.seed[env];
     std::vector<float> inc(sdc::kNoiseThreads * sdc::kNoiseSeg, 0.f);
-    for (int i4 = 0; i4 < (int)inc.size() / 4; ++i4) {
-        float z[4];
-        sdc::noise_normals4(seed, episode, (uint32_t)i4, z);
-        for (int k = 0; k < 4; ++k) inc[i4 * 4 + k] = 0.02f * z[k];
+    for (int seg = 0; seg < sdc::kNoiseThreads; ++seg) {    // one PCG32 stream per segment, two normals per pair of draws
+        sdc::Pcg32 g = sdc::noise_stream(seed, episode, (uint32_t)seg);
+        for (int q = 0; q < sdc::kNoiseSeg; q += 2) {
+            float z[2];
+            const uint32_t a = sdc::pcg32_next(g), b = sdc::pcg32_next(g);
+            sdc::noise_normals2(a, b, z);
+            inc[seg * sdc::kNoiseSeg + q] = 0.02f * z[0]; inc[seg * sdc::kNoiseSeg + q + 1] = 0.02f * z[1];
+        }
     }
     std::vector<double> walk(n);
     double acc = 0.0;
@@ -209,7 +213,7 @@ static void generate_weather(const sdc::State& S, int env, int t0, int roll, uin
     double ss = 0.0;
     for (int j = 0; j < n; ++j) ss += (walk[j] - mean) * (walk[j] - mean);
     const double scale = 0.75 / std::sqrt(ss / n);
-    double* wt = S.weather + (size_t)env * 2 * S.win_len;
+    double* wt = sdc::weather_pend(S, env);                  // generated into the staging buffer, flipped in by the reset
     double* ww = wt + S.win_len;
     for (int i = 0; i < S.win_len; ++i) { wt[i] = 0.0; ww[i] = 0.0; }
     double tmin = INFINITY, tmax = -INFINITY;
@@ -224,27 +228,30 @@ static void generate_weather(const sdc::State& S, int env, int t0, int roll, uin
             ww[t - t0] = std::fmin(std::fmax(L.wetb_base[j] + noise, 0.0), 45.0);
         }
     }
-    S.t_min[env] = tmin; S.t_max[env] = tmax;
+    S.pend_tmin[env] = tmin; S.pend_tmax[env] = tmax;
 }
 
 static const char* launch_reset(Context&, const sdc::State& S, const int32_t* list, const int32_t* count, float* obs, float* share, void*) {
     for (int i = 0; i < *count; ++i) {
         const int env = list[i];
         int day, hour, roll = 0;
-        if (S.pend_valid && S.pend_valid[env]) {
-            S.pend_valid[env] = 0;
+        if (S.pend_valid[env] & 1) {
             day = S.pend_day[env]; hour = S.pend_hour[env];
-            memcpy(S.weather + (size_t)env * 2 * S.win_len, S.pend_weather + (size_t)env * 2 * S.win_len, 2 * S.win_len * sizeof(double));
-            S.t_min[env] = S.pend_tmin[env]; S.t_max[env] = S.pend_tmax[env];
         } else {
             const uint32_t ep = S.episode[env];
             sdc::draw_episode_start(S.seed[env], ep, S.day_lo[env], S.day_hi[env], &day, &hour, &roll);
             generate_weather(S, env, day * 96 + hour * 4, roll, ep);
         }
+        const double* window = sdc::weather_pend(S, env);
+        S.t_min[env] = S.pend_tmin[env]; S.t_max[env] = S.pend_tmax[env];
+        S.cur_buf[env] ^= 1;
+        S.pend_valid[env] = 0;
         S.episode[env] += 1;
         memset(S.ls_ring + (size_t)env * (S.ls_mask + 1), 0, S.ls_mask + 1);
         ObsRow o{obs + (size_t)env * 3 * SDC_OBS_DIM};
-        sdc::reset_scalar_state(S, env, day * 96 + hour * 4, o);
+        const int t0 = day * 96 + hour * 4;
+        sdc::reset_scalars(S, env, t0);
+        sdc::reset_observation(S, env, t0, window, S.t_min[env], S.t_max[env], o);
         sdc::share_from_obs(o.row, share + (size_t)env * SDC_SHARE_DIM);
     }
     return nullptr;

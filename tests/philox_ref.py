@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE: numpy restatement of the device's counter-based RNG streams (sdc_core.h: Philox4x32-10 keyed by
 the env seed, counter = (index, episode, stream, 0x5DCB200); RS_START = 0 -> start day / hour / weather roll,
-RS_NOISE = 1 -> Box-Muller normals of the weather random walk).  Independent of the C++ source: written from the
+RS_NOISE = 1 -> seeds of the per-segment PCG32 streams behind the Box-Muller normals of the weather random walk).  Independent of the C++ source: written from the
 published algorithm (Salmon et al., SC'11) and the stream layout documented in sdc_core.h."""
 import numpy as np
 
@@ -34,22 +34,33 @@ def episode_start(seed, episode, day_lo, day_hi):
     return int(day_lo + int(r[0]) % (day_hi - day_lo + 1)), int(r[1]) % 24, int(r[2]) % 14
 
 
+N_SEG, SEG = 256, 140          # sdc_core.h kNoiseThreads, kNoiseSeg
+
+
 def noise_increments(seed, episode, n=35040):
-    """The n fp32 random-walk increments 0.02f * N(0,1) of one episode (stream RS_NOISE), as float64."""
-    n4 = (n + 3) // 4
-    r = env_random(seed, episode, 1, np.arange(n4, dtype=np.uint32))
+    """The n fp32 random-walk increments 0.02f * N(0,1) of one episode, as float64.  Segment i (samples 140 i ...) draws
+    from its own PCG32 stream (XSH-RR 64/32) seeded by the Philox block (i, episode, RS_NOISE); two normals per pair of
+    draws: radius from the top 24 bits of the first, angle in [-pi, pi) from the second read as int32 (Box-Muller)."""
+    r = env_random(seed, episode, 1, np.arange(N_SEG, dtype=np.uint32)).astype(np.uint64)
+    state = r[:, 0] | (r[:, 1] << np.uint64(32))
+    inc = (r[:, 2] | (r[:, 3] << np.uint64(32))) | np.uint64(1)
+    mult = np.uint64(6364136223846793005)
+    draws = np.zeros((N_SEG, SEG), np.uint32)
+    with np.errstate(over="ignore"):
+        for q in range(SEG):
+            old = state
+            state = old * mult + inc
+            xs = (((old >> np.uint64(18)) ^ old) >> np.uint64(27)).astype(np.uint32)
+            rot = (old >> np.uint64(59)).astype(np.uint32)
+            draws[:, q] = (xs >> rot) | (xs << ((np.uint32(32) - rot) & np.uint32(31)))
     f32 = np.float32
-    k = f32(2.3283064365386963e-10)
-    u1 = ((r[:, 0] >> 8).astype(f32) + f32(0.5)) * f32(1.0 / 16777216.0)
-    u2 = r[:, 1].astype(f32) * k
-    u3 = ((r[:, 2] >> 8).astype(f32) + f32(0.5)) * f32(1.0 / 16777216.0)
-    u4 = r[:, 3].astype(f32) * k
-    ra = np.sqrt(f32(-2.0) * np.log(u1)).astype(f32)
-    rb = np.sqrt(f32(-2.0) * np.log(u3)).astype(f32)
-    a2, a4 = f32(6.283185307179586) * u2, f32(6.283185307179586) * u4
-    z = np.stack([ra * np.cos(a2).astype(f32), ra * np.sin(a2).astype(f32), rb * np.cos(a4).astype(f32), rb * np.sin(a4).astype(f32)],
-                 axis=1).astype(f32).reshape(-1)[:n]
-    return (f32(0.02) * z).astype(np.float64)
+    a, b = draws[:, 0::2], draws[:, 1::2]
+    u1 = ((a >> 8).astype(f32) + f32(0.5)) * f32(1.0 / 16777216.0)
+    th = b.view(np.int32).astype(f32) * f32(1.4629180792671596e-9)
+    rad = np.sqrt(f32(-2.0) * np.log(u1)).astype(f32)
+    z = np.empty((N_SEG, SEG), f32)
+    z[:, 0::2], z[:, 1::2] = rad * np.cos(th).astype(f32), rad * np.sin(th).astype(f32)
+    return (f32(0.02) * z).astype(np.float64).reshape(-1)[:n]
 
 
 class ReplayNpRng:

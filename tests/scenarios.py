@@ -146,7 +146,7 @@ def device_generated_resets_match_host_statement(lib):
     cpu = Engine(N, [location_traces("ny")], [size_datacenter("ny")[0]], lib=hostsim_build.load(), **kw)
     og, _ = gpu.reset_host(); oc, _ = cpu.reset_host()
     assert np.array_equal(gpu.read_state("t0"), cpu.read_state("t0"))
-    assert scaled_err(gpu.read_state("weather"), cpu.read_state("weather")) <= 1e-5
+    assert scaled_err(gpu.read_state("weather"), cpu.read_state("weather")) <= 1e-4     # hardware log / sincos on the device
     assert scaled_err(og, oc) <= 1e-4
     lo, hi = gpu.day_lo.astype(int) * 96, gpu.day_hi.astype(int) * 96 + 23 * 4
     t0 = gpu.read_state("t0")

@@ -89,35 +89,6 @@ def test_state_blob_roundtrip(lib):
     scenarios.state_blob_roundtrip(lib)
 
 
-def test_split_phase_variant_is_bit_identical(lib):
-    """sdc_set_tuning(split=1): physics, observations and normaliser as three kernels; same outputs as the fused k_step."""
-    import torch
-    from dc_rl_b200.dc_config import size_datacenter
-    from dc_rl_b200.engine import Engine
-    from replay import location_traces
-    N = 1500
-    outs = []
-    for split in (0, 1):
-        eng = Engine(N, [location_traces("ny")], [size_datacenter("ny")[0]], months=np.arange(N) % 12,
-                     seeds=np.arange(N, dtype=np.uint64) + 11, days_per_episode=1, lib=lib)
-        eng.set_tuning(split=split)
-        rng = np.random.RandomState(4)
-        eng.prefill_history((300.0 + 50.0 * rng.standard_normal((N, 600))).astype(np.float32))
-        eng.reset_host()
-        rec = []
-        for s in range(210):                       # two auto-resets of every env
-            o, sh, r, d, info, term = eng.step_host(rng.randint(0, 3, size=(N, 3)).astype(np.int32))
-            if s % 5 == 0 or s > 200:
-                rec.append([x.copy() for x in (o, sh, r, d, info, term)])
-        outs.append((rec, eng.metrics(), eng.hvac_histogram()[0], eng.read_state("err")))
-        eng.close()
-    for ra, rb in zip(outs[0][0], outs[1][0]):
-        for xa, xb in zip(ra, rb):
-            assert np.array_equal(xa, xb)
-    assert np.allclose(outs[0][1], outs[1][1], rtol=1e-12) and np.array_equal(outs[0][2], outs[1][2])
-    assert not outs[0][3].any() and not outs[1][3].any()
-
-
 def test_host_buffer_modes_agree(lib):
     """sdc_step_host on the handle's pinned buffers: kernel stores straight into host memory (direct_host = 3, default),
     staged device buffers + D2H (0), and caller-owned pageable arrays all return the same step results."""

@@ -147,7 +147,7 @@ def _generated_engine(lib, n, days, loc="ny"):
 def test_device_generator_matches_oracle_weather_reset(lib, days, n):
     """Generated mode: the device draws start day / hour / roll and 35 040 normals from its Philox streams.  The oracle's
     Weather_Manager.reset statement (sdc_oracle.weather_reset), handed those same normals and roll through a stand-in
-    np_rng, must produce the same realised windows and 30-day range: |dT| <= 2e-5 C (fp32 Box-Muller on the device vs
+    np_rng, must produce the same realised windows and 30-day range: |dT| <= 1e-4 C (fp32 Box-Muller on the device vs
     numpy float32 here; the reference's own values are fp64 draws from another generator -- parity is of the
     CONSTRUCTION).  30-day episodes (the shipped HARL yaml) cover windows longer than the 2880-sample range slice."""
     import philox_ref
@@ -164,9 +164,9 @@ def test_device_generator_matches_oracle_weather_reset(lib, days, n):
         rng = philox_ref.ReplayNpRng(philox_ref.noise_increments(int(eng.seeds[i]), 0), roll)
         temp, wetb, o_min, o_max = sdc_oracle.weather_reset(tr, int(t0[i]), rng)
         k = min(wl, sdc_oracle.YEAR_STEPS - int(t0[i]))
-        assert np.max(np.abs(w[i, 0, :k] - temp[t0[i]:t0[i] + k])) <= 2e-5, i
-        assert np.max(np.abs(w[i, 1, :k] - wetb[t0[i]:t0[i] + k])) <= 2e-5, i
-        assert abs(tmin[i] - o_min) <= 2e-5 and abs(tmax[i] - o_max) <= 2e-5, i
+        assert np.max(np.abs(w[i, 0, :k] - temp[t0[i]:t0[i] + k])) <= 1e-4, i
+        assert np.max(np.abs(w[i, 1, :k] - wetb[t0[i]:t0[i] + k])) <= 1e-4, i
+        assert abs(tmin[i] - o_min) <= 1e-4 and abs(tmax[i] - o_max) <= 1e-4, i
     if days == 30:                       # and the env steps through the whole 30-day window with realised (non-zero) weather
         rng = np.random.RandomState(1)
         for s in range(days * 96 - 1):
