@@ -34,7 +34,9 @@ constexpr int kCollectAim = 110;      // half-width of the re-centring interval 
 constexpr int kCollectCap = 512;      // values a refresh can collect per bracket
 constexpr int kWexpMax = 6;           // |log2| range of the adaptive interval width
 constexpr int kTailCap = 128;         // values per tail band
-constexpr int kBandTarget = 40;       // a refresh narrows the bands when one holds more values than this
+constexpr int kBandTarget = 96;       // a refresh narrows the bands when one holds more values than this ...
+constexpr int kBandSparse = 40;       // ... and widens them when both hold fewer than this (the bands are sorted: a step's cost does
+                                      // not depend on their population, a wide band is re-centred less often)
 constexpr int kAlphaOff = 12;         // narrowest tail band: alpha = 0.5 / 2^12 of the IQR
 constexpr int kPassJobBytes = 192;     // size of one maintenance-pass record (sdc_kernels.cu PassJob)
 constexpr int kTailRetry = 200;       // steps of plain scans before another attempt at tail sets that did not fit
@@ -107,8 +109,10 @@ struct State {
     int32_t* q_m;                  // [N][2] elements in the list
     // incremental reward normaliser: window moments about c0, tail multisets, adaptive refresh parameters
     double* mom_s1; double* mom_s2; double* mom_c0;   // [N]
-    float* tails;                  // [ceil(N/32)][2][kTailCap][32] interleaved (tail_ptr)
-    int32_t* tail_n;               // [N][2] set sizes, -1 = no valid sets
+    float* tails;                  // [N][2][kTailCap] the two tail bands, each SORTED ascending (tail_ptr)
+    int32_t* tail_n;               // [N][2] band sizes, -1 = no valid bands
+    int32_t* tail_nb;              // [N][2] band values beyond the fence: the first nb of the lower band, the last nb of the upper one
+    double* tail_bs;               // [N][2][2] sum / sum of squares about c0 of those nb values
     float* tail_thr;               // [N][4] TL, TH (inner thresholds), TL2, TH2 (outer thresholds)
     int32_t* agg_n; double* agg_s; // [N][2] count, [N][2][2] sum / sum of squares about c0 of the values beyond TL2 / TH2
     uint32_t* fast_cfg;            // [N] byte 0 tail slack exponent, 1 retry countdown, 2/3 interval width exponents (int8)
@@ -287,10 +291,11 @@ SDC_HD double chiller_power(double max_cap, double load, double ambient) {
     const double rat = 0.94483600 + (-0.05700880) * d_t + 0.00185486 * (d_t * d_t);
     const double avail = (rat != 0.0) ? max_cap * rat : 0.0;
     const double fpr = 2.333 + (-1.975) * rat + 0.6121 * (rat * rat);
-    const double plr = (avail > 0.0) ? fmax(0.05, fmin(load / avail, 1.0)) : 0.0;
+    const double la = (avail > 0.0) ? load / avail : 0.0;
+    const double plr = (avail > 0.0) ? fmax(0.05, fmin(la, 1.0)) : 0.0;
     const double ffl = 0.03303 + 0.6852 * plr + 0.2818 * (plr * plr);
     double opl = 0.0;
-    if (avail > 0.0) opl = (load / avail < 0.05) ? load / avail : plr;
+    if (avail > 0.0) opl = (la < 0.05) ? la : plr;
     const double frac = (opl < 0.05) ? fmin(1.0, opl / 0.05) : 1.0;
     const double power = ffl * fpr * avail / 3.0 * frac;
     return (opl > 0.0) ? power : 0.0;
@@ -444,15 +449,17 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
     }
     util += (double)ns / 100;                                                         // :275-276
     LsStats ls;
+    const double inv_len = 1.0 / (double)(len > 1 ? len : 1);
     if (len > 0) {
-        ls.oldest = ((double)(q - head) / 4.0) / 24;
-        ls.avg = (((double)((long long)len * q - sum) / 4.0) / len) / 24;
+        ls.oldest = (double)(q - head) / 96.0;              // (x / 4) / 24 of an integer x: one correctly rounded division
+        ls.avg = (((double)((long long)len * q - sum) * 0.25) * inv_len) * (1.0 / 24.0);
     } else {
         ls.oldest = 0.0; ls.avg = 0.0;
     }
     b4 = len - (b0 + b1 + b2 + b3);
-    const int dl = len > 1 ? len : 1;
-    ls.hist[0] = (double)b0 / dl; ls.hist[1] = (double)b1 / dl; ls.hist[2] = (double)b2 / dl; ls.hist[3] = (double)b3 / dl;
+    // (fp64 divisions cost ~25 dependent instructions each; quotients that only reach fp32 outputs are formed with one
+    //  reciprocal instead: <= 1 ulp of fp64 off, which survives the fp32 cast with probability ~2e-9 per value)
+    ls.hist[0] = (double)b0 * inv_len; ls.hist[1] = (double)b1 * inv_len; ls.hist[2] = (double)b2 * inv_len; ls.hist[3] = (double)b3 * inv_len;
     ls.hist[4] = b4 > 0 ? 1.0 : 0.0;                                                  // :63-73
     ls.norm_q = (double)len / kQueueMax;
     S.ls_head[env] = head; S.ls_len[env] = len; S.ls_sum[env] = sum;
@@ -481,23 +488,31 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
     S.setpoint[env] = sp; S.dc_run[env] = run; S.dc_scale[env] = scale; S.dc_last[env] = (int8_t)delta;
     const double load_pct = util * 100;
     double p_it = 0.0, sum_out = 0.0;
-    for (int c = 0; c < P.n_classes; ++c) {                      // datacenter.py:157-181,250-317 per rack class
-        const double t_in = P.cls_supply[c] + sp;
-        const double base = (P.m_cpu + 0.05) * t_in + P.c_cpu;
-        const double ratio = base + P.shift_cpu * (load_pct / 100);
-        const double n = P.cls_ncpu[c];
-        const double pc = fmax(P.cls_idle[c], P.cls_full[c] * ratio) * n;
-        const double v = (P.m_fan * 10 * t_in + P.c_fan * 5) + P.shift_fan * (load_pct / 20);
-        const double pf = (P.itfan_ref_p * (v / P.itfan_ref_v_ratio)) * n;
-        const double vf = (P.itfan_full_load_v * v) * n;
+    const double load_cpu = P.shift_cpu * (load_pct / 100), load_fan = P.shift_fan * (load_pct / 20);
+    const double k_out = 1.918 / (P.c_air * P.rho_air * 0.526);
+    // datacenter.py:157-181,250-317 per rack class, two classes per trip (the second one a zero-weight copy of the first when
+    // the count is odd): each class is a ~150-instruction dependent chain through log / exp, and two independent chains
+    // in flight nearly halve the time a lane spends here
+    for (int c = 0; c < P.n_classes; c += 2) {
+        const int c1 = c + 1 < P.n_classes ? c + 1 : c;
+        const double w1 = c + 1 < P.n_classes ? P.cls_mult[c1] : 0.0;
+        const double t_in0 = P.cls_supply[c] + sp, t_in1 = P.cls_supply[c1] + sp;
+        const double ratio0 = ((P.m_cpu + 0.05) * t_in0 + P.c_cpu) + load_cpu, ratio1 = ((P.m_cpu + 0.05) * t_in1 + P.c_cpu) + load_cpu;
+        const double n0 = P.cls_ncpu[c], n1 = P.cls_ncpu[c1];
+        const double pc0 = fmax(P.cls_idle[c], P.cls_full[c] * ratio0) * n0, pc1 = fmax(P.cls_idle[c1], P.cls_full[c1] * ratio1) * n1;
+        const double v0 = (P.m_fan * 10 * t_in0 + P.c_fan * 5) + load_fan, v1 = (P.m_fan * 10 * t_in1 + P.c_fan * 5) + load_fan;
+        const double pf0 = (P.itfan_ref_p * (v0 / P.itfan_ref_v_ratio)) * n0, pf1 = (P.itfan_ref_p * (v1 / P.itfan_ref_v_ratio)) * n1;
+        const double vf0 = (P.itfan_full_load_v * v0) * n0, vf1 = (P.itfan_full_load_v * v1) * n1;
         // 1.918 P^1.096 / (c_air rho V^0.824 0.526) as ONE exponential of a difference of logarithms: a few ulp instead of
         // pow's < 1 ulp (invisible after the fp32 cast of every output that depends on it, ~1e-15 relative on the energy)
-        // for a quarter of the instructions of two pow calls and a division; 7 of these per env-step
-        const double ratio_pv = exp(1.096 * log(pc + pf) - 0.824 * log(vf));
-        const double t_out = t_in + (1.918 / (P.c_air * P.rho_air * 0.526)) * ratio_pv + (-14.01);
-        if (t_out - t_in < 2.0) err |= SDC_F_OUTLET_DELTA;                            // :295-300
-        p_it += P.cls_mult[c] * (pc + pf);
-        sum_out += P.cls_mult[c] * t_out;
+        // for a quarter of the instructions of two pow calls and a division
+        const double lp0 = log(pc0 + pf0), lp1 = log(pc1 + pf1);
+        const double lv0 = log(vf0), lv1 = log(vf1);
+        const double r0 = exp(1.096 * lp0 - 0.824 * lv0), r1 = exp(1.096 * lp1 - 0.824 * lv1);
+        const double t_out0 = t_in0 + k_out * r0 + (-14.01), t_out1 = t_in1 + k_out * r1 + (-14.01);
+        if (t_out0 - t_in0 < 2.0 || t_out1 - t_in1 < 2.0) err |= SDC_F_OUTLET_DELTA;  // :295-300
+        p_it += P.cls_mult[c] * (pc0 + pf0) + w1 * (pc1 + pf1);
+        sum_out += P.cls_mult[c] * t_out0 + w1 * t_out1;
     }
     const double mean_out = sum_out / P.n_racks;
     const double t_ret = P.ret_mean + mean_out;                                       // :531-541
@@ -518,8 +533,8 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
     wtr += wtr * 0.01;
     const double water = round_dec((wtr * 1000) / 4, 1e4);
     const double total_kw = (p_it + ct + comp) / 1e3;
-    info(I_DC_ITE_KW, (float)(p_it / 1e3)); info(I_DC_CT_KW, (float)(ct / 1e3)); info(I_DC_COMP_KW, (float)(comp / 1e3));
-    info(I_DC_HVAC_KW, (float)((ct + comp) / 1e3)); info(I_DC_TOTAL_KW, (float)total_kw);
+    info(I_DC_ITE_KW, (float)(p_it * 1e-3)); info(I_DC_CT_KW, (float)(ct * 1e-3)); info(I_DC_COMP_KW, (float)(comp * 1e-3));
+    info(I_DC_HVAC_KW, (float)((ct + comp) * 1e-3)); info(I_DC_TOTAL_KW, (float)total_kw);
     info(I_DC_SP_DELTA, (float)delta); info(I_DC_SP, (float)sp); info(I_DC_CPU_FRAC, (float)util);
     info(I_DC_INT_TEMP, (float)mean_out); info(I_DC_AMBIENT, (float)ambient);
     info(I_DC_POWER_LB, (float)P.power_lb_kw); info(I_DC_POWER_UB, (float)P.power_ub_kw);
@@ -529,8 +544,8 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
     // Battery (envs/bat_env_fwd_view.py:84-126,194-284; envs/battery_model.py:94-139)
     // ------------------------------------------------------------------------------------------
     const double dcl = total_kw / 1e3;                           // MW                 sustaindc_env.py:652
-    const double capb = P.bat_capacity_mwh;
-    const double soc0 = b / capb;
+    const double capb = P.bat_capacity_mwh, inv_capb = 1.0 / capb;
+    const double soc0 = b * inv_capb;
     double energy, co2;
     if (bat_charge) {                                            // charge
         const double t_u = round_dec(0.5 * (1 - sigmoid(10 * (soc0 - 0.5))), 1e4) * 15 / 60;
@@ -552,7 +567,7 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
         co2 = energy * ci_now;
     }
     S.bat_load[env] = b;
-    const double soc = b / capb;
+    const double soc = b * inv_capb;
     info(I_BAT_ACTION, a_bat_f); info(I_BAT_SOC, (float)soc); info(I_BAT_CO2, (float)co2);
     info(I_BAT_AVG_CI, (float)ci_now); info(I_BAT_E_WITHOUT, (float)(dcl * 1e3 * 0.25)); info(I_BAT_E_WITH, (float)energy);
     info(I_BAT_MAX_CAP, (float)capb); info(I_BAT_DCLOAD_MIN, (float)(P.power_lb_kw / 4));
@@ -566,18 +581,19 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
     S.t[env] = tn; S.step_in_ep[env] = step_in_ep;
     const int terminal = step_in_ep >= S.ep_len;
     od.ls = ls; od.soc = soc; od.nm = nm; od.tn = tn;
-    const double nci_next = (ci_fut[0] - nm.cmin) / nm.crng;
+    const double inv_crng = 1.0 / nm.crng;
+    const double nci_next = (ci_fut[0] - nm.cmin) * inv_crng;
     info(I_OUTSIDE_TEMP, (float)outside_next); info(I_DAY, (float)(tn / 96)); info(I_HOUR, (float)((tn % 96) * 0.25));
     info(I_NORM_CI, (float)nci_next);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) info(I_FORECAST0 + i, (float)((ci_fut[i] - nm.cmin) / nm.crng));
+    for (int i = 0; i < 8; ++i) info(I_FORECAST0 + i, (float)((ci_fut[i] - nm.cmin) * inv_crng));
     info(I_ISTERMINAL, terminal ? 1.f : 0.f);
 
     out.energy = energy; out.nci_next = nci_next;
     out.ls_penalty = (-0.3 * sqrt((double)over) + 0.3) + (-0.1 * ls.oldest);
     out.terminal = terminal; out.step_after = step_in_ep;
-    out.co2 = co2; out.water = water; out.ite_kw = p_it / 1e3; out.ct_kw = ct / 1e3; out.comp_kw = comp / 1e3;
-    out.hvac_kw = (ct + comp) / 1e3; out.total_kw = total_kw;
+    out.co2 = co2; out.water = water; out.ite_kw = p_it * 1e-3; out.ct_kw = ct * 1e-3; out.comp_kw = comp * 1e-3;
+    out.hvac_kw = (ct + comp) * 1e-3; out.total_kw = total_kw;
     out.tasks_in_queue = len; out.tasks_dropped = dropped; out.overdue = over;
     if (err) flag_error(S, env, err);
 }
@@ -606,10 +622,12 @@ SDC_HDN void emit_obs(const State& S, const Tables& T, int env, const ObsDeferre
 //    the evicted one; resynchronised exactly by every refresh).
 //  * tails    clipping only changes the values beyond the fences, so sum(clip(x)) = S1 + sum_{x<lo}(lo - x) -
 //    sum_{x>hi}(x - hi) (likewise for squares).  Around each fence a BAND of values (fence -/+ alpha IQR) is kept
-//    individually as an unsorted multiset, everything beyond the band as (count, sum, sum of squares): a loop over
-//    a few dozen floats instead of 10 000.  When a fence leaves its band, or a band overflows, the refresh rebuilds
-//    both (alpha adapts to the density at the fences; distributions with heavy ties exactly at a fence fall back to
-//    a plain clipped-moment pass every step).
+//    individually as a SORTED list together with the split position of the fence inside it and the (sum, sum of
+//    squares) of the band values beyond the fence; everything beyond the band as (count, sum, sum of squares).  A
+//    step moves the split by the 0-2 values the fence crossed -- O(1) instead of a walk over the band -- and the rare
+//    sample that enters / leaves a band (~2 % of the env-steps) is a sorted-list edit done by the whole warp.  When a
+//    fence leaves its band, or a band overflows, the refresh rebuilds both (alpha adapts to the density at the fences;
+//    distributions with heavy ties exactly at a fence fall back to a plain clipped-moment pass every step).
 struct QView {              // the two lists of an env (rows of S.qlist)
     float* lst[2];
     int a[2], m[2];
@@ -647,12 +665,8 @@ struct Moments { double c1, c2, c0; int ok; };   // clipped sums about c0 from t
 #define SDC_INF_F INFINITY
 #endif
 
-// tail set `side` (0: below TL, 1: above TH) of an env: element i lives at p[i * kTailStride].  Interleaved by 32 envs
-// so that one lane per env walks its set with coalesced loads.
-constexpr int kTailStride = 32;
-SDC_HD float* tail_ptr(const State& S, int env, int side) {
-    return S.tails + ((size_t)(env >> 5) * 2 + side) * kTailCap * kTailStride + (env & 31);
-}
+// tail band `side` (0: below TL, 1: above TH) of an env: kTailCap floats, sorted ascending.
+SDC_HD float* tail_ptr(const State& S, int env, int side) { return S.tails + ((size_t)env * 2 + side) * kTailCap; }
 
 // Shifts inside a bracket run in batches of 8 (all loads of a batch before its stores): one lane moves up to a
 // hundred floats through global memory, and element-by-element that is a chain of dependent round trips.
@@ -837,91 +851,120 @@ SDC_HDN void reward_prepare(const State& S, int env, double& energy, int len, in
 // outer threshold (TL2 <= x < TL, TH < x <= TH2; the fence lies inside the band) are kept individually, those
 // beyond the outer threshold only as (count, sum, sum of squares) -- they are clipped whatever the fence does inside
 // the band.  So a large outlier population (e.g. after a regime change) costs nothing per step.
-SDC_HD void tail_load8(const float* p, int cnt, int i0, float pad, float* xs) {
-#pragma unroll
-    for (int u = 0; u < 8; ++u) xs[u] = (i0 + u < cnt) ? p[(size_t)(i0 + u) * kTailStride] : pad;
-}
-// `first8`: the band's first batch, loaded by the caller (so that both bands' first rows are in flight together)
-SDC_HD void tail_side(float* p, int& cnt, int& agg_n, double& agg_s1, double& agg_s2, bool below, float t_in, float t_out,
-                      double fence, double c0, float e, float o, bool evict, double& c1, double& c2, bool& valid, int& err,
-                      const float* first8) {
-    const double yf = fence - c0;
-    // far tail: clipped to the fence as a whole
-    const bool e_far = below ? e < t_out : e > t_out, o_far = evict && (below ? o < t_out : o > t_out);
-    if (e_far) { const double y = (double)e - c0; agg_n += 1; agg_s1 += y; agg_s2 = fma(y, y, agg_s2); }
-    if (o_far) { const double y = (double)o - c0; agg_n -= 1; agg_s1 -= y; agg_s2 = fma(-y, y, agg_s2); }
-    c1 += (double)agg_n * yf - agg_s1;
-    c2 += (double)agg_n * yf * yf - agg_s2;
-    // band: individual values; sum (fence - x) over those beyond the fence.  Batches of 8 loads issued together (the walk
-    // is latency-bound: one lane per env, the 32 envs of a unit interleaved so that a batch row is one 128-byte line).
-    const bool rm = evict && !o_far && (below ? o < t_in : o > t_in);
-    const float pad = below ? SDC_INF_F : -SDC_INF_F;            // contributes nothing, never equals o
-    int idx = -1;
-    for (int i0 = 0; i0 < cnt; i0 += 8) {
-        float xs[8];
-        if (i0 == 0) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) xs[u] = first8[u];
-        } else {
-            tail_load8(p, cnt, i0, pad, xs);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float x = xs[u];
-            if (rm && idx < 0 && x == o) { idx = i0 + u; continue; }
-            const double t = fence - (double)x;                  // > 0 below the lower fence, < 0 above the upper one
-            if (below ? t > 0.0 : t < 0.0) { c1 += t; c2 = fma(t, yf + ((double)x - c0), c2); }
-        }
+//
+// A step's work on the bands has three phases:
+//   A (reward_plan_a, the env's lane)  window moments, far-tail aggregates, and whether the step's appended / evicted
+//                                      sample is a band value (BandPlan)
+//   B (band_edit; on the device the whole warp, k_step)  sorted removal / insertion of those samples
+//   C (reward_plan_c, the env's lane)  split bookkeeping of the edits, the 0-2 values the fence crossed, clipped sums,
+//                                      and what kind of window pass (if any) the step needs
+struct BandPlan { int rm[2], ins[2]; };    // per side: the evicted sample leaves / the new sample enters the band
+struct BandDone { int rm[2], pos[2]; };    // per side: index the evicted sample was removed at, index the new one went to (-1: none)
+
+// Phase B, serial statement (host build; the CUDA kernel does the same with ballots over the 32 lanes).
+// Removes the first element equal to `o` (if do_rm) and inserts `e` after its ties (if do_ins and the band has room).
+SDC_HDN void band_edit(float* B, int n, bool do_rm, bool do_ins, float o, float e, int& rm, int& pos) {
+    rm = -1; pos = -1;
+    if (do_rm) for (int i = 0; i < n; ++i) if (B[i] == o) { rm = i; break; }
+    const int n1 = n - (rm >= 0);
+    if (do_ins && n1 < kTailCap) {
+        pos = 0;
+        for (int i = 0; i < n; ++i) pos += (i != rm && B[i] <= e);
     }
-    if (rm) {
-        if (idx < 0) { err |= SDC_F_BRACKET; valid = false; }
-        else { cnt -= 1; if (idx != cnt) p[(size_t)idx * kTailStride] = p[(size_t)cnt * kTailStride]; }
-    }
-    if (!e_far && (below ? e < t_in : e > t_in)) {
-        if (cnt >= kTailCap) valid = false;
-        else {
-            p[(size_t)cnt * kTailStride] = e; cnt += 1;
-            const double t = fence - (double)e;
-            if (below ? t > 0.0 : t < 0.0) { c1 += t; c2 = fma(t, yf + ((double)e - c0), c2); }
-        }
-    }
+    ListEdit ed; ed.rm = rm; ed.drop = 0; ed.ins = pos; ed.val = e; ed.m0 = n;
+    edit_apply(B, ed);
 }
 
-SDC_HDN void reward_plan(const State& S, int env, ScanRequest& rq, Moments& M) {
+SDC_HDN void reward_plan_a(const State& S, int env, const ScanRequest& rq, Moments& M, BandPlan& bp) {
     const float e = rq.e, o = rq.o;
     const bool evict = rq.evict != 0;
     // all loads of the env's incremental state first (independent, in flight together), stores afterwards
     const double c0 = S.mom_c0[env];
     double s1 = S.mom_s1[env], s2 = S.mom_s2[env];
-    int nl = S.tail_n[2 * env], nh = S.tail_n[2 * env + 1];
+    const bool valid = S.tail_n[2 * env] >= 0;
+    const float tl = S.tail_thr[4 * env], th = S.tail_thr[4 * env + 1], tl2 = S.tail_thr[4 * env + 2], th2 = S.tail_thr[4 * env + 3];
+    int an[2] = {S.agg_n[2 * env], S.agg_n[2 * env + 1]};
+    double a1[2] = {S.agg_s[4 * env], S.agg_s[4 * env + 2]}, a2[2] = {S.agg_s[4 * env + 1], S.agg_s[4 * env + 3]};
+    const double ye = (double)e - c0, yo = (double)o - c0;
+    s1 += ye; s2 = fma(ye, ye, s2);
+    if (evict) { s1 -= yo; s2 = fma(-yo, yo, s2); }
+    S.mom_s1[env] = s1; S.mom_s2[env] = s2;
+    M.ok = valid; M.c0 = c0; M.c1 = s1; M.c2 = s2;       // whole-window sums; the clip corrections are added below and in phase C
+    bp.rm[0] = bp.rm[1] = bp.ins[0] = bp.ins[1] = 0;
+    if (!valid) return;
+#pragma unroll
+    for (int sd = 0; sd < 2; ++sd) {
+        const bool below = sd == 0;
+        const float t_in = below ? tl : th, t_out = below ? tl2 : th2;
+        // far tail: clipped to the fence as a whole
+        const bool e_far = below ? e < t_out : e > t_out, o_far = evict && (below ? o < t_out : o > t_out);
+        if (e_far) { an[sd] += 1; a1[sd] += ye; a2[sd] = fma(ye, ye, a2[sd]); }
+        if (o_far) { an[sd] -= 1; a1[sd] -= yo; a2[sd] = fma(-yo, yo, a2[sd]); }
+        const double yf = (below ? rq.lo64 : rq.hi64) - c0;
+        M.c1 += (double)an[sd] * yf - a1[sd];
+        M.c2 += (double)an[sd] * yf * yf - a2[sd];
+        bp.rm[sd] = evict && !o_far && (below ? o < t_in : o > t_in);
+        bp.ins[sd] = !e_far && (below ? e < t_in : e > t_in);
+    }
+    S.agg_n[2 * env] = an[0]; S.agg_n[2 * env + 1] = an[1];
+    S.agg_s[4 * env] = a1[0]; S.agg_s[4 * env + 1] = a2[0]; S.agg_s[4 * env + 2] = a1[1]; S.agg_s[4 * env + 3] = a2[1];
+}
+
+SDC_HDN void reward_plan_c(const State& S, int env, ScanRequest& rq, Moments& M, const BandPlan& bp, const BandDone& bd) {
+    const float e = rq.e, o = rq.o;
     uint32_t fc = S.fast_cfg[env];
     const float tl = S.tail_thr[4 * env], th = S.tail_thr[4 * env + 1], tl2 = S.tail_thr[4 * env + 2], th2 = S.tail_thr[4 * env + 3];
-    int al = S.agg_n[2 * env], ah = S.agg_n[2 * env + 1];
-    double al1 = S.agg_s[4 * env], al2 = S.agg_s[4 * env + 1], ah1 = S.agg_s[4 * env + 2], ah2 = S.agg_s[4 * env + 3];
-    { const double y = (double)e - c0; s1 += y; s2 = fma(y, y, s2); }
-    if (evict) { const double y = (double)o - c0; s1 -= y; s2 = fma(-y, y, s2); }
-    S.mom_s1[env] = s1; S.mom_s2[env] = s2;
-    bool valid = nl >= 0;
-    M.ok = 0; M.c0 = c0; M.c1 = 0.0; M.c2 = 0.0;
-    if (valid) {
-        const double lo = rq.lo64, hi = rq.hi64;
-        double c1 = 0.0, c2 = 0.0;
+    const bool had_bands = M.ok != 0;
+    if (M.ok) {
+        const double c0 = M.c0;
+        bool valid = true;
         int err = 0;
-        float* p_lo = tail_ptr(S, env, 0);
-        float* p_hi = tail_ptr(S, env, 1);
-        float x_lo[8], x_hi[8];
-        tail_load8(p_lo, nl, 0, SDC_INF_F, x_lo);
-        tail_load8(p_hi, nh, 0, -SDC_INF_F, x_hi);
-        tail_side(p_lo, nl, al, al1, al2, true, tl, tl2, lo, c0, e, o, evict, c1, c2, valid, err, x_lo);
-        tail_side(p_hi, nh, ah, ah1, ah2, false, th, th2, hi, c0, e, o, evict, c1, c2, valid, err, x_hi);
-        if (err) flag_error(S, env, err);
-        if (!valid) { nl = -1; nh = -1; }
-        S.tail_n[2 * env] = nl; S.tail_n[2 * env + 1] = nh;
-        S.agg_n[2 * env] = al; S.agg_n[2 * env + 1] = ah;
-        S.agg_s[4 * env] = al1; S.agg_s[4 * env + 1] = al2; S.agg_s[4 * env + 2] = ah1; S.agg_s[4 * env + 3] = ah2;
-        if (valid && (double)tl2 <= lo && lo <= (double)tl && (double)th <= hi && hi <= (double)th2) {
-            M.ok = 1; M.c1 = s1 + c1; M.c2 = s2 + c2;
+        int n[2] = {S.tail_n[2 * env], S.tail_n[2 * env + 1]}, nb[2] = {S.tail_nb[2 * env], S.tail_nb[2 * env + 1]};
+        double b1[2] = {S.tail_bs[4 * env], S.tail_bs[4 * env + 2]}, b2[2] = {S.tail_bs[4 * env + 1], S.tail_bs[4 * env + 3]};
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            const bool below = sd == 0;
+            const float* p = tail_ptr(S, env, sd);
+            // bookkeeping of the edits phase B applied: the lower band's beyond-set is its first nb values, the upper band's its last nb
+            if (bp.rm[sd]) {
+                if (bd.rm[sd] < 0) { err |= SDC_F_BRACKET; valid = false; }
+                else {
+                    if (below ? bd.rm[sd] < nb[sd] : bd.rm[sd] >= n[sd] - nb[sd]) { const double y = (double)o - c0; nb[sd] -= 1; b1[sd] -= y; b2[sd] = fma(-y, y, b2[sd]); }
+                    n[sd] -= 1;
+                }
+            }
+            if (bp.ins[sd]) {
+                if (bd.pos[sd] < 0) valid = false;                               // band full: rebuilt (narrower) by the next refresh
+                else {
+                    if (below ? bd.pos[sd] < nb[sd] : bd.pos[sd] > n[sd] - nb[sd]) { const double y = (double)e - c0; nb[sd] += 1; b1[sd] += y; b2[sd] = fma(y, y, b2[sd]); }
+                    n[sd] += 1;
+                }
+            }
+            // the values the fence crossed since the last step (usually none or one)
+            const double fence = below ? rq.lo64 : rq.hi64;
+            if (valid) {
+                if (below) {
+                    while (nb[sd] > 0 && !((double)p[nb[sd] - 1] < fence)) { nb[sd] -= 1; const double y = (double)p[nb[sd]] - c0; b1[sd] -= y; b2[sd] = fma(-y, y, b2[sd]); }
+                    while (nb[sd] < n[sd] && (double)p[nb[sd]] < fence) { const double y = (double)p[nb[sd]] - c0; b1[sd] += y; b2[sd] = fma(y, y, b2[sd]); nb[sd] += 1; }
+                } else {
+                    int sx = n[sd] - nb[sd];                                     // first index of the beyond-set
+                    while (sx < n[sd] && !((double)p[sx] > fence)) { const double y = (double)p[sx] - c0; b1[sd] -= y; b2[sd] = fma(-y, y, b2[sd]); sx += 1; }
+                    while (sx > 0 && (double)p[sx - 1] > fence) { sx -= 1; const double y = (double)p[sx] - c0; b1[sd] += y; b2[sd] = fma(y, y, b2[sd]); }
+                    nb[sd] = n[sd] - sx;
+                }
+                if (nb[sd] == 0) { b1[sd] = 0.0; b2[sd] = 0.0; }                 // no rounding residue survives an empty set
+                const double yf = fence - c0;
+                M.c1 += (double)nb[sd] * yf - b1[sd];
+                M.c2 += (double)nb[sd] * yf * yf - b2[sd];
+            }
         }
+        if (err) flag_error(S, env, err);
+        if (!valid) { n[0] = -1; n[1] = -1; }
+        S.tail_n[2 * env] = n[0]; S.tail_n[2 * env + 1] = n[1];
+        S.tail_nb[2 * env] = nb[0]; S.tail_nb[2 * env + 1] = nb[1];
+        S.tail_bs[4 * env] = b1[0]; S.tail_bs[4 * env + 1] = b2[0]; S.tail_bs[4 * env + 2] = b1[1]; S.tail_bs[4 * env + 3] = b2[1];
+        const double lo = rq.lo64, hi = rq.hi64;
+        M.ok = valid && (double)tl2 <= lo && lo <= (double)tl && (double)th <= hi && hi <= (double)th2;
     }
     // ---- what does this step need from the window? ----
     const bool moments_needed = rq.n >= 2 && !rq.degenerate;
@@ -953,7 +996,7 @@ SDC_HDN void reward_plan(const State& S, int env, ScanRequest& rq, Moments& M) {
             if ((double)th > rq.hi64) th = nextafterf(th, -SDC_INF_F);
             if ((double)tl2 > rq.lo64) tl2 = nextafterf(tl2, -SDC_INF_F);
             if ((double)th2 < rq.hi64) th2 = nextafterf(th2, SDC_INF_F);
-            rq.tails = (want_tails && nl >= 0) ? 2 : 1;         // 2: a fence left its (still valid) band
+            rq.tails = (want_tails && had_bands) ? 2 : 1;       // 2: a fence left its (still valid) band
             rq.tl = tl; rq.th = th; rq.tl2 = tl2; rq.th2 = th2;
         }
     } else if (moments_needed && !M.ok) {
@@ -965,15 +1008,18 @@ SDC_HDN void reward_plan(const State& S, int env, ScanRequest& rq, Moments& M) {
 struct RefreshRaw {
     double s1, s2;          // exact unclipped sums about the new centre (ScanRequest::shift)
     int n_tail[2];          // values inside the lower / upper band (may exceed kTailCap: then only the count is valid)
+    int band_nb[2];         // of those, the values beyond the fence of the requesting step, with their
+    double band_b1[2], band_b2[2];   // sum / sum of squares about the new centre
     int agg_n[2]; double agg_s1[2], agg_s2[2];   // values beyond the outer thresholds: count and sums about the new centre
     int c[2], below[2];     // per list: values inside [ca, cb] (may exceed kCollectCap), values below ca
 };
 
 // Turns the collected values into the env's new incremental state.  `sorted[j]`: the c[j] collected values of list j in
-// ascending order (valid when c[j] <= kCollectCap).  Lane-strided so that a warp can share the copying; all lanes get
-// the same return values.  On the host lane = 0, n_lanes = 1.
+// ascending order (valid when c[j] <= kCollectCap); `bands[sd]`: the n_tail[sd] band values in ascending order (valid when
+// both fit).  Lane-strided so that a warp can share the copying; all lanes get the same return values.  On the host
+// lane = 0, n_lanes = 1.
 SDC_HDN void refresh_commit(const State& S, int env, const ScanRequest& rq, const RefreshRaw& raw, const float* const* sorted,
-                            QView& Q, ScanResult& rs, int lane, int n_lanes) {
+                            const float* const* bands, QView& Q, ScanResult& rs, int lane, int n_lanes) {
     uint32_t fc = S.fast_cfg[env];
     int aexp = (int)(fc & 0xffu), retry = (int)((fc >> 8) & 0xffu);
     int wexp[2] = {(int)(int8_t)(fc >> 16), (int)(int8_t)(fc >> 24)};
@@ -1012,17 +1058,24 @@ SDC_HDN void refresh_commit(const State& S, int env, const ScanRequest& rq, cons
         const bool fits = raw.n_tail[0] <= kTailCap && raw.n_tail[1] <= kTailCap;
         if (fits) {
             const int big = raw.n_tail[0] > raw.n_tail[1] ? raw.n_tail[0] : raw.n_tail[1];
+            for (int sd = 0; sd < 2; ++sd) {
+                float* p = tail_ptr(S, env, sd);
+                for (int i = lane; i < raw.n_tail[sd]; i += n_lanes) p[i] = bands[sd][i];
+            }
             if (lane == 0) {
                 S.tail_n[2 * env] = raw.n_tail[0]; S.tail_n[2 * env + 1] = raw.n_tail[1];
+                S.tail_nb[2 * env] = raw.band_nb[0]; S.tail_nb[2 * env + 1] = raw.band_nb[1];
+                S.tail_bs[4 * env] = raw.band_b1[0]; S.tail_bs[4 * env + 1] = raw.band_b2[0];
+                S.tail_bs[4 * env + 2] = raw.band_b1[1]; S.tail_bs[4 * env + 3] = raw.band_b2[1];
                 S.tail_thr[4 * env] = rq.tl; S.tail_thr[4 * env + 1] = rq.th; S.tail_thr[4 * env + 2] = rq.tl2; S.tail_thr[4 * env + 3] = rq.th2;
                 S.agg_n[2 * env] = raw.agg_n[0]; S.agg_n[2 * env + 1] = raw.agg_n[1];
                 S.agg_s[4 * env] = raw.agg_s1[0]; S.agg_s[4 * env + 1] = raw.agg_s2[0];
                 S.agg_s[4 * env + 2] = raw.agg_s1[1]; S.agg_s[4 * env + 3] = raw.agg_s2[1];
                 S.mom_s1[env] = raw.s1; S.mom_s2[env] = raw.s2; S.mom_c0[env] = (double)rq.shift;
             }
-            // band width policy: widen after a refresh that was forced by a fence leaving its band (rq.tails == 2),
-            // narrow when a band is more crowded than needed (the walk over the band is the per-step cost)
-            if (rq.tails == 2) { if (aexp > 0) aexp -= 1; }
+            // band width policy: widen after a refresh that was forced by a fence leaving its band (rq.tails == 2) or when both
+            // bands came out sparse, narrow when one is close to its capacity
+            if (rq.tails == 2 || big < kBandSparse) { if (aexp > 0) aexp -= 1; }
             else for (int b = big; b > kBandTarget && aexp < kAlphaOff; b >>= 1) aexp += 1;
         } else {
             if (lane == 0) { S.tail_n[2 * env] = -1; S.tail_n[2 * env + 1] = -1; }

@@ -153,17 +153,12 @@ __device__ __forceinline__ void prefetch_env(const sdc::State& S, const sdc::Tab
     prefetch_line(l0); prefetch_line(l0 + max(qm.x - 1, 0)); prefetch_line(l0 + min(max((n_after - 1) / 4 - qa.x, 0), sdc::kListCap - 1));
     const float* l1 = l0 + sdc::kListCap;
     prefetch_line(l1); prefetch_line(l1 + max(qm.y - 1, 0)); prefetch_line(l1 + min(max((3 * (n_after - 1)) / 4 - qa.y, 0), sdc::kListCap - 1));
-    prefetch_line(S.agg_s + 4 * (size_t)env); prefetch_line(S.tail_thr + 4 * (size_t)env);
-    const int lane = threadIdx.x & 31;
-    int rows_lo = active ? tn.x : 0, rows_hi = active ? tn.y : 0;   // lane j fetches rows j, j+32, ... of the unit's interleaved band arrays
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        rows_lo = max(rows_lo, __shfl_xor_sync(0xffffffffu, rows_lo, o));
-        rows_hi = max(rows_hi, __shfl_xor_sync(0xffffffffu, rows_hi, o));
-    }
-    const float* band = S.tails + (size_t)(env >> 5) * 2 * sdc::kTailCap * sdc::kTailStride;
-    for (int r = lane; r < rows_lo; r += 32) prefetch_line(band + (size_t)r * sdc::kTailStride);
-    for (int r = lane; r < rows_hi; r += 32) prefetch_line(band + (size_t)(sdc::kTailCap + r) * sdc::kTailStride);
+    prefetch_line(S.agg_s + 4 * (size_t)env); prefetch_line(S.tail_thr + 4 * (size_t)env); prefetch_line(S.tail_bs + 4 * (size_t)env);
+    // the band values at the split (where the fence sits inside each sorted band)
+    const int2 nb = reinterpret_cast<const int2*>(S.tail_nb)[env];
+    const float* band = S.tails + (size_t)env * 2 * sdc::kTailCap;
+    prefetch_line(band + min(max(nb.x, 0), sdc::kTailCap - 1));
+    prefetch_line(band + sdc::kTailCap + min(max(tn.y - nb.y, 0), sdc::kTailCap - 1));
 }
 
 struct GlobalInfoSink {
@@ -175,7 +170,8 @@ struct GlobalInfoSink {
 // Parameters and results of the pass in flight (one at a time per CTA).
 struct PassJob {
     // request (written by the lane that owns the env)
-    int env, n, kind;
+    int env, n, kind, pad;
+    double lo64, hi64;                      // the step's fences in fp64: where the rebuilt bands are split
     float lo, hi, shift, tl, th, tl2, th2;
     int dir[2]; float thr[2];
     int rc[2], k[2]; float ca[2], cb[2];
@@ -189,6 +185,8 @@ struct PassShared {
     unsigned long long bar;                 // mbarrier of the bulk copy
     PassJob job;
     int fill[5];                            // slots handed out: lower band, upper band, collect list 0, collect list 1, hit list
+    int band_nb[2];                         // rebuilt bands: values beyond the fence, their sums about the new centre
+    double band_b1[2], band_b2[2];
     float red_f[kWarpsPerBlock][4];         // s1, s2, ext0, ext1
     double red_d[kWarpsPerBlock][6];        // S1, S2, far sums
     int red_i[kWarpsPerBlock][6];           // cnt0, cnt1, below0, below1, far counts
@@ -238,6 +236,7 @@ __device__ __forceinline__ void block_bitonic_sort(float* buf, int p2) {
 // `scr`, then sorted) and the single-rank fallback -- then warp 0 commits the env's new incremental state.
 // `win` = hist_cap floats of shared memory.  Called by all threads of the CTA; `phase` = parity of the mbarrier.
 __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, float* win, float* scr, float* hits, int hit_cap, unsigned phase) {
+    float* band_scr = scr + 2 * sdc::kCollectCap;                        // [2][kTailCap] band values, sorted by warps 0 / 1 below
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PassJob& J = ps.job;
     const int n = J.n, env = J.env;
@@ -260,8 +259,6 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
     const float ca1 = (refresh && J.rc[1]) ? J.ca[1] : SDC_INF_F, cb1 = (refresh && J.rc[1]) ? J.cb[1] : -SDC_INF_F;
     const float quiet_lo = refresh ? fmaxf(tl, fmaxf(dir0 == sdc::SCAN_BELOW ? thr0 : -SDC_INF_F, dir1 == sdc::SCAN_BELOW ? thr1 : -SDC_INF_F)) : -SDC_INF_F;
     const float quiet_hi = refresh ? fminf(th, fminf(dir0 == sdc::SCAN_ABOVE ? thr0 : SDC_INF_F, dir1 == sdc::SCAN_ABOVE ? thr1 : SDC_INF_F)) : SDC_INF_F;
-    float* tail_lo = sdc::tail_ptr(S, env, 0);
-    float* tail_hi = sdc::tail_ptr(S, env, 1);
     float s1 = 0.f, s2 = 0.f;
     double S1 = 0.0, S2 = 0.0;
     const double c0 = (double)shift;
@@ -283,9 +280,9 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
             if (dir1 == sdc::SCAN_ABOVE && x > thr1) { cnt1 += 1; ext1 = fminf(ext1, x); }
         }
         if (x < tl2) { far_n0 += 1; far_a0 += y; far_b0 = fma(y, y, far_b0); }
-        else if (x < tl) { const int pos = atomicAdd(&ps.fill[0], 1); if (pos < sdc::kTailCap) tail_lo[(size_t)pos * sdc::kTailStride] = x; }
+        else if (x < tl) { const int pos = atomicAdd(&ps.fill[0], 1); if (pos < sdc::kTailCap) band_scr[pos] = x; }
         if (x > th2) { far_n1 += 1; far_a1 += y; far_b1 = fma(y, y, far_b1); }
-        else if (x > th) { const int pos = atomicAdd(&ps.fill[1], 1); if (pos < sdc::kTailCap) tail_hi[(size_t)pos * sdc::kTailStride] = x; }
+        else if (x > th) { const int pos = atomicAdd(&ps.fill[1], 1); if (pos < sdc::kTailCap) band_scr[sdc::kTailCap + pos] = x; }
         if (x >= ca0 && x <= cb0) { const int pos = atomicAdd(&ps.fill[2], 1); if (pos < sdc::kCollectCap) scr[pos] = x; }
         if (x >= ca1 && x <= cb1) { const int pos = atomicAdd(&ps.fill[3], 1); if (pos < sdc::kCollectCap) scr[sdc::kCollectCap + pos] = x; }
     };
@@ -325,6 +322,35 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
         ps.red_i[warp][4] = far_n0; ps.red_i[warp][5] = far_n1;
     }
     __syncthreads();                                                     // partials + all band / collect stores visible
+    if (refresh && J.tails && warp < 2 && ps.fill[0] <= sdc::kTailCap && ps.fill[1] <= sdc::kTailCap) {
+        // warp `warp` sorts band `warp` (bitonic over kTailCap slots in shared memory, warp-synchronous) and splits it at the
+        // requesting step's fence: count and sums about the new centre of the values beyond it
+        float* b = band_scr + warp * sdc::kTailCap;
+        const int cntb = ps.fill[warp];
+        for (int i = cntb + lane; i < sdc::kTailCap; i += 32) b[i] = SDC_INF_F;
+        __syncwarp();
+        for (int k = 2; k <= sdc::kTailCap; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = lane; i < sdc::kTailCap; i += 32) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const float x = b[i], y = b[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((x > y) == up) { b[i] = y; b[ixj] = x; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        const double fence = warp == 0 ? J.lo64 : J.hi64;
+        int nbz = 0; double z1 = 0.0, z2 = 0.0;
+        for (int i = lane; i < cntb; i += 32) {
+            const float x = b[i];
+            if (warp == 0 ? (double)x < fence : (double)x > fence) { const double y = (double)x - c0; nbz += 1; z1 += y; z2 = fma(y, y, z2); }
+        }
+        nbz = warp_sum(nbz); z1 = warp_sum(z1); z2 = warp_sum(z2);
+        if (lane == 0) { ps.band_nb[warp] = nbz; ps.band_b1[warp] = z1; ps.band_b2[warp] = z2; }
+    }
     sdc::RefreshRaw raw;
     sdc::ScanResult rs;
     {
@@ -349,6 +375,7 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
         raw.agg_s1[0] = d[2]; raw.agg_s2[0] = d[3]; raw.agg_s1[1] = d[4]; raw.agg_s2[1] = d[5];
         raw.n_tail[0] = ps.fill[0]; raw.n_tail[1] = ps.fill[1]; raw.c[0] = ps.fill[2]; raw.c[1] = ps.fill[3];
     }
+    // (band_nb / band_b1 / band_b2 are read by warp 0 after the barrier that follows the bracket sorts)
     if (refresh) {
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {                                    // uniform across the CTA
@@ -376,7 +403,9 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
             Ql.lst[0] = S.qlist + (size_t)env * 2 * sdc::kListCap; Ql.lst[1] = Ql.lst[0] + sdc::kListCap;
             Ql.a[0] = J.q_a[0]; Ql.a[1] = J.q_a[1]; Ql.m[0] = J.q_m[0]; Ql.m[1] = J.q_m[1];
             const float* sorted[2] = {win, win + sdc::kCollectCap};
-            sdc::refresh_commit(S, env, rl, raw, sorted, Ql, rs, lane, 32);
+            const float* bands[2] = {band_scr, band_scr + sdc::kTailCap};
+            for (int sd = 0; sd < 2; ++sd) { raw.band_nb[sd] = ps.band_nb[sd]; raw.band_b1[sd] = ps.band_b1[sd]; raw.band_b2[sd] = ps.band_b2[sd]; }
+            sdc::refresh_commit(S, env, rl, raw, sorted, bands, Ql, rs, lane, 32);
             // cursors of the re-centred brackets (a maintenance pass has no owner lane that would store them)
             if (lane < 2 && (rs.recentred & (1 << lane))) { S.q_a[env * 2 + lane] = rs.new_a[lane]; S.q_m[env * 2 + lane] = rs.new_m[lane]; }
         }
@@ -600,8 +629,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         }
         __syncthreads();
     }
-    float* scr = reinterpret_cast<float*>(smem_raw + table_bytes);      // [2][kCollectCap] collect scratch of the window pass
-    float* win = scr + 2 * sdc::kCollectCap;                            // [hist_cap] the staged window
+    float* scr = reinterpret_cast<float*>(smem_raw + table_bytes);      // [2][kCollectCap] + [2][kTailCap] collect scratch of the window pass
+    float* win = scr + 2 * sdc::kCollectCap + 2 * sdc::kTailCap;        // [hist_cap] the staged window
     const int win_floats = S.hist_cap > 2 * sdc::kCollectCap ? S.hist_cap : 2 * sdc::kCollectCap;
     float* hits = win + win_floats;                                     // parked hits of a pass: the rest of the region the obs tiles use
 
@@ -643,6 +672,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         st.terminal = 0;
         en.energy = 0.0; en.nci_next = 0.0; en.ls_penalty = 0.0;
         rq.kind = sdc::SCAN_SKIP; rq.n = 0; rq.lo = rq.hi = rq.shift = 0.f; rq.tl = rq.th = rq.tl2 = rq.th2 = 0.f; rq.tails = 0;
+        rq.lo64 = rq.hi64 = rq.q1 = 0.0; rq.e = rq.o = 0.f; rq.evict = 0;
         rq.dir[0] = rq.dir[1] = 0; rq.thr[0] = rq.thr[1] = 0.f; rq.rc[0] = rq.rc[1] = 0; rq.k[0] = rq.k[1] = 0;
         rq.ca[0] = rq.ca[1] = rq.cb[0] = rq.cb[1] = 0.f; rq.degenerate = 0;
         rs.s1 = rs.s2 = 0.f; rs.cnt[0] = rs.cnt[1] = 0; rs.ext[0] = rs.ext[1] = 0.f; rs.recentred = 0;
@@ -652,6 +682,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         Q.a[0] = Q.a[1] = Q.m[0] = Q.m[1] = 0;
         long long tk1 = tk0;
         float alt3[3] = {0.f, 0.f, 0.f};
+        sdc::BandPlan bp; bp.rm[0] = bp.rm[1] = bp.ins[0] = bp.ins[1] = 0;
+        sdc::BandDone bd; bd.rm[0] = bd.rm[1] = bd.pos[0] = bd.pos[1] = -1;
         prefetch_env(S, T, env, active, 3);
         if (active) {
             const int2 qa = reinterpret_cast<const int2*>(S.q_a)[env], qm = reinterpret_cast<const int2*>(S.q_m)[env];
@@ -669,7 +701,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
             Q.a[0] = qa.x; Q.a[1] = qa.y; Q.m[0] = qm.x; Q.m[1] = qm.y;
             if (S.append_history) {                    // utils/reward_creator.py:62-63: only default_ls_reward grows the window
                 sdc::reward_prepare(S, env, en.energy, st.hist_len, st.hist_head, st.evicted, Q, rq, edits);   // en.energy -> relative
-                sdc::reward_plan(S, env, rq, M);
+                sdc::reward_plan_a(S, env, rq, M, bp);
             }
         }
         __syncwarp();
@@ -696,6 +728,54 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                 __syncwarp();
             }
         }
+        // The step's sample entering / the evicted one leaving a tail band (~2 % of the env-steps): sorted removal / insertion
+        // by the whole warp -- every lane holds four band slots, ballots find the evicted value and count the values <= the
+        // new one (insertion after ties), then the edited band is written back like a bracket.
+#pragma unroll 1
+        for (int sd = 0; sd < 2; ++sd) {
+            unsigned need = __ballot_sync(0xffffffffu, active && (bp.rm[sd] | bp.ins[sd]));
+            while (need) {
+                const int l = __ffs(need) - 1;
+                need &= need - 1;
+                const int do_rm = __shfl_sync(0xffffffffu, bp.rm[sd], l), do_ins = __shfl_sync(0xffffffffu, bp.ins[sd], l);
+                const float o_l = __shfl_sync(0xffffffffu, rq.o, l), e_l = __shfl_sync(0xffffffffu, rq.e, l);
+                float* B = sdc::tail_ptr(S, env0 + l, sd);
+                const int nB = S.tail_n[2 * (env0 + l) + sd];              // same address for the warp: one broadcast load
+                float v[sdc::kTailCap / 32];
+#pragma unroll
+                for (int t = 0; t < sdc::kTailCap / 32; ++t) { const int i = lane + 32 * t; v[t] = i < nB ? B[i] : SDC_INF_F; }
+                int rm = -1, pos = -1;
+                if (do_rm) {
+#pragma unroll
+                    for (int t = 0; t < sdc::kTailCap / 32; ++t) {
+                        const unsigned hit = __ballot_sync(0xffffffffu, lane + 32 * t < nB && v[t] == o_l);
+                        if (hit && rm < 0) rm = 32 * t + __ffs(hit) - 1;
+                    }
+                }
+                if (do_ins && nB - (rm >= 0) < sdc::kTailCap) {
+                    pos = 0;
+#pragma unroll
+                    for (int t = 0; t < sdc::kTailCap / 32; ++t) {
+                        const int i = lane + 32 * t;
+                        pos += __popc(__ballot_sync(0xffffffffu, i < nB && i != rm && v[t] <= e_l));
+                    }
+                }
+                if (rm >= 0 || pos >= 0) {
+                    sdc::ListEdit ed; ed.rm = rm; ed.drop = 0; ed.ins = pos; ed.val = e_l; ed.m0 = nB;
+                    const int len = sdc::edit_len(ed);
+                    float w[sdc::kTailCap / 32];
+#pragma unroll
+                    for (int t = 0; t < sdc::kTailCap / 32; ++t) { const int i = lane + 32 * t; w[t] = i < len ? sdc::edit_at(B, ed, i) : 0.f; }
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < sdc::kTailCap / 32; ++t) { const int i = lane + 32 * t; if (i < len) B[i] = w[t]; }
+                    __syncwarp();
+                }
+                if (lane == l) { bd.rm[sd] = rm; bd.pos[sd] = pos; }
+            }
+        }
+        if (active && S.append_history) sdc::reward_plan_c(S, env, rq, M, bp, bd);
+        __syncwarp();
         const long long tk2 = clock64();
         // A pass whose result this step's reward does not need (the brackets still hold the quartile ranks and the tail
         // bands still contain the fences: the refresh only restores slack for FUTURE steps) is a maintenance pass: its
@@ -736,7 +816,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                 // bands / moments of this env, all of which this lane has finished writing)
                 const int idx = atomicAdd(a.ctr + 10, 1);
                 PassJob J;
-                J.env = env; J.n = rq.n; J.kind = kind;
+                J.env = env; J.n = rq.n; J.kind = kind; J.pad = 0; J.lo64 = rq.lo64; J.hi64 = rq.hi64;
                 J.lo = rq.lo; J.hi = rq.hi; J.shift = rq.shift; J.tl = rq.tl; J.th = rq.th; J.tl2 = rq.tl2; J.th2 = rq.th2;
                 J.dir[0] = 0; J.dir[1] = 0; J.thr[0] = 0.f; J.thr[1] = 0.f;
                 J.rc[0] = rq.rc[0]; J.rc[1] = rq.rc[1]; J.k[0] = rq.k[0]; J.k[1] = rq.k[1];
@@ -823,7 +903,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                 mask &= mask - 1;
                 if (warp == w && lane == l) {
                     PassJob& J = ps.job;
-                    J.env = env; J.n = rq.n; J.kind = rq.kind;
+                    J.env = env; J.n = rq.n; J.kind = rq.kind; J.pad = 0; J.lo64 = rq.lo64; J.hi64 = rq.hi64;
                     J.lo = rq.lo; J.hi = rq.hi; J.shift = rq.shift; J.tl = rq.tl; J.th = rq.th; J.tl2 = rq.tl2; J.th2 = rq.th2;
                     J.dir[0] = rq.dir[0]; J.dir[1] = rq.dir[1]; J.thr[0] = rq.thr[0]; J.thr[1] = rq.thr[1];
                     J.rc[0] = rq.rc[0]; J.rc[1] = rq.rc[1]; J.k[0] = rq.k[0]; J.k[1] = rq.k[1];
@@ -1044,7 +1124,7 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     // Dynamic shared memory of k_step after the tables: collect scratch + the staged window (which also receives the sorted
     // collections: at least 2 x kCollectCap floats) + the parked-hit list.  The fused kernel shares the region with its
     // observation tiles (whatever they leave beyond scratch + window is the hit list).
-    const size_t pass_floats = (size_t)2 * sdc::kCollectCap + (S.hist_cap > 2 * sdc::kCollectCap ? S.hist_cap : 2 * sdc::kCollectCap);
+    const size_t pass_floats = (size_t)2 * sdc::kCollectCap + 2 * sdc::kTailCap + (S.hist_cap > 2 * sdc::kCollectCap ? S.hist_cap : 2 * sdc::kCollectCap);
     const size_t tile_floats = (size_t)kWarpsPerBlock * 32 * kTileStride;
     size_t smem_floats = pass_floats > tile_floats ? pass_floats : tile_floats;
     const int hit_cap = (int)(smem_floats - pass_floats);

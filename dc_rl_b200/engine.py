@@ -21,7 +21,7 @@ _STATE_DTYPES = {
     "ls_sum": np.int32, "ls_bins": np.uint16, "ls_ring": np.uint8, "setpoint": np.float64, "dc_run": np.int32,
     "dc_scale": np.int32, "dc_last": np.int8, "bat_load": np.float64, "hist": np.float32, "hist_ref": np.float64, "hist_len": np.int32,
     "hist_head": np.int32, "phase_clocks": np.uint64, "qlist": np.float32, "q_a": np.int32, "q_m": np.int32, "err": np.int32,
-    "mom_s1": np.float64, "mom_s2": np.float64, "mom_c0": np.float64, "tails": np.float32, "tail_n": np.int32,
+    "mom_s1": np.float64, "mom_s2": np.float64, "mom_c0": np.float64, "tails": np.float32, "tail_n": np.int32, "tail_nb": np.int32, "tail_bs": np.float64,
     "tail_thr": np.float32, "agg_n": np.int32, "agg_s": np.float64, "fast_cfg": np.uint32, "counters": np.int32, "pass_stats": np.int32,
     "pend_valid": np.uint8, "pend_weather": np.float64, "cur_buf": np.uint8, "pend_obs": np.float32, "metrics": np.float64, "hvac_hist": np.uint64,
 }
@@ -218,7 +218,7 @@ class Engine:
         dt = np.dtype(_STATE_DTYPES[name])
         n = self.n_envs
         per_env = {"weather": 2 * self.win_len, "pend_weather": 2 * self.win_len, "pend_obs": N_AGENTS * OBS_DIM, "ls_bins": 4, "hist": self.hist_cap, "qlist": 2 * _lib.LIST_CAP, "q_a": 2, "q_m": 2,
-                   "tail_n": 2, "tail_thr": 4, "agg_n": 2, "agg_s": 4}.get(name, 1)
+                   "tail_n": 2, "tail_nb": 2, "tail_bs": 4, "tail_thr": 4, "agg_n": 2, "agg_s": 4, "tails": 2 * _lib.TAIL_CAP}.get(name, 1)
         if name == "phase_clocks":
             out = np.zeros(16, dt)
         elif name == "counters":
@@ -227,8 +227,6 @@ class Engine:
             out = np.zeros(4, dt)
         elif name in ("metrics", "hvac_hist"):
             out = np.zeros(_lib.HVAC_BINS if name == "hvac_hist" else N_METRICS, dt)
-        elif name == "tails":
-            out = np.zeros(((n + 31) // 32) * 2 * _lib.TAIL_CAP * 32, dt)
         elif name == "ls_ring":
             out = np.zeros(n * 65536, dt)       # upper bound; trimmed below
         else:
@@ -238,7 +236,7 @@ class Engine:
         if name in ("phase_clocks", "counters", "pass_stats", "metrics", "hvac_hist"):
             return out
         if name == "tails":
-            return out.reshape(-1, 2, _lib.TAIL_CAP, 32)         # [env // 32][side][slot][env % 32]
+            return out.reshape(n, 2, _lib.TAIL_CAP)              # [env][side][slot], each band sorted ascending
         return out.reshape(n, -1) if out.size != n else out
 
     def write_state(self, name, values):

@@ -61,6 +61,7 @@ def check_incremental_state(eng, envs=None, tag=""):
     hist = eng.read_state("hist").reshape(n, -1)
     tn, thr, tails = eng.read_state("tail_n").reshape(n, 2), eng.read_state("tail_thr").reshape(n, 4), eng.read_state("tails")
     an, ag = eng.read_state("agg_n").reshape(n, 2), eng.read_state("agg_s").reshape(n, 2, 2)
+    nb, bs = eng.read_state("tail_nb").reshape(n, 2), eng.read_state("tail_bs").reshape(n, 2, 2)
     s1, s2, c0 = (eng.read_state(k).reshape(n) for k in ("mom_s1", "mom_s2", "mom_c0"))
     valid = 0
     for e in (range(n) if envs is None else envs):
@@ -75,10 +76,18 @@ def check_incremental_state(eng, envs=None, tag=""):
         if tn[e, 0] < 0:
             continue
         valid += 1
-        lo_set = np.sort(tails[e // 32, 0, :tn[e, 0], e % 32])
-        hi_set = np.sort(tails[e // 32, 1, :tn[e, 1], e % 32])
+        lo_set, hi_set = tails[e, 0, :tn[e, 0]], tails[e, 1, :tn[e, 1]]            # stored sorted
         assert np.array_equal(lo_set, srt[(srt < thr[e, 0]) & (srt >= thr[e, 2])]), (tag, "low band", e)
         assert np.array_equal(hi_set, srt[(srt > thr[e, 1]) & (srt <= thr[e, 3])]), (tag, "high band", e)
+        # split of each band at the fences of the last step (np.percentile 'linear' in fp64, as the device computes them)
+        w64 = w.astype(np.float64)
+        q1, q3 = np.percentile(w64, 25), np.percentile(w64, 75)
+        f_lo, f_hi = q1 - 1.5 * (q3 - q1), q3 + 1.5 * (q3 - q1)
+        for side, beyond in enumerate((lo_set[lo_set.astype(np.float64) < f_lo], hi_set[hi_set.astype(np.float64) > f_hi])):
+            yb = beyond.astype(np.float64) - c0[e]
+            assert nb[e, side] == len(beyond), (tag, "band split", e, side, nb[e, side], len(beyond))
+            assert abs(yb.sum() - bs[e, side, 0]) <= 1e-9 * max(1.0, float(np.abs(yb).sum())), (tag, "band s1", e, side)
+            assert abs((yb * yb).sum() - bs[e, side, 1]) <= 1e-9 * max(1.0, float((yb * yb).sum())), (tag, "band s2", e, side)
         for side, far in enumerate((srt[srt < thr[e, 2]], srt[srt > thr[e, 3]])):
             yf = far.astype(np.float64) - c0[e]
             assert an[e, side] == len(far), (tag, "far count", e, side)

@@ -67,13 +67,12 @@ static void scan_plain(const sdc::State& S, int env, const sdc::ScanRequest& rq,
 
 // refresh pass: serial statement of scan_refresh in sdc_kernels.cu
 static void scan_refresh(const sdc::State& S, int env, const sdc::ScanRequest& rq, sdc::RefreshRaw& raw, sdc::ScanResult& rs,
-                         std::vector<float> coll[2]) {
+                         std::vector<float> coll[2], std::vector<float> band[2]) {
     const float* h = S.hist + (size_t)env * S.hist_cap;
     float s1 = 0.f, s2 = 0.f;
     double S1 = 0.0, S2 = 0.0;
     const double c0 = (double)rq.shift;
-    float* tl = sdc::tail_ptr(S, env, 0);
-    float* th = sdc::tail_ptr(S, env, 1);
+    band[0].clear(); band[1].clear();
     raw.n_tail[0] = raw.n_tail[1] = 0;
     for (int j = 0; j < 2; ++j) { raw.agg_n[j] = 0; raw.agg_s1[j] = raw.agg_s2[j] = 0.0; }
     for (int j = 0; j < 2; ++j) {
@@ -95,15 +94,22 @@ static void scan_refresh(const sdc::State& S, int env, const sdc::ScanRequest& r
             }
         }
         if (x < rq.tl2) { raw.agg_n[0]++; raw.agg_s1[0] += y; raw.agg_s2[0] += y * y; }
-        else if (x < rq.tl) { if (raw.n_tail[0] < sdc::kTailCap) tl[(size_t)raw.n_tail[0] * sdc::kTailStride] = x; raw.n_tail[0]++; }
+        else if (x < rq.tl) { if (raw.n_tail[0] < sdc::kTailCap) band[0].push_back(x); raw.n_tail[0]++; }
         if (x > rq.th2) { raw.agg_n[1]++; raw.agg_s1[1] += y; raw.agg_s2[1] += y * y; }
-        else if (x > rq.th) { if (raw.n_tail[1] < sdc::kTailCap) th[(size_t)raw.n_tail[1] * sdc::kTailStride] = x; raw.n_tail[1]++; }
+        else if (x > rq.th) { if (raw.n_tail[1] < sdc::kTailCap) band[1].push_back(x); raw.n_tail[1]++; }
     }
     for (int j = 0; j < 2; ++j) {
         if (rq.dir[j] == sdc::SCAN_NONE) rs.ext[j] = 0.f;
         std::sort(coll[j].begin(), coll[j].end());
     }
     rs.s1 = s1; rs.s2 = s2; raw.s1 = S1; raw.s2 = S2;
+    for (int sd = 0; sd < 2; ++sd) {                 // sorted bands + the part of each beyond the requesting step's fence
+        std::sort(band[sd].begin(), band[sd].end());
+        raw.band_nb[sd] = 0; raw.band_b1[sd] = raw.band_b2[sd] = 0.0;
+        for (float x : band[sd]) {
+            if (sd == 0 ? (double)x < rq.lo64 : (double)x > rq.hi64) { const double y = (double)x - c0; raw.band_nb[sd]++; raw.band_b1[sd] += y; raw.band_b2[sd] += y * y; }
+        }
+    }
 }
 
 static const char* launch_reset(Context&, const sdc::State& S, const int32_t* list, const int32_t* count, float* obs, float* share, void*);
@@ -132,17 +138,24 @@ static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs&
         if (S.append_history) {
             sdc::reward_prepare(S, env, e_rel, st.hist_len, st.hist_head, st.evicted, Q, rq, edits);
             for (int j = 0; j < 2; ++j) sdc::edit_apply(Q.lst[j], edits[j]);      // the CUDA kernel does this warp-cooperatively
-            sdc::reward_plan(S, env, rq, mo);
+            sdc::BandPlan bp;
+            sdc::BandDone bd; bd.rm[0] = bd.rm[1] = bd.pos[0] = bd.pos[1] = -1;
+            sdc::reward_plan_a(S, env, rq, mo, bp);
+            for (int sd = 0; sd < 2; ++sd)                                         // the CUDA kernel does this warp-cooperatively too
+                if (bp.rm[sd] || bp.ins[sd])
+                    sdc::band_edit(sdc::tail_ptr(S, env, sd), S.tail_n[2 * env + sd], bp.rm[sd], bp.ins[sd], rq.o, rq.e, bd.rm[sd], bd.pos[sd]);
+            sdc::reward_plan_c(S, env, rq, mo, bp, bd);
         }
         if (rq.kind == sdc::SCAN_PLAIN) {
             scan_plain(S, env, rq, rs);
             a.ctr[4] += 1;
         } else if (rq.kind == sdc::SCAN_REFRESH) {
             sdc::RefreshRaw raw;
-            std::vector<float> coll[2];
-            scan_refresh(S, env, rq, raw, rs, coll);
+            std::vector<float> coll[2], band[2];
+            scan_refresh(S, env, rq, raw, rs, coll, band);
             const float* sorted[2] = {coll[0].data(), coll[1].data()};
-            sdc::refresh_commit(S, env, rq, raw, sorted, Q, rs, 0, 1);
+            const float* bands[2] = {band[0].data(), band[1].data()};
+            sdc::refresh_commit(S, env, rq, raw, sorted, bands, Q, rs, 0, 1);
             a.ctr[5] += 1;
         }
         sdc::RewardInputs en{e_rel, st.nci_next, st.ls_penalty};
