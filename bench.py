@@ -1,27 +1,36 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/s of the batched SustainDC step (BASELINE.json metric) on N GPUs of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs 65536] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 3|4] [--envs E] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 65 536 envs per GPU, synthetic
-1-year NY traces (seed 1234), default dc_config (20 racks x 200 CPUs), 7-day episodes with de-synchronised
-phases so that ~N/672 envs auto-reset every step, reward windows pre-filled to H = 10 000 with N(330, 40) kWh,
-uniform random actions.  A "step" = one sdc_step over all envs of a rank.
+Workload (--config 3, BASELINE.json configs[2], the configuration the metric is quoted on): 65 536 envs per GPU, synthetic
+1-year NY traces (seed 1234), default dc_config (20 racks x 200 CPUs), 7-day episodes with de-synchronised phases so that
+~N/672 envs auto-reset every step, uniform random actions, reward windows pre-filled to H = 10 000 with N(330, 40) kWh
+ and then turned over ORGANICALLY: `--settle` (default 12 000) untimed steps run before anything is timed, so
+that every window holds the env's own energies and the rate of window refresh passes is stationary whatever --steps is.
+--config 4 (BASELINE.json configs[3]): 32 768 envs per GPU, env i -> location {az, ny, wa}[i mod 3], geometry
+{dc1, dc2, dc3}[(i // 3) mod 3] through the tolerant dc_config loader, metrics all-gathered every 1 024 steps.
 
-  value      whole-job env-steps/s, inputs resident in HBM, CUDA events around the K timed steps (max over ranks)
-  e2e        the same metric through the host-buffer C-ABI call (numpy in / numpy out): per step H2D of the
-             actions and D2H of obs / share_obs / rewards / dones are inside the timed region
-  roofline   algorithmic bytes (4*H + 1024 = 41 024 B per env-step, the fixed numerator) / k_step
-             launch time vs the measured HBM copy bandwidth in MEASURED_PEAKS.json.  k_step maintains the reward
-             normaliser incrementally and streams a window only when an env's incremental state needs a refresh
-             (DESIGN.md section 4), so it touches ~8x fewer physical bytes than the algorithmic figure: `frac` > 1
-             is expected ("report both"); `traffic` is the ncu DRAM figure of the same launch
-  cpu_baseline  the oracle port of the reference's SustainDC.step (oracle/sdc_oracle.py) on the host cores,
-             one env per process, reward window pre-filled the same way, bounded sample
-`--impl reference` prints the CPU arm alone (the reference is pure Python/numpy: its own implementation of this
-path IS the CPU path; /root/reference does not exist on the GPU box, so the pinned oracle port stands in).
+A "step" = one sdc_step over all envs of a rank.  One JSON line:
+  value           whole-job env-steps/s, inputs resident in HBM, EVERY output of the real call produced (obs, share_obs,
+                  rewards, dones, the 59-column info table, terminal observations); CUDA events around the K timed steps,
+                  max over ranks.  `value_core_outputs`: the same without info / terminal observations (round-1 definition).
+  e2e             the same metric through the host-buffer C-ABI call a numpy caller makes (sdc_step_compact_host: actions
+                  in; the 53 unpadded observation floats, rewards, dones and terminal rows out), H2D + D2H inside the timed
+                  region.  `e2e_padded`: sdc_step_host (obs[N,3,26] + share[N,29]); `e2e_vec_env`: CudaShareVecEnv.step, the
+                  object harl.runners drive (zero-copy views / reference-like copies).
+  roofline        `achieved` / `frac`: algorithmic bytes (4*H + 1024 = 41 024 B per env-step, the fixed
+                  numerator) / k_step launch time vs the measured HBM copy bandwidth.  k_step keeps the reward normaliser
+                  incrementally exact and streams a window only when its incremental state needs a refresh, so it moves far
+                  fewer PHYSICAL bytes: `traffic` (ncu dram bytes of one steady-state launch, read from
+                  profiles/r02_kstep_ncu.json), `physical` (GB/s and fraction of peak) and `limiters` (issue slots, fp64
+                  pipe, occupancy from the same capture) say what bounds the kernel: latency, not bandwidth.
+  cpu_baseline    the reference's own SustainDC.step (unmodified files under baseline/_ref, `kind: reference`) on the host
+                  cores, one env per process, reward window pre-filled the same way, bounded sample; the oracle port
+                  (`kind: port`) only when baseline/_ref is absent.
+`--impl reference` prints that CPU arm alone.
 """
 import argparse
 import json
@@ -37,11 +46,9 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 B_ALG_STEADY = 4 * 10000 + 1024      # bytes per env-step at H = 10 000
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch at N = 65 536 (launch 151 of the bench workload, ~390
-# window refreshes in flight) from the round-1 `ncu --set full` capture (profiles/r01_kstep_ncu_raw.csv); only
-# meaningful for the default --envs
-TRAFFIC_BYTES_PER_LAUNCH = 236.845312e6 + 76.829440e6
 METRIC = "env-steps/sec at N=65536 parallel envs, 1/2/4/8xB200; HBM GB/s fraction"
+REF_ROOT = os.path.join(REPO, "baseline", "_ref")
+NCU_JSON = os.path.join(REPO, "profiles", "r02_kstep_ncu.json")
 
 
 def measured_peak():
@@ -86,9 +93,34 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference step, one env per process
+# CPU arm: the reference's own step (baseline/_ref), or the oracle port when that tree is absent
 # ---------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
+def _ref_worker(args):
+    """One live reference env (unmodified files under baseline/_ref) in this process."""
+    rank, n_steps, seed = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["SDC_REFERENCE_ROOT"] = REF_ROOT
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import random
+    import live_ref                                       # shims only (gymnasium / matplotlib / psychrolib / dashboard stubs)
+    env = live_ref.fresh_env({"location": "ny", "month": 6, "days_per_episode": 7})
+    from utils import reward_creator                      # the reference's module: its window is a per-process global
+    random.seed(seed + rank); np.random.seed(seed + rank)
+    rng = np.random.RandomState(5678 + rank)
+    env.reset()
+    reward_creator.energy_history.extend((330 + 40 * rng.standard_normal(10000)).tolist())
+    agents = ("agent_ls", "agent_dc", "agent_bat")
+    for _ in range(10):
+        env.step(dict(zip(agents, rng.randint(0, 3, 3))))
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        _, _, _, trunc, _ = env.step(dict(zip(agents, rng.randint(0, 3, 3))))
+        if trunc["__all__"]:
+            env.reset()
+    return n_steps, time.perf_counter() - t0
+
+
+def _port_worker(args):
     rank, n_steps, seed = args
     os.environ["OMP_NUM_THREADS"] = "1"
     sys.path.insert(0, os.path.join(REPO, "oracle"))
@@ -104,7 +136,7 @@ def _cpu_worker(args):
     rng = np.random.RandomState(5678 + rank)
     env.history.extend((330 + 40 * rng.standard_normal(10000)).tolist())
     env.reset()
-    for _ in range(20):
+    for _ in range(10):
         env.step(*rng.randint(0, 3, 3))
     t0 = time.perf_counter()
     for _ in range(n_steps):
@@ -117,30 +149,45 @@ def _cpu_worker(args):
 def cpu_arm(steps_per_proc, cores=None):
     import multiprocessing as mp
     cores = cores or min(os.cpu_count() or 1, 64)
+    live = os.path.isfile(os.path.join(REF_ROOT, "sustaindc_env.py"))
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(r, steps_per_proc, 91011) for r in range(cores)])
+        res = pool.map(_ref_worker if live else _port_worker, [(r, steps_per_proc, 91011) for r in range(cores)])
         wall = time.perf_counter() - t0
-    per_proc = [n / dt for n, dt in res]
-    total = sum(per_proc)
-    return dict(value=total, unit="env-steps/s", cores=cores, kind="port",
-                sample="%d processes x %d warm steps of oracle/sdc_oracle.py OracleEnv.step (H=10000 pre-filled, NY synthetic "
-                       "traces, random actions, auto-reset); per-core %.1f steps/s; pool wall %.1f s" % (
-                           cores, steps_per_proc, total / cores, wall))
+    total = sum(n / dt for n, dt in res)
+    what = ("the reference's own sustaindc_env.SustainDC.step (unmodified files under baseline/_ref, real NY data files)" if live
+            else "oracle/sdc_oracle.py OracleEnv.step (port; baseline/_ref absent)")
+    return dict(value=total, unit="env-steps/s", cores=cores, kind="reference" if live else "port",
+                sample="%d processes x %d warm steps of %s, H=10000 pre-filled, 7-day episodes, random actions, auto-reset; "
+                       "per-core %.1f steps/s; pool wall %.1f s" % (cores, steps_per_proc, what, total / cores, wall))
 
 
 # ---------------------------------------------------------------------------------------------------
-def build_engine(n_envs, device, seed_base=0):
+def build_engine(n_envs, device, seed_base=0, config=3):
     from dc_rl_b200.dc_config import size_datacenter
     from dc_rl_b200.engine import Engine
     from dc_rl_b200.traces import LocationTraces
+    ids = np.arange(n_envs) + seed_base
+    months = np.where(ids < 12, ids % 12, ids % 3 + 5)            # make_train_env rule, harl/utils/envs_tools.py:56-62
+    seeds = ids.astype(np.uint64) * 1000 + 91011
+    if config == 4:
+        with open(os.path.join(REPO, "tests", "golden", "dc_configs.json")) as f:      # the reference's dc_config_dc{1,2,3}.json
+            cfgs = json.load(f)
+        locs, geos = ["az", "ny", "wa"], ["dc1", "dc2", "dc3"]
+        traces = [LocationTraces.synthetic(l, 1234) for l in locs]
+        params, derived = [], None
+        for g in geos:
+            for l in locs:
+                p, derived = size_datacenter(l, cfgs[g])
+                params.append(p)
+        loc_id = (ids % 3).astype(np.uint8)
+        cfg_id = (((ids // 3) % 3) * 3 + ids % 3).astype(np.uint8)
+        eng = Engine(n_envs, traces, params, loc_id=loc_id, cfg_id=cfg_id, months=months, seeds=seeds, days_per_episode=7, device=device)
+        return eng, derived
     traces = LocationTraces.synthetic("ny", 1234)
     params, derived = size_datacenter("ny")
-    ids = np.arange(n_envs)
-    months = np.where(ids < 12, ids % 12, ids % 3 + 5)            # make_train_env rule, harl/utils/envs_tools.py:56-62
-    eng = Engine(n_envs, [traces], [params], months=months, seeds=(ids + seed_base).astype(np.uint64) * 1000 + 91011,
-                 days_per_episode=7, device=device)
+    eng = Engine(n_envs, [traces], [params], months=months, seeds=seeds, days_per_episode=7, device=device)
     return eng, derived
 
 
@@ -158,12 +205,22 @@ def prepare(eng, n_envs, rank):
     eng.write_state("t", eng.read_state("t0").astype(np.int32) + phase)
 
 
+def ncu_capture():
+    try:
+        with open(NCU_JSON) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4])
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: 65536 for config 3, 32768 for config 4)")
+    ap.add_argument("--settle", type=int, default=12000, help="untimed steps that turn the pre-filled reward windows over")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=1500)
     ap.add_argument("--no-cpu", action="store_true")
@@ -172,10 +229,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg = {"workload": "configs[2]: N=65536 envs/GPU, synthetic 1-year NY traces, default dc_config 20 racks x 200 CPUs, "
-                       "7-day episodes (desynchronised), H=10000 pre-filled, random actions",
-           "envs_per_gpu": args.envs, "n_envs_total": args.envs * max(world, 1), "history_len": 10000,
-           "l2": "inputs larger than L2 (reward windows: %.2f GB per GPU)" % (args.envs * 40000 / 1e9)}
+    n = args.envs or (65536 if args.config == 3 else 32768)
+    if args.config == 3:
+        workload = ("configs[2]: N=%d envs/GPU, synthetic 1-year NY traces, default dc_config 20 racks x 200 CPUs, 7-day episodes "
+                    "(desynchronised), H=10000 pre-filled then turned over by %d untimed steps, random actions" % (n, args.settle))
+    else:
+        workload = ("configs[3]: N=%d envs/GPU, env i -> {az,ny,wa}[i%%3] x {dc1,dc2,dc3}[(i//3)%%3] (tolerant dc_config loader), synthetic "
+                    "1-year traces per location, 7-day episodes (desynchronised), H=10000 pre-filled then turned over by %d untimed "
+                    "steps, random actions, metric all-gather every 1024 steps" % (n, args.settle))
+    cfg = {"workload": workload, "envs_per_gpu": n, "n_envs_total": n * max(world, 1), "history_len": 10000,
+           "l2": "inputs larger than L2 (reward windows: %.2f GB per GPU)" % (n * 40000 / 1e9)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -193,20 +256,21 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from dc_rl_b200 import numa
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    placement = numa.bind_to_gpu(local)          # before the engine allocates its pinned host buffers
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    n = args.envs
-    eng, _ = build_engine(n, local, seed_base=rank * n)
+    eng, _ = build_engine(n, local, seed_base=rank * n, config=args.config)
     for kv in filter(None, args.tune.split(",")):
         k, v = kv.split("=")
         eng.set_tuning(**{k: int(v)})
     prepare(eng, n, rank)
 
     obs = torch.zeros(n, 3, 26, device=dev); share = torch.zeros(n, 29, device=dev); rew = torch.zeros(n, 3, device=dev)
-    done = torch.zeros(n, dtype=torch.uint8, device=dev)
+    done = torch.zeros(n, dtype=torch.uint8, device=dev); info = torch.zeros(64, n, device=dev); term = torch.zeros(n, 3, 26, device=dev)
     g = torch.Generator(device=dev); g.manual_seed(5678 + rank)
     n_act = 8
     acts = [torch.randint(0, 3, (n, 3), dtype=torch.int32, device=dev, generator=g) for _ in range(n_act)]
@@ -217,56 +281,89 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def one_step(i):
+    def core_step(i):
         eng.step_device(acts[i % n_act], obs, share, rew, done, None, None, stream.cuda_stream)
 
+    def full_step(i):
+        eng.step_device(acts[i % n_act], obs, share, rew, done, info, term, stream.cuda_stream)
+
+    def gather_metrics():
+        if world > 1:                                # the path's one collective: the logger's episode-metric vector
+            m = torch.tensor(eng.metrics(), device=dev)
+            dist.all_gather([torch.zeros_like(m) for _ in range(world)], m)
+
+    # ---- untimed: turn the pre-filled windows over, then warm up the timed call ----
+    t_settle = time.perf_counter()
+    for i in range(args.settle):
+        core_step(i)
+    torch.cuda.synchronize(dev)
+    t_settle = time.perf_counter() - t_settle
     for i in range(max(args.warmup, 3)):
-        one_step(i)
+        full_step(i)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    eng.set_tuning(timing=1)
-    eng.kernel_times()
-    launches0 = eng.launch_count
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    ev[0].record(stream)
-    for i in range(args.steps):
-        one_step(i)
-        ev[i + 1].record(stream)
-    if world > 1:
-        m = torch.tensor(eng.metrics(), device=dev)        # the path's one collective: episode metrics
-        gathered = [torch.zeros_like(m) for _ in range(world)]
-        dist.all_gather(gathered, m)
-    barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    launches = eng.launch_count - launches0
-    ktimes = eng.kernel_times()             # CUDA events recorded by the library on the launch stream
-    pass_stats = eng.read_state("pass_stats")   # window passes of the last timed step: plain, refresh, by brackets, by tails
-    eng.set_tuning(timing=0)
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = n * world * args.steps / (total_ms_max / 1e3)
 
-    # ---- end to end through the host-buffer C-ABI call (numpy in, numpy out) ----
+    def timed(step_fn, steps, with_kernel_times=False):
+        eng.set_tuning(clear_pass_total=1)
+        if with_kernel_times:
+            eng.set_tuning(timing=1)
+            eng.kernel_times()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier()
+        ev[0].record(stream)
+        for i in range(steps):
+            step_fn(i)
+            ev[i + 1].record(stream)
+            if args.config == 4 and (i + 1) % 1024 == 0:
+                gather_metrics()
+        gather_metrics()
+        barrier()
+        total_ms = ev[0].elapsed_time(ev[-1])
+        step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+        kt = eng.kernel_times() if with_kernel_times else None
+        if with_kernel_times:
+            eng.set_tuning(timing=0)
+        passes = eng.read_state("pass_total").astype(np.float64) / steps
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), step_ms, kt, passes
+
+    launches0 = eng.launch_count
+    total_ms_max, step_ms, ktimes, passes = timed(full_step, args.steps, with_kernel_times=True)
+    launches = eng.launch_count - launches0
+    value = n * world * args.steps / (total_ms_max / 1e3)
+    core_ms_max, _, _, _ = timed(core_step, args.steps)
+    value_core = n * world * args.steps / (core_ms_max / 1e3)
+
+    # ---- end to end through the host-buffer calls (numpy in, numpy out; H2D + D2H inside the timed region) ----
     rng = np.random.RandomState(5678 + rank)
     host_acts = [rng.randint(0, 3, size=(n, 3)).astype(np.int32) for _ in range(4)]
-    for i in range(3):
-        eng.step_host(host_acts[i % 4], want_info=False, want_term=False)
     e2e_steps = max(5, min(args.steps, 200))
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        eng.step_host(host_acts[i % 4], want_info=False, want_term=False)
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = n * world * e2e_steps / float(e2e_s.item())
+
+    def host_timed(fn):
+        for i in range(3):
+            fn(host_acts[i % 4])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            fn(host_acts[i % 4])
+        barrier()
+        s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(s, op=dist.ReduceOp.MAX)
+        return n * world * e2e_steps / float(s.item())
+
+    e2e_compact = host_timed(lambda a: eng.step_compact_host(a, want_info=False, want_term=True))
+    e2e_padded = host_timed(lambda a: eng.step_host(a, want_info=False, want_term=True))
+    from dc_rl_b200.vec_env import CudaShareVecEnv
+    vec_args = {"nonoverlapping_shared_obs_space": True}
+    vec_views = CudaShareVecEnv(dict(vec_args, output_views=True), n, engine=eng)
+    e2e_vec_views = host_timed(lambda a: vec_views.step(a))
+    vec_copy = CudaShareVecEnv(vec_args, n, engine=eng)
+    e2e_vec_copy = host_timed(lambda a: vec_copy.step(a))
     clocks = sampler.summary() if sampler else None
     err = int(np.bitwise_or.reduce(eng.read_state("err")))
 
@@ -274,26 +371,39 @@ def main():
         peak, peak_src = measured_peak()
         k_ms = float(ktimes[1] / max(ktimes[0], 1))          # mean k_step launch duration over the timed region
         achieved = B_ALG_STEADY * n / (k_ms / 1e3) / 1e9
+        cap = ncu_capture()
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_step", "launch_ms_mean": k_ms, "launch_ms_max": float(ktimes[3]),
+                "step_ms_median": float(np.median(step_ms)), "bytes_per_launch": B_ALG_STEADY * n, "peak_source": peak_src,
+                "numerator": "SURVEY 8d algorithmic bytes, 4*H + 1024 per env-step (a window pass per step); the kernel maintains the "
+                             "normaliser incrementally, so frac > 1 is expected -- `physical` and `limiters` bound it",
+                "passes_per_step_mean": {"plain": passes[0], "refresh": passes[1], "by_brackets": passes[2], "by_bands": passes[3],
+                                         "share_of_env_steps": float((passes[0] + passes[1]) / n)}}
+        if cap and n == cap.get("n_envs"):
+            roof["traffic"] = cap["dram_bytes_per_launch"]
+            phys = cap["dram_bytes_per_launch"] / (k_ms / 1e3) / 1e9
+            roof["physical"] = {"achieved": phys, "frac": phys / peak, "bytes_per_env_step": cap["dram_bytes_per_launch"] / n,
+                                "source": "profiles/r02_kstep_ncu.json (%s)" % cap.get("commit", "?")}
+            roof["limiters"] = {k: cap[k] for k in ("issue_slot_pct", "fp64_pipe_pct", "achieved_occupancy_pct", "ipc", "ncu_duration_us",
+                                                    "warp_instructions", "top_stalls") if k in cap}
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 reward window / f64 scalar physics", "data": "synthetic",
-            "config": cfg,
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 3 * 4,
-                    "d2h_bytes_per_step": n * (78 + 29 + 3) * 4 + n, "steps": e2e_steps,
-                    "call": "sdc_step_host (numpy actions in; obs, share_obs, rewards, dones out)"},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_BYTES_PER_LAUNCH if n == 65536 else None, "kernel": "k_step", "launch_ms_mean": k_ms,
-                         "launch_ms_max": float(ktimes[3]),                          "step_ms_median": float(np.median(step_ms)),
-                         "bytes_per_launch": B_ALG_STEADY * n, "peak_source": peak_src,
-                         "physical_frac": (TRAFFIC_BYTES_PER_LAUNCH / (k_ms / 1e3) / 1e9 / peak) if n == 65536 else None,
-                         "note": "algorithmic bytes are the fixed SURVEY 8d numerator; the kernel is incremental and latency / "
-                                 "issue bound, not HBM bound (physical_frac = ncu DRAM bytes per launch / launch time / peak)",
-                         "passes_last_step": [int(x) for x in pass_stats]},
-            "clocks": clocks, "env_error_flags": err,
+            "config": dict(cfg, settle_steps=args.settle, settle_s=round(t_settle, 2), numa=placement),
+            "value_core_outputs": value_core,
+            "e2e": {"value": e2e_compact, "unit": "env-steps/s", "h2d_bytes_per_step": n * 3 * 4,
+                    "d2h_bytes_per_step": n * (53 + 3) * 4 + n, "steps": e2e_steps,
+                    "call": "sdc_step_compact_host (numpy actions in; 53 unpadded observation floats, rewards, dones out; terminal rows of "
+                            "finished envs; pinned host buffers of the handle)"},
+            "e2e_padded": {"value": e2e_padded, "unit": "env-steps/s", "d2h_bytes_per_step": n * (78 + 29 + 3) * 4 + n,
+                           "call": "sdc_step_host (obs[N,3,26] + share_obs[N,29] + rewards + dones)"},
+            "e2e_vec_env": {"value": e2e_vec_views, "copies": e2e_vec_copy, "unit": "env-steps/s",
+                            "call": "CudaShareVecEnv.step (harl ShareVecEnv surface: obs, share_obs[N,3,29], rewards, dones, lazy infos, "
+                                    "avail); value: output_views=True, copies: fresh arrays like the reference"},
+            "gpu_launches": launches, "roofline": roof, "clocks": clocks, "env_error_flags": err,
         }
-        if not args.no_cpu and world >= 1:
+        if not args.no_cpu:
             line["cpu_baseline"] = cpu_arm(args.cpu_steps)
         print(json.dumps(line))
     if world > 1:

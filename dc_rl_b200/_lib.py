@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 MAX_RACK_CLASSES = 32
-N_AGENTS, OBS_DIM, SHARE_DIM, INFO_STRIDE = 3, 26, 29, 64
+N_AGENTS, OBS_DIM, SHARE_DIM, INFO_STRIDE, OBS_COMPACT = 3, 26, 29, 64, 53
 YEAR_STEPS, TRACE_PAD, HIST_CAP, N_METRICS = 35040, 64, 10000, 16
 LIST_CAP, TAIL_CAP = 128, 128
 HVAC_BINS = 4096          # sdc_core.h kListCap / kTailCap (state inspection only)
@@ -66,6 +66,14 @@ _PROTOS = {
     "sdc_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sdc_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "sdc_reset_host": (C.c_int, [_P, _P, _P, _P]),
+    "sdc_step_host_begin": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "sdc_step_host_end": (C.c_int, [_P]),
+    "sdc_step_compact": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "sdc_step_compact_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "sdc_step_compact_host_begin": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "sdc_host_buffers_compact": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    "sdc_expand_obs": (None, [_P, C.c_int64, _P, _P]),
+    "sdc_fetch_info": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "sdc_host_buffers": (C.c_int, [_P] + [C.POINTER(_P)] * 7),
     "sdc_metrics": (C.c_int, [_P, _P, C.c_int32]),
     "sdc_hvac_histogram": (C.c_int, [_P, _P, _P, C.c_int32]),

@@ -193,96 +193,99 @@ struct LsStats { double oldest, avg, norm_q, hist[5]; };
 // addressed by trace index: wrel[t] = dry bulb, wrel[win_len + t] = wet bulb at index t (wrel = window start - t0).
 struct Norms { double cmin, crng, tmin, trng; const double* wrel; };
 
-// Builds the three observations at trace index t. Sink: void operator()(int agent, int idx, float v).
-// Layouts: SURVEY.md A.6 / sustaindc_env.py:302-433.
-// All trace reads are issued first, in one straight-line batch, so that their memory latencies overlap: under the
-// HBM-saturating window scans of the other warps a dependent global read costs ~2 us (profiles/r01_summary.md).
-template <class Sink>
-SDC_HDN void build_obs(const State& S, const Tables& T, int env, int t, const LsStats& ls, double soc, const Norms& nm, Sink& sink) {
-    const LocTables& L = T.loc[S.loc_id[env]];
-    const double* wtemp = nm.wrel + t;
+// The observation features come in two independent halves (carbon intensity of the location, temperature of the env's
+// weather window); build_obs computes both in one thread, the look-ahead episode generation one half each on two threads.
+struct CiFeat { double x0, f[7]; };          // norm CI at t + the 7 features of sustaindc_env.py:266-300
+struct TempFeat { double nt0, nt1, f[6]; };  // norm temperature at t, t+1 + the 6 features of :366-384
+
+// Min-max normalisation by a multiplication with the reciprocal range (two divisions instead of 42): the quotient may
+// differ from the reference's in the last fp64 bit, which survives the fp32 cast of an observation with probability
+// ~2e-9 per value (the golden replays stay bit-identical).
+SDC_HDN void ci_features(const LocTables& L, int t, double cmin, double crng, CiFeat& out) {
     const int tp = t >= 16 ? t - 16 : 0;              // start of the 16-sample past window (empty before t = 16)
-#ifndef SDC_LAZY_OBS_LOADS
-    double ci_raw[25], wt_raw[17];
+    double ci_raw[25];
 #pragma unroll
     for (int i = 0; i < 16; ++i) ci_raw[i] = L.ci[tp + i];
 #pragma unroll
     for (int i = 0; i < 9; ++i) ci_raw[16 + i] = L.ci[t + i];
+    const double inv_crng = 1.0 / crng;
+    double x[9];                                       // x[0..8] = cur, fut[8]
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[i] = (ci_raw[16 + i] - cmin) * inv_crng;
+    double sm[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sm[i] = (((x[i] + x[i + 1]) + x[i + 2]) + x[i + 3]) / 4;
+    out.f[0] = ols_slope<6>(sm);
+    double p[17];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[i] = (ci_raw[i] - cmin) * inv_crng;
+    p[16] = x[0];
+    double smp[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) smp[i] = (((p[i] + p[i + 1]) + p[i + 2]) + p[i + 3]) / 4;
+    // empty past window at the start of the year -> zero slope
+    out.f[1] = t >= 16 ? ols_slope<14>(smp) : 0.0;
+    trend_features<8>(x[0], x + 1, out.f + 2);
+    out.x0 = x[0];
+}
+// wtemp: the env's dry-bulb window at trace index t (17 samples are read)
+SDC_HDN void temp_features(const double* wtemp, double tmin, double trng, TempFeat& out) {
+    double wt_raw[17];
 #pragma unroll
     for (int i = 0; i < 17; ++i) wt_raw[i] = wtemp[i];
-#else
-    const double* ci_raw = L.ci + tp;        // experiment: read where used
-    const double* wt_raw = wtemp;
-    const int ci_shift = t - tp - 16;        // 0 unless t < 16
-#define SDC_CI_NOW(i) L.ci[t + (i)]
-#endif
-    const double w = L.workload[t], w_next = L.workload[t + 1];
-    const int hq = t % 96;
-    const double cos_h = S.hour_cos[hq], sin_h = S.hour_sin[hq];
-
-    // Min-max normalisation by a multiplication with the reciprocal range (two divisions instead of 42): the quotient may
-    // differ from the reference's in the last fp64 bit, which survives the fp32 cast of an observation with probability
-    // ~2e-9 per value (the golden replays stay bit-identical).
-    const double inv_crng = 1.0 / nm.crng, inv_trng = 1.0 / nm.trng;
-    // carbon-intensity features: x[0..8] = cur, fut[8]; past[16]
-    double x[9];
+    const double inv_trng = 1.0 / trng;
+    double nt[17];                                     // nt[0..16] = normT[t..t+16]
 #pragma unroll
-#ifndef SDC_LAZY_OBS_LOADS
-    for (int i = 0; i < 9; ++i) x[i] = (ci_raw[16 + i] - nm.cmin) * inv_crng;
-#else
-    for (int i = 0; i < 9; ++i) x[i] = (SDC_CI_NOW(i) - nm.cmin) * inv_crng;
-    (void)ci_shift;
-#endif
-    double f_ci[7];
-    {
-        double sm[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) sm[i] = (((x[i] + x[i + 1]) + x[i + 2]) + x[i + 3]) / 4;
-        f_ci[0] = ols_slope<6>(sm);
-        double p[17];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) p[i] = (ci_raw[i] - nm.cmin) * inv_crng;
-        p[16] = x[0];
-        double smp[14];
-#pragma unroll
-        for (int i = 0; i < 14; ++i) smp[i] = (((p[i] + p[i + 1]) + p[i + 2]) + p[i + 3]) / 4;
-        // empty past window at the start of the year -> zero slope
-        f_ci[1] = t >= 16 ? ols_slope<14>(smp) : 0.0;
-        trend_features<8>(x[0], x + 1, f_ci + 2);
-    }
-    // temperature features: nt[0..16] = normT[t..t+16]
-    double nt[17];
-#pragma unroll
-    for (int i = 0; i < 17; ++i) nt[i] = (wt_raw[i] - nm.tmin) * inv_trng;
-    double f_t[6];
-    f_t[0] = ols_slope<17>(nt);
-    trend_features<16>(nt[0], nt + 1, f_t + 1);
-
+    for (int i = 0; i < 17; ++i) nt[i] = (wt_raw[i] - tmin) * inv_trng;
+    out.f[0] = ols_slope<17>(nt);
+    trend_features<16>(nt[0], nt + 1, out.f + 1);
+    out.nt0 = nt[0]; out.nt1 = nt[1];
+}
+// The three rows.  Sink: void operator()(int agent, int idx, float v).  Layouts: SURVEY.md A.6 / sustaindc_env.py:302-433.
+template <class Sink>
+SDC_HDN void emit_obs_rows(double cos_h, double sin_h, double w, double w_next, const CiFeat& ci, const TempFeat& tf, const LsStats& ls,
+                           double soc, Sink& sink) {
     // agent_ls [26]
     int k = 0;
-    sink(0, k++, (float)cos_h); sink(0, k++, (float)sin_h); sink(0, k++, (float)x[0]);
+    sink(0, k++, (float)cos_h); sink(0, k++, (float)sin_h); sink(0, k++, (float)ci.x0);
 #pragma unroll
-    for (int i = 0; i < 7; ++i) sink(0, k++, (float)f_ci[i]);
+    for (int i = 0; i < 7; ++i) sink(0, k++, (float)ci.f[i]);
     sink(0, k++, (float)ls.oldest); sink(0, k++, (float)ls.avg); sink(0, k++, (float)ls.norm_q);
-    sink(0, k++, (float)w); sink(0, k++, (float)nt[0]);
+    sink(0, k++, (float)w); sink(0, k++, (float)tf.nt0);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) sink(0, k++, (float)f_t[i]);
+    for (int i = 0; i < 6; ++i) sink(0, k++, (float)tf.f[i]);
 #pragma unroll
     for (int i = 0; i < 5; ++i) sink(0, k++, (float)ls.hist[i]);
     // agent_dc [14] (+ zero padding to 26)
     k = 0;
-    sink(1, k++, (float)cos_h); sink(1, k++, (float)sin_h); sink(1, k++, (float)x[0]);
+    sink(1, k++, (float)cos_h); sink(1, k++, (float)sin_h); sink(1, k++, (float)ci.x0);
 #pragma unroll
-    for (int i = 0; i < 7; ++i) sink(1, k++, (float)f_ci[i]);
-    sink(1, k++, (float)w); sink(1, k++, (float)w_next); sink(1, k++, (float)nt[0]); sink(1, k++, (float)nt[1]);
+    for (int i = 0; i < 7; ++i) sink(1, k++, (float)ci.f[i]);
+    sink(1, k++, (float)w); sink(1, k++, (float)w_next); sink(1, k++, (float)tf.nt0); sink(1, k++, (float)tf.nt1);
     for (; k < SDC_OBS_DIM; ++k) sink(1, k, 0.0f);
     // agent_bat [13]
     k = 0;
-    sink(2, k++, (float)cos_h); sink(2, k++, (float)sin_h); sink(2, k++, (float)x[0]);
+    sink(2, k++, (float)cos_h); sink(2, k++, (float)sin_h); sink(2, k++, (float)ci.x0);
 #pragma unroll
-    for (int i = 0; i < 7; ++i) sink(2, k++, (float)f_ci[i]);
-    sink(2, k++, (float)w); sink(2, k++, (float)nt[0]); sink(2, k++, (float)soc);
+    for (int i = 0; i < 7; ++i) sink(2, k++, (float)ci.f[i]);
+    sink(2, k++, (float)w); sink(2, k++, (float)tf.nt0); sink(2, k++, (float)soc);
     for (; k < SDC_OBS_DIM; ++k) sink(2, k, 0.0f);
+}
+
+// Builds the three observations at trace index t (one thread).
+// All trace reads are issued first, in one straight-line batch, so that their memory latencies overlap: a dependent
+// global read costs ~1-2 us under load (profiles/r01_summary.md).
+template <class Sink>
+SDC_HDN void build_obs(const State& S, const Tables& T, int env, int t, const LsStats& ls, double soc, const Norms& nm, Sink& sink) {
+    const LocTables& L = T.loc[S.loc_id[env]];
+    const double w = L.workload[t], w_next = L.workload[t + 1];
+    const int hq = t % 96;
+    const double cos_h = S.hour_cos[hq], sin_h = S.hour_sin[hq];
+    CiFeat ci;
+    TempFeat tf;
+    ci_features(L, t, nm.cmin, nm.crng, ci);
+    temp_features(nm.wrel + t, nm.tmin, nm.trng, tf);
+    emit_obs_rows(cos_h, sin_h, w, w_next, ci, tf, ls, soc, sink);
 }
 
 // ---- EnergyPlus-style electric chiller (envs/datacenter.py:356-429) ---------------------------
@@ -1170,7 +1173,7 @@ SDC_HD U4 env_random(uint64_t seed, uint32_t episode, uint32_t stream, uint32_t 
     U4 c; c.x = idx; c.y = episode; c.z = stream; c.w = 0x5DCB200u;
     return philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
-// Weather noise: the year-long random walk is cut into kNoiseThreads segments of kNoiseSeg samples; segment i draws its
+// Weather noise: the year-long random walk is cut into kNoiseSegs segments of kNoiseSeg samples; segment i draws its
 // normals from its own PCG32 stream (O'Neill 2014, XSH-RR 64/32), seeded by one Philox block keyed by (env seed, episode,
 // segment).  ~10 integer instructions per 32-bit draw instead of ~23 for Philox: the walk is 35 040 normals per episode,
 // a fifth of all instructions of a step when it ran on Philox alone.
@@ -1212,12 +1215,16 @@ SDC_HD void draw_episode_start(uint64_t seed, uint32_t episode, int day_lo, int 
     *hour = (int)(r.y % 24u);
     *roll = (int)(r.z % 14u);
 }
-constexpr int kNoiseThreads = 256;                        // segments of the year-long random walk
-constexpr int kNoiseSeg = 140;                            // even segment length, 256*140 >= 35040
+constexpr int kNoiseThreads = 256;                        // threads of an episode generation, one walk segment each
+constexpr int kNoiseSegs = kNoiseThreads;                 // segments of the year-long random walk (one PCG32 stream each)
+constexpr int kNoiseSeg = 140;                            // even segment length, 256 * 140 >= 35040
 
 // Buffers and knobs of one step launch (all device pointers; see sdc_step in include/sdc_b200.h).
 struct StepArgs {
     const int32_t* actions; float* obs; float* share; float* rew; uint8_t* done; float* info; float* term_obs;
+    // compact outputs (sdc_step_compact): the three unpadded rows back to back, [N][SDC_OBS_COMPACT]; obs / share / term_obs
+    // may then be null
+    float* obs_c; float* term_c;
     // this step's counters (ctr) and the next step's (ctr_next, zeroed by this launch):
     //   [0] unit tickets  [1] finished envs appended to reset_list  [2] units past the scalar phase
     //   [3] reset_list slots claimed by workers  [4..7] statistics: plain passes, refresh passes, by brackets, by tails
@@ -1237,8 +1244,12 @@ struct StepArgs {
     unsigned long long* hvac_hist;      // [SDC_HVAC_BINS] counts of positive HVAC power samples
     float hvac_bins_per_kw;             // SDC_HVAC_BINS / range
     unsigned long long* phase_clocks;   // optional [16]: summed per-warp clock64 deltas of the k_step phases (diagnostics)
+    unsigned long long* pass_total;     // [4] running totals of ctr[4..7] (window passes: plain, refresh, by brackets, by tails)
     int32_t unit_envs, blocks_per_sm;
 };
+
+// compact column c of [agent_ls 26 | agent_dc 14 | agent_bat 13] -> column of the zero-padded [3][26] row
+SDC_HD int compact_to_padded(int c) { return c < 40 ? c : c + 12; }
 
 // HARL shared observation (harl/envs/sustaindc/harlsustaindc_env.py:78-85): ls[0:26] | dc[11] | dc[13] |
 // last element of the zero-padded battery row (always 0.0).

@@ -185,8 +185,8 @@ struct PassShared {
     unsigned long long bar;                 // mbarrier of the bulk copy
     PassJob job;
     int fill[5];                            // slots handed out: lower band, upper band, collect list 0, collect list 1, hit list
-    int band_nb[2];                         // rebuilt bands: values beyond the fence, their sums about the new centre
-    double band_b1[2], band_b2[2];
+    int band_pn[kWarpsPerBlock];            // rebuilt bands: per-warp partials of the values beyond the fence (count, sums about
+    double band_p1[kWarpsPerBlock], band_p2[kWarpsPerBlock];   // the new centre); warps 0-3 lower band, 4-7 upper band
     float red_f[kWarpsPerBlock][4];         // s1, s2, ext0, ext1
     double red_d[kWarpsPerBlock][6];        // S1, S2, far sums
     int red_i[kWarpsPerBlock][6];           // cnt0, cnt1, below0, below1, far counts
@@ -211,23 +211,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// CTA-wide bitonic sort of buf[0..p2) (ascending), p2 a power of two <= 2 * blockDim.x.
-__device__ __forceinline__ void block_bitonic_sort(float* buf, int p2) {
-    for (int k = 2; k <= p2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < p2; i += kStepThreads) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const float x = buf[i], y = buf[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) { buf[i] = y; buf[ixj] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
 }
 
 // The pass itself (sdc_core.h, "reward normaliser").  SCAN_PLAIN: clipped moments of this step only.  SCAN_REFRESH:
@@ -322,34 +305,27 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
         ps.red_i[warp][4] = far_n0; ps.red_i[warp][5] = far_n1;
     }
     __syncthreads();                                                     // partials + all band / collect stores visible
-    if (refresh && J.tails && warp < 2 && ps.fill[0] <= sdc::kTailCap && ps.fill[1] <= sdc::kTailCap) {
-        // warp `warp` sorts band `warp` (bitonic over kTailCap slots in shared memory, warp-synchronous) and splits it at the
-        // requesting step's fence: count and sums about the new centre of the values beyond it
-        float* b = band_scr + warp * sdc::kTailCap;
-        const int cntb = ps.fill[warp];
-        for (int i = cntb + lane; i < sdc::kTailCap; i += 32) b[i] = SDC_INF_F;
-        __syncwarp();
-        for (int k = 2; k <= sdc::kTailCap; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = lane; i < sdc::kTailCap; i += 32) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const float x = b[i], y = b[ixj];
-                        const bool up = (i & k) == 0;
-                        if ((x > y) == up) { b[i] = y; b[ixj] = x; }
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        const double fence = warp == 0 ? J.lo64 : J.hi64;
+    // Rebuilt bands: rank sort (thread i places value i of its band: the rank is the number of smaller values plus equal ones
+    // before it; broadcast reads of shared memory, no barrier) into the free hit list, 128 threads per band, and the split
+    // at the requesting step's fence: count and sums about the new centre of the values beyond it (per-warp partials, summed
+    // in a fixed order by the committing warp: bit-reproducible whatever CTA runs the pass).
+    float* band_sorted = hits;                                           // [2][kTailCap]; the parked hits were consumed above
+    static_assert(kStepThreads == 2 * sdc::kTailCap, "one thread per band slot");
+    if (refresh && J.tails) {
+        const int sd = tid / sdc::kTailCap, me = tid - sd * sdc::kTailCap;
+        const int cntb = ps.fill[sd];
         int nbz = 0; double z1 = 0.0, z2 = 0.0;
-        for (int i = lane; i < cntb; i += 32) {
-            const float x = b[i];
-            if (warp == 0 ? (double)x < fence : (double)x > fence) { const double y = (double)x - c0; nbz += 1; z1 += y; z2 = fma(y, y, z2); }
+        if (ps.fill[0] <= sdc::kTailCap && ps.fill[1] <= sdc::kTailCap && me < cntb) {
+            const float* b = band_scr + sd * sdc::kTailCap;
+            const float x = b[me];
+            int r = 0;
+#pragma unroll 4
+            for (int i = 0; i < cntb; ++i) { const float y = b[i]; r += (y < x) | ((y == x) & (i < me)); }
+            band_sorted[sd * sdc::kTailCap + r] = x;
+            if (sd == 0 ? (double)x < J.lo64 : (double)x > J.hi64) { const double y = (double)x - c0; nbz = 1; z1 = y; z2 = y * y; }
         }
         nbz = warp_sum(nbz); z1 = warp_sum(z1); z2 = warp_sum(z2);
-        if (lane == 0) { ps.band_nb[warp] = nbz; ps.band_b1[warp] = z1; ps.band_b2[warp] = z2; }
+        if (lane == 0) { ps.band_pn[warp] = nbz; ps.band_p1[warp] = z1; ps.band_p2[warp] = z2; }
     }
     sdc::RefreshRaw raw;
     sdc::ScanResult rs;
@@ -375,22 +351,24 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
         raw.agg_s1[0] = d[2]; raw.agg_s2[0] = d[3]; raw.agg_s1[1] = d[4]; raw.agg_s2[1] = d[5];
         raw.n_tail[0] = ps.fill[0]; raw.n_tail[1] = ps.fill[1]; raw.c[0] = ps.fill[2]; raw.c[1] = ps.fill[3];
     }
-    // (band_nb / band_b1 / band_b2 are read by warp 0 after the barrier that follows the bracket sorts)
+    // (the band partials are read by warp 0 after the barrier that follows the bracket sorts)
     if (refresh) {
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {                                    // uniform across the CTA
             const int c = raw.c[j];
             if (c >= 1 && c <= sdc::kCollectCap) {
-                // bitonic sort in place (padded to a power of two), then copied out: ~350 instructions and 36-45 barriers per
-                // thread; a rank sort (one pass over the c values per thread) was the single most executed line of the kernel
-                float* buf = scr + j * sdc::kCollectCap;
+                // rank sort of the collected values (typically ~250): every thread places up to two of them; one pass over
+                // the c values per element with broadcast reads and no barrier (a bitonic network needs 36-45 CTA barriers,
+                // which is what a pass's latency was made of)
+                const float* buf = scr + j * sdc::kCollectCap;
                 float* out = win + j * sdc::kCollectCap;              // the staged window is no longer needed
-                int p2 = 2;
-                while (p2 < c) p2 <<= 1;
-                for (int i = c + tid; i < p2; i += kStepThreads) buf[i] = SDC_INF_F;
-                __syncthreads();
-                block_bitonic_sort(buf, p2);
-                for (int i = tid; i < c; i += kStepThreads) out[i] = buf[i];
+                for (int me = tid; me < c; me += kStepThreads) {
+                    const float x = buf[me];
+                    int r = 0;
+#pragma unroll 4
+                    for (int i = 0; i < c; ++i) { const float y = buf[i]; r += (y < x) | ((y == x) & (i < me)); }
+                    out[r] = x;
+                }
             }
         }
         __syncthreads();
@@ -403,8 +381,14 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
             Ql.lst[0] = S.qlist + (size_t)env * 2 * sdc::kListCap; Ql.lst[1] = Ql.lst[0] + sdc::kListCap;
             Ql.a[0] = J.q_a[0]; Ql.a[1] = J.q_a[1]; Ql.m[0] = J.q_m[0]; Ql.m[1] = J.q_m[1];
             const float* sorted[2] = {win, win + sdc::kCollectCap};
-            const float* bands[2] = {band_scr, band_scr + sdc::kTailCap};
-            for (int sd = 0; sd < 2; ++sd) { raw.band_nb[sd] = ps.band_nb[sd]; raw.band_b1[sd] = ps.band_b1[sd]; raw.band_b2[sd] = ps.band_b2[sd]; }
+            const float* bands[2] = {band_sorted, band_sorted + sdc::kTailCap};
+            for (int sd = 0; sd < 2; ++sd) {
+                raw.band_nb[sd] = 0; raw.band_b1[sd] = raw.band_b2[sd] = 0.0;
+                for (int w = 0; w < kWarpsPerBlock / 2; ++w) {
+                    const int q = sd * (kWarpsPerBlock / 2) + w;
+                    raw.band_nb[sd] += ps.band_pn[q]; raw.band_b1[sd] += ps.band_p1[q]; raw.band_b2[sd] += ps.band_p2[q];
+                }
+            }
             sdc::refresh_commit(S, env, rl, raw, sorted, bands, Ql, rs, lane, 32);
             // cursors of the re-centred brackets (a maintenance pass has no owner lane that would store them)
             if (lane < 2 && (rs.recentred & (1 << lane))) { S.q_a[env * 2 + lane] = rs.new_a[lane]; S.q_m[env * 2 + lane] = rs.new_m[lane]; }
@@ -446,6 +430,17 @@ __device__ __forceinline__ double block_minmax(double v, bool is_min, double* re
     return t;
 }
 
+struct OutPtrs { float* obs; float* share; float* obs_c; };       // any of them may be null
+// One env's observation rows from its zero-padded [3][26] row: padded obs, HARL shared row, compact row.
+__device__ __forceinline__ void store_env_rows(const float* row, int env, const OutPtrs& o, int t, int n_thr) {
+    if (o.obs) for (int k = t; k < kObsRow; k += n_thr) o.obs[(size_t)env * kObsRow + k] = row[k];
+    if (o.share) for (int k = t; k < SDC_SHARE_DIM; k += n_thr) {
+        const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
+        o.share[(size_t)env * SDC_SHARE_DIM + k] = row[src];
+    }
+    if (o.obs_c) for (int k = t; k < SDC_OBS_COMPACT; k += n_thr) o.obs_c[(size_t)env * SDC_OBS_COMPACT + k] = row[sdc::compact_to_padded(k)];
+}
+
 struct RowSink {
     float* row;
     __device__ __forceinline__ void operator()(int agent, int idx, float v) { row[agent * SDC_OBS_DIM + idx] = v; }
@@ -453,9 +448,11 @@ struct RowSink {
 
 struct ResetShared {
     double red[kResetThreads / 32];
-    double seg_off[kResetThreads];
+    double seg_off[sdc::kNoiseSegs];
     int start[3];
     float row[kObsRow];
+    sdc::CiFeat ci;                 // the two halves of a staged reset observation (pregen_one_env)
+    sdc::TempFeat tf;
 };
 
 constexpr int kNormWindow = 2880;                 // 30 days of quarter-hours (utils/managers.py:435,606)
@@ -483,6 +480,7 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
     const int k_keep = max(k_norm, k_win);
     // pass 1: this thread's segment of the walk (utils/managers.py:45-46), normals from the segment's own PCG32 stream.
     // Walk sample j lands at trace index (j + 96 roll) mod n, i.e. at window position k = j + c_lo (c_hi past the wrap).
+    // (Two interleaved half-segments per thread were measured: 7 % slower -- registers, not latency, bound this loop.)
     double run = 0.0, sum_run = 0.0, sum_run2 = 0.0;
     const int j0 = tid * sdc::kNoiseSeg;
     const int cnt = max(0, min(sdc::kNoiseSeg, n - j0));    // even for every thread (n and the segment length are even)
@@ -504,15 +502,25 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
     }
     sh.seg_off[tid] = run;
     __syncthreads();
-    if (tid == 0) {                           // serial exclusive prefix, same order as the host statement
-        double acc = 0.0;
-        for (int k = 0; k < kResetThreads; ++k) { const double s = sh.seg_off[k]; sh.seg_off[k] = acc; acc += s; }
+    if (tid < 32) {                           // exclusive prefix over the segment totals: 8 per lane + a warp scan
+        constexpr int kPer = sdc::kNoiseSegs / 32;
+        double v[kPer], tot = 0.0;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) { v[i] = sh.seg_off[tid * kPer + i]; tot += v[i]; }
+        double incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double up = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += up; }
+        double acc = incl - tot;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) { sh.seg_off[tid * kPer + i] = acc; acc += v[i]; }
     }
     __syncthreads();
-    const double off = sh.seg_off[tid];
     // walk_j = off + run_j  ->  sums of w and w^2 from the partial sums
-    const double sw = block_sum((double)cnt * off + sum_run, sh.red);
-    const double sw2 = block_sum((double)cnt * off * off + 2.0 * off * sum_run + sum_run2, sh.red);
+    const double off = sh.seg_off[tid];
+    const double pw = (double)cnt * off + sum_run;
+    const double pw2 = (double)cnt * off * off + 2.0 * off * sum_run + sum_run2;
+    const double sw = block_sum(pw, sh.red);
+    const double sw2 = block_sum(pw2, sh.red);
     const double mean = sw / n;
     const double scale = 0.75 / sqrt(sw2 / n - mean * mean);              // managers.py:46-48
     // emit: roll, clip, window, 30-day min/max (managers.py:598-608), one window position per thread and trip
@@ -521,7 +529,7 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
     for (int k = tid; k < max(k_keep, S.win_len); k += kResetThreads) {
         if (k < k_keep) {
             int j = t0 + k - 96 * roll; if (j < 0) j += n;
-            const double noise = (sh.seg_off[j / sdc::kNoiseSeg] + runbuf[k]) * scale;
+            const double noise = (sh.seg_off[j / sdc::kNoiseSeg] + runbuf[k]) * scale;     // segment offset + position inside it
             const double vt = fmin(fmax(L.temp_base[j] + noise, 0.0), 45.0);
             if (k < k_norm) { tmin = fmin(tmin, vt); tmax = fmax(tmax, vt); }
             if (k < k_win) { wt[k] = vt; ww[k] = fmin(fmax(L.wetb_base[j] + noise, 0.0), 45.0); }
@@ -542,10 +550,24 @@ __device__ __forceinline__ void pregen_one_env(const sdc::State& S, int env, dou
     double* wt = sdc::weather_pend(S, env);
     generate_episode(S, env, wt, wt + S.win_len, S.pend_tmin + env, S.pend_tmax + env, runbuf, sh);
     __syncthreads();                                    // window, range and start are in place (global / shared memory)
+    // the reset observation (sustaindc_env.py:488-494): its two halves on two warps, then one thread writes the rows
+    const int t0 = sh.start[0] * 96 + sh.start[1] * 4;
+    const sdc::LocTables& L = S.loc[S.loc_id[env]];
+    if (threadIdx.x == 0) {
+        const double cmin = L.ci_min30[t0];
+        sdc::ci_features(L, t0, cmin, L.ci_max30[t0] - cmin, sh.ci);
+    } else if (threadIdx.x == 32) {
+        const double tmin = S.pend_tmin[env];
+        sdc::temp_features(wt, tmin, S.pend_tmax[env] - tmin, sh.tf);
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         S.pend_day[env] = sh.start[0]; S.pend_hour[env] = sh.start[1];
+        sdc::LsStats ls;
+        ls.oldest = 0.0; ls.avg = 0.0; ls.norm_q = 0.0;
+        for (int i = 0; i < 5; ++i) ls.hist[i] = 0.0;
         RowSink sink{S.pend_obs + (size_t)env * kObsRow};
-        sdc::reset_observation(S, env, sh.start[0] * 96 + sh.start[1] * 4, wt, S.pend_tmin[env], S.pend_tmax[env], sink);
+        sdc::emit_obs_rows(S.hour_cos[t0 % 96], S.hour_sin[t0 % 96], L.workload[t0], L.workload[t0 + 1], sh.ci, sh.tf, ls, 0.0, sink);
         __threadfence();
         S.pend_valid[env] = 3;
     }
@@ -553,7 +575,7 @@ __device__ __forceinline__ void pregen_one_env(const sdc::State& S, int env, dou
 
 // Episode reset of one env by one CTA (k_reset, and the worker jobs of k_step for envs whose next episode was not staged
 // with its observation: first resets, host-staged replays).  `runbuf` = run_buf_bytes(S) of shared memory.
-__device__ __forceinline__ void reset_one_env(const sdc::State& S, int env, float* obs, float* share, double* runbuf, ResetShared& sh) {
+__device__ __forceinline__ void reset_one_env(const sdc::State& S, int env, const OutPtrs& out, double* runbuf, ResetShared& sh) {
     const int tid = threadIdx.x;
     const int staged = S.pend_valid[env];
     double* wt = sdc::weather_pend(S, env);             // the next episode's window: staged, or generated right here
@@ -582,12 +604,7 @@ __device__ __forceinline__ void reset_one_env(const sdc::State& S, int env, floa
         }
     }
     __syncthreads();
-    for (int k = tid; k < kObsRow; k += kResetThreads) obs[(size_t)env * kObsRow + k] = sh.row[k];
-    if (tid < SDC_SHARE_DIM) {
-        const int k = tid;
-        const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
-        share[(size_t)env * SDC_SHARE_DIM + k] = sh.row[src];
-    }
+    store_env_rows(sh.row, env, out, tid, kResetThreads);
 }
 
 // =================================================================================================
@@ -598,7 +615,8 @@ __global__ void __launch_bounds__(kResetThreads) k_reset(const sdc::State S, con
     extern __shared__ double runbuf[];              // [run_buf_doubles] walk values inside the episode window / 30-day slice
     __shared__ ResetShared sh;
     const int total = *count;
-    for (int i = blockIdx.x; i < total; i += gridDim.x) reset_one_env(S, list[i], obs, share, runbuf, sh);
+    const OutPtrs out{obs, share, nullptr};
+    for (int i = blockIdx.x; i < total; i += gridDim.x) reset_one_env(S, list[i], out, runbuf, sh);
 }
 
 // =================================================================================================
@@ -794,6 +812,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                 if (slow) {          // statistics only
                     atomicAdd(a.ctr + 4, __popc(slow) - (int)n_refresh); atomicAdd(a.ctr + 5, (int)n_refresh);
                     atomicAdd(a.ctr + 6, (int)n_lists); atomicAdd(a.ctr + 7, (int)n_tails);
+                    atomicAdd(a.pass_total + 0, (unsigned long long)(__popc(slow) - (int)n_refresh)); atomicAdd(a.pass_total + 1, (unsigned long long)n_refresh);
+                    atomicAdd(a.pass_total + 2, (unsigned long long)n_lists); atomicAdd(a.pass_total + 3, (unsigned long long)n_tails);
                 }
             }
         }
@@ -868,26 +888,49 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
             __syncwarp();
             if (have_unit) {
                 const int n_here = min(U, N - env0);
-                const int total = n_here * kObsRow;
-                float4* dst4 = reinterpret_cast<float4*>(a.obs + (size_t)env0 * kObsRow);      // env0 is a multiple of 8
-                for (int i = lane; i < total / 4; i += 32) {
-                    float v[4];
+                if (a.obs) {
+                    const int total = n_here * kObsRow;
+                    float4* dst4 = reinterpret_cast<float4*>(a.obs + (size_t)env0 * kObsRow);      // env0 is a multiple of 8
+                    for (int i = lane; i < total / 4; i += 32) {
+                        float v[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { const int f = 4 * i + q; const int e = f / kObsRow; v[q] = tile[e * kTileStride + (f - e * kObsRow)]; }
-                    dst4[i] = make_float4(v[0], v[1], v[2], v[3]);
+                        for (int q = 0; q < 4; ++q) { const int f = 4 * i + q; const int e = f / kObsRow; v[q] = tile[e * kTileStride + (f - e * kObsRow)]; }
+                        dst4[i] = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                    for (int f = (total & ~3) + lane; f < total; f += 32) { const int e = f / kObsRow; a.obs[(size_t)env0 * kObsRow + f] = tile[e * kTileStride + (f - e * kObsRow)]; }
                 }
-                for (int f = (total & ~3) + lane; f < total; f += 32) { const int e = f / kObsRow; a.obs[(size_t)env0 * kObsRow + f] = tile[e * kTileStride + (f - e * kObsRow)]; }
-                float* dsh = a.share + (size_t)env0 * SDC_SHARE_DIM;
-                for (int f = lane; f < n_here * SDC_SHARE_DIM; f += 32) {
-                    const int e = f / SDC_SHARE_DIM, k = f - e * SDC_SHARE_DIM;
-                    const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
-                    dsh[f] = tile[e * kTileStride + src];
+                if (a.share) {
+                    float* dsh = a.share + (size_t)env0 * SDC_SHARE_DIM;
+                    for (int f = lane; f < n_here * SDC_SHARE_DIM; f += 32) {
+                        const int e = f / SDC_SHARE_DIM, k = f - e * SDC_SHARE_DIM;
+                        const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
+                        dsh[f] = tile[e * kTileStride + src];
+                    }
+                }
+                if (a.obs_c) {
+                    // compact rows: 53 floats per env, no padding, no shared row -- half the bytes of obs + share, which is what a
+                    // host caller pays for over PCIe
+                    const int total = n_here * SDC_OBS_COMPACT;
+                    float4* dst4 = reinterpret_cast<float4*>(a.obs_c + (size_t)env0 * SDC_OBS_COMPACT);   // env0 * 53 * 4 B: 16-byte aligned for env0 % 4 == 0
+                    for (int i = lane; i < total / 4; i += 32) {
+                        float v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int f = 4 * i + q; const int e = f / SDC_OBS_COMPACT;
+                            v[q] = tile[e * kTileStride + sdc::compact_to_padded(f - e * SDC_OBS_COMPACT)];
+                        }
+                        dst4[i] = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                    for (int f = (total & ~3) + lane; f < total; f += 32) {
+                        const int e = f / SDC_OBS_COMPACT;
+                        a.obs_c[(size_t)env0 * SDC_OBS_COMPACT + f] = tile[e * kTileStride + sdc::compact_to_padded(f - e * SDC_OBS_COMPACT)];
+                    }
                 }
                 unsigned fin = __ballot_sync(0xffffffffu, finished != 0);
-                while (fin && a.term_obs) {
+                while (fin && (a.term_obs || a.term_c)) {
                     const int l = __ffs(fin) - 1;
                     fin &= fin - 1;
-                    for (int k = lane; k < kObsRow; k += 32) a.term_obs[(size_t)(env0 + l) * kObsRow + k] = tile[l * kTileStride + k];
+                    store_env_rows(tile + l * kTileStride, env0 + l, OutPtrs{a.term_obs, nullptr, a.term_c}, lane, 32);
                 }
             }
         }
@@ -949,12 +992,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                 const int e = env0 + l;
                 uint4* ring = reinterpret_cast<uint4*>(S.ls_ring + (size_t)e * (S.ls_mask + 1));
                 for (int k = lane; k < (S.ls_mask + 1) / 16; k += 32) ring[k] = make_uint4(0u, 0u, 0u, 0u);
-                const float* po = S.pend_obs + (size_t)e * kObsRow;
-                for (int k = lane; k < kObsRow; k += 32) a.obs[(size_t)e * kObsRow + k] = po[k];
-                if (lane < SDC_SHARE_DIM) {
-                    const int src = lane < 26 ? lane : (lane == 26 ? SDC_OBS_DIM + 11 : (lane == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
-                    a.share[(size_t)e * SDC_SHARE_DIM + lane] = po[src];
-                }
+                store_env_rows(S.pend_obs + (size_t)e * kObsRow, e, OutPtrs{a.obs, a.share, a.obs_c}, lane, 32);
                 if (lane == 0) {
                     S.t_min[e] = S.pend_tmin[e]; S.t_max[e] = S.pend_tmax[e];
                     S.cur_buf[e] ^= 1;
@@ -1037,7 +1075,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
             const long long tw0 = clock64();
             if (kind == 1) {
                 __threadfence();
-                reset_one_env(S, env, a.obs, a.share, runbuf, rsh);
+                reset_one_env(S, env, OutPtrs{a.obs, a.share, a.obs_c}, runbuf, rsh);
                 __syncthreads();
             } else if (kind == 2) {
                 const int* src = reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(a.pass_jobs) + (size_t)env * sdc::kPassJobBytes);
@@ -1128,6 +1166,7 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     const size_t tile_floats = (size_t)kWarpsPerBlock * 32 * kTileStride;
     size_t smem_floats = pass_floats > tile_floats ? pass_floats : tile_floats;
     const int hit_cap = (int)(smem_floats - pass_floats);
+    if (hit_cap < 2 * sdc::kTailCap) return "k_step: shared memory layout leaves no room for the sorted bands";
     size_t smem = smem_floats * sizeof(float);
     if (smem < run_buf_bytes(S)) smem = run_buf_bytes(S);                              // reset workers reuse the region
     // shared-memory copy of the location / dc parameter tables: only what this handle needs

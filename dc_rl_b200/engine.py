@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import INFO_STRIDE, N_AGENTS, N_METRICS, OBS_DIM, SHARE_DIM
+from ._lib import INFO_STRIDE, N_AGENTS, N_METRICS, OBS_COMPACT, OBS_DIM, SHARE_DIM
 from .dc_config import start_day_range
 from .traces import hour_table
 
@@ -22,7 +22,7 @@ _STATE_DTYPES = {
     "dc_scale": np.int32, "dc_last": np.int8, "bat_load": np.float64, "hist": np.float32, "hist_ref": np.float64, "hist_len": np.int32,
     "hist_head": np.int32, "phase_clocks": np.uint64, "qlist": np.float32, "q_a": np.int32, "q_m": np.int32, "err": np.int32,
     "mom_s1": np.float64, "mom_s2": np.float64, "mom_c0": np.float64, "tails": np.float32, "tail_n": np.int32, "tail_nb": np.int32, "tail_bs": np.float64,
-    "tail_thr": np.float32, "agg_n": np.int32, "agg_s": np.float64, "fast_cfg": np.uint32, "counters": np.int32, "pass_stats": np.int32,
+    "tail_thr": np.float32, "agg_n": np.int32, "agg_s": np.float64, "fast_cfg": np.uint32, "counters": np.int32, "pass_stats": np.int32, "pass_total": np.uint64,
     "pend_valid": np.uint8, "pend_weather": np.float64, "cur_buf": np.uint8, "pend_obs": np.float32, "metrics": np.float64, "hvac_hist": np.uint64,
 }
 
@@ -160,6 +160,8 @@ class Engine:
             n = self.n_envs
             p = [C.c_void_p() for _ in range(7)]
             self._check(self.lib.sdc_host_buffers(self._h, *[C.byref(x) for x in p]))
+            q = [C.c_void_p() for _ in range(2)]
+            self._check(self.lib.sdc_host_buffers_compact(self._h, *[C.byref(x) for x in q]))
 
             def view(ptr, shape, ctype, dtype):
                 count = int(np.prod(shape))
@@ -169,7 +171,9 @@ class Engine:
                             share=view(p[2], (n, SHARE_DIM), C.c_float, np.float32),
                             rew=view(p[3], (n, N_AGENTS), C.c_float, np.float32), done=view(p[4], (n,), C.c_uint8, np.uint8),
                             info=view(p[5], (INFO_STRIDE, n), C.c_float, np.float32),
-                            term=view(p[6], (n, N_AGENTS, OBS_DIM), C.c_float, np.float32))
+                            term=view(p[6], (n, N_AGENTS, OBS_DIM), C.c_float, np.float32),
+                            obs_c=view(q[0], (n, OBS_COMPACT), C.c_float, np.float32),
+                            term_c=view(q[1], (n, OBS_COMPACT), C.c_float, np.float32))
         return self._hb
 
     def reset_host(self, mask=None):
@@ -178,15 +182,57 @@ class Engine:
         self._check(self.lib.sdc_reset_host(self._h, _ptr(m), _ptr(b["obs"]), _ptr(b["share"])))
         return b["obs"], b["share"]
 
-    def step_host(self, actions, want_info=True, want_term=True):
-        """actions int32 [N,3] -> (obs[N,3,26], share[N,29], rew[N,3], done[N], info[64,N] | None, term_obs | None).
-        The returned arrays are reused by the next call."""
+    def step_host_begin(self, actions, want_info=True, want_term=True):
+        """First half of step_host (ShareVecEnv.step_async): copies and the step are enqueued, the call returns."""
         b = self._host_buffers()
         a = b["actions"]
         a[...] = np.asarray(actions).reshape(self.n_envs, N_AGENTS)       # the one host copy: caller's actions -> pinned
-        self._check(self.lib.sdc_step_host(self._h, _ptr(a), _ptr(b["obs"]), _ptr(b["share"]), _ptr(b["rew"]), _ptr(b["done"]),
-                                           _ptr(b["info"]) if want_info else None, _ptr(b["term"]) if want_term else None))
+        self._pending = (want_info, want_term)
+        self._check(self.lib.sdc_step_host_begin(self._h, _ptr(a), _ptr(b["obs"]), _ptr(b["share"]), _ptr(b["rew"]), _ptr(b["done"]),
+                                                 _ptr(b["info"]) if want_info else None, _ptr(b["term"]) if want_term else None))
+
+    def step_host_end(self):
+        b = self._host_buffers()
+        want_info, want_term = self._pending
+        self._check(self.lib.sdc_step_host_end(self._h))
+        self.host_step_id = getattr(self, "host_step_id", 0) + 1
         return b["obs"], b["share"], b["rew"], b["done"], (b["info"] if want_info else None), (b["term"] if want_term else None)
+
+    def step_host(self, actions, want_info=True, want_term=True):
+        """actions int32 [N,3] -> (obs[N,3,26], share[N,29], rew[N,3], done[N], info[64,N] | None, term_obs | None).
+        The returned arrays are views of the handle's pinned buffers, reused by the next call.  term_obs rows are valid
+        for the envs that finished in this step."""
+        self.step_host_begin(actions, want_info, want_term)
+        return self.step_host_end()
+
+    def step_compact_host(self, actions, want_info=False, want_term=True):
+        """Compact host call: (obs53[N,53], rew[N,3], done[N], info | None, term53[N,53] | None) -- the three unpadded
+        observation rows back to back; `expand_obs` rebuilds the padded rows and the shared observation."""
+        b = self._host_buffers()
+        a = b["actions"]
+        a[...] = np.asarray(actions).reshape(self.n_envs, N_AGENTS)
+        self._check(self.lib.sdc_step_compact_host(self._h, _ptr(a), _ptr(b["obs_c"]), _ptr(b["rew"]), _ptr(b["done"]),
+                                                   _ptr(b["info"]) if want_info else None, _ptr(b["term_c"]) if want_term else None))
+        self.host_step_id = getattr(self, "host_step_id", 0) + 1
+        return b["obs_c"], b["rew"], b["done"], (b["info"] if want_info else None), (b["term_c"] if want_term else None)
+
+    def step_compact_device(self, actions, obs53, rew, done, info=None, term53=None, stream=None):
+        self._check(self.lib.sdc_step_compact(self._h, _ptr(actions), _ptr(obs53), _ptr(rew), _ptr(done), _ptr(info), _ptr(term53),
+                                              _ptr(stream)))
+
+    def expand_obs(self, obs53, want_share=True):
+        """Host utility: compact rows -> (obs[n,3,26] zero padded, share[n,29] | None)."""
+        c = np.ascontiguousarray(obs53, np.float32).reshape(-1, OBS_COMPACT)
+        obs = np.empty((len(c), N_AGENTS, OBS_DIM), np.float32)
+        share = np.empty((len(c), SHARE_DIM), np.float32) if want_share else None
+        self.lib.sdc_expand_obs(_ptr(c), len(c), _ptr(obs), _ptr(share))
+        return obs, share
+
+    def fetch_info(self, first_col=0, n_cols=INFO_STRIDE):
+        """Columns of the LAST host step's info table, [n_cols, N] (needs set_tuning(lazy_info=1) or want_info)."""
+        out = np.empty((n_cols, self.n_envs), np.float32)
+        self._check(self.lib.sdc_fetch_info(self._h, int(first_col), int(n_cols), _ptr(out)))
+        return out
 
     # ---- metrics / state -----------------------------------------------------------------------
     def metrics(self, clear=False):
@@ -223,7 +269,7 @@ class Engine:
             out = np.zeros(16, dt)
         elif name == "counters":
             out = np.zeros(64, dt)
-        elif name == "pass_stats":
+        elif name in ("pass_stats", "pass_total"):
             out = np.zeros(4, dt)
         elif name in ("metrics", "hvac_hist"):
             out = np.zeros(_lib.HVAC_BINS if name == "hvac_hist" else N_METRICS, dt)
@@ -233,7 +279,7 @@ class Engine:
             out = np.zeros(n * per_env, dt)
         got = self._check(self.lib.sdc_read_state(self._h, name.encode(), _ptr(out), out.nbytes))
         out = out[:got // dt.itemsize]
-        if name in ("phase_clocks", "counters", "pass_stats", "metrics", "hvac_hist"):
+        if name in ("phase_clocks", "counters", "pass_stats", "pass_total", "metrics", "hvac_hist"):
             return out
         if name == "tails":
             return out.reshape(n, 2, _lib.TAIL_CAP)              # [env][side][slot], each band sorted ascending

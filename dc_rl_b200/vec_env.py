@@ -144,16 +144,26 @@ _VECTOR_KEYS = (info_layout.INFO_HIST_KEY, info_layout.INFO_FORECAST_KEY, "bat_a
 
 
 class InfoBatch:
-    """``infos`` of one vec-env step: ``len(infos) == N``, ``infos[i][agent]`` is an InfoRow.  Backed by one
-    [64, N] float table copied from the device; nothing per-env is materialised until it is indexed."""
+    """``infos`` of one vec-env step: ``len(infos) == N``, ``infos[i][agent]`` is an InfoRow.  Backed by the step's
+    [64, N] float table, which stays ON THE DEVICE until something is read: `column(key)` copies one column (what a logger
+    needs: a dozen columns, not 16 MB per step), indexing a row copies the table once.  Valid until the env's next step."""
 
-    def __init__(self, table, extras):
-        self.table = table                      # [INFO_STRIDE, N] float32 (a copy owned by this object)
+    def __init__(self, table, extras, n_envs=None, fetch=None):
+        self._table = table                     # [INFO_STRIDE, N] float32 (owned), or None while it is still on the device
+        self._fetch = fetch                     # fetch(first_col, n_cols) -> [n_cols, N]
+        self._n = int(n_envs if n_envs is not None else table.shape[1])
         self._extras = extras                   # {env index: dict of extra keys for agent 0}
         self._rows = {}
+        self._cols = {}
+
+    @property
+    def table(self):
+        if self._table is None:
+            self._table = self._fetch(0, info_layout.INFO_K_USED)
+        return self._table
 
     def __len__(self):
-        return self.table.shape[1]
+        return self._n
 
     def __getitem__(self, i):
         if isinstance(i, slice):
@@ -173,7 +183,12 @@ class InfoBatch:
 
     def column(self, key):
         """Vectorised access: one info key for all envs (fast path for loggers)."""
-        return self.table[info_layout.COL[key]]
+        col = info_layout.COL[key]
+        if self._table is not None:
+            return self._table[col]
+        if col not in self._cols:
+            self._cols[col] = self._fetch(col, 1)[0]
+        return self._cols[col]
 
 
 def _cyclic(value, index):
@@ -194,13 +209,24 @@ class CudaShareVecEnv:
     Dead keys of the reference (weather_file, cintensity_file, flexible_load, individual_reward_weight, max_bat_cap_Mw,
     evaluation) are accepted and ignored, as there."""
 
-    def __init__(self, env_args, n_envs, seed=0, months=None, seeds=None, device=0, lib=None, first_env_id=0):
+    def __init__(self, env_args, n_envs, seed=0, months=None, seeds=None, device=0, lib=None, first_env_id=0, engine=None):
+        """engine: wrap an existing `Engine` (its envs, traces and sizing) instead of building one from env_args."""
         args = dict(env_args)
         self.env_args = args
         self.num_envs = int(n_envs)
         self.n_agents = N_AGENTS
         self.nonoverlapping = bool(args.get("nonoverlapping_shared_obs_space", False))
         self.observation_space, self.share_observation_space, self.action_space = make_spaces(self.nonoverlapping)
+        self.closed = False
+        self._avail = np.ones((self.num_envs, N_AGENTS, 3), np.float32)
+        self.lazy_info = args.get("info", "lazy") == "lazy"
+        self.views = bool(args.get("output_views", False))
+        if engine is not None:
+            if engine.n_envs != self.num_envs:
+                raise ValueError("engine holds %d envs, not %d" % (engine.n_envs, self.num_envs))
+            self.engine = engine
+            engine.set_tuning(lazy_info=int(self.lazy_info))
+            return
         ids = np.arange(first_env_id, first_env_id + self.num_envs)
         location = args.get("location", "ny")
         n_loc_cycle = len(location) if isinstance(location, (list, tuple)) else 1
@@ -234,47 +260,66 @@ class CudaShareVecEnv:
             seeds = (int(seed) + ids * 1000).astype(np.uint64)   # envs_tools.py:67
         self.engine = Engine(self.num_envs, traces, params, loc_id=loc_id, cfg_id=cfg_id, months=months, seeds=seeds,
                              days_per_episode=int(args.get("days_per_episode", 7)), device=device, lib=lib)
+        # additive keys: "info": "lazy" (default; the info table stays on the device until read) | "eager";
+        # "output_views": True returns views of the pinned I/O buffers, valid until the next step, instead of fresh copies
+        self.engine.set_tuning(lazy_info=int(self.lazy_info))
         rewards = [args.get(key, "default_%s" % key) for key in ("ls_reward", "dc_reward", "bat_reward")]
         if rewards != ["default_ls_reward", "default_dc_reward", "default_bat_reward"]:
             self.engine.set_reward_methods(*rewards)              # sustaindc_env.py:137-144
-        self.closed = False
-        self._avail = np.ones((self.num_envs, N_AGENTS, 3), np.float32)
 
     # ---- ShareVecEnv API -----------------------------------------------------------------------
     def _share(self, obs, share):
         if self.nonoverlapping:
-            return np.repeat(share[:, None, :], N_AGENTS, axis=1)
+            return np.broadcast_to(share[:, None, :], (self.num_envs, N_AGENTS, SHARE_DIM)) if self.views else np.repeat(
+                share[:, None, :], N_AGENTS, axis=1)
         flat = obs.reshape(self.num_envs, 1, N_AGENTS * OBS_DIM)
-        return np.repeat(flat, N_AGENTS, axis=1)
+        return np.broadcast_to(flat, (self.num_envs, N_AGENTS, N_AGENTS * OBS_DIM)) if self.views else np.repeat(flat, N_AGENTS, axis=1)
 
     def reset(self):
         obs, share = self.engine.reset_host()
-        obs = obs.copy()
-        return obs, self._share(obs, share), self._avail.copy()
+        if not self.views:
+            obs = obs.copy()
+        return obs, self._share(obs, share), (self._avail if self.views else self._avail.copy())
 
-    def step(self, actions):
+    def step_async(self, actions):
         a = np.asarray(actions).reshape(self.num_envs, N_AGENTS)
-        obs, share, rew, done, info, term = self.engine.step_host(a, want_info=True, want_term=True)
-        obs = obs.copy()
+        self.engine.step_host_begin(a, want_info=not self.lazy_info, want_term=True)
+
+    def step_wait(self):
+        eng = self.engine
+        obs, share, rew, done, info, term = eng.step_host_end()
+        if not self.views:
+            obs = obs.copy()
         share_obs = self._share(obs, share)
         extras = {}
         finished = np.nonzero(done)[0]
         if len(finished):
-            term_share = np.concatenate([term[:, 0, :], term[:, 1, 11:12], term[:, 1, 13:14], term[:, 2, 25:26]], axis=1)
-            for i in finished:
-                o = term[i].copy()
-                s = (np.repeat(term_share[i][None], N_AGENTS, 0) if self.nonoverlapping
+            rows = term[finished]                                     # copies only the finished envs' terminal rows
+            term_share = np.concatenate([rows[:, 0, :], rows[:, 1, 11:12], rows[:, 1, 13:14], rows[:, 2, 25:26]], axis=1)
+            for j, i in enumerate(finished):
+                o = rows[j]
+                s = (np.repeat(term_share[j][None], N_AGENTS, 0) if self.nonoverlapping
                      else np.repeat(o.reshape(1, -1), N_AGENTS, 0))
                 extras[int(i)] = {"original_obs": o, "original_state": s, "original_avail_actions": self._avail[i].copy()}
-        infos = InfoBatch(info.copy(), extras)
+        if self.lazy_info:
+            step_id = eng.host_step_id
+
+            def fetch(first, count):
+                if eng.host_step_id != step_id:
+                    raise RuntimeError("this InfoBatch belongs to an earlier step: its info table has been overwritten on the device")
+                return eng.fetch_info(first, count)
+            infos = InfoBatch(None, extras, self.num_envs, fetch)
+        else:
+            infos = InfoBatch(info.copy(), extras)
+        if self.views:
+            dones = np.broadcast_to(done.view(np.bool_)[:, None], (self.num_envs, N_AGENTS))
+            return obs, share_obs, rew.reshape(self.num_envs, N_AGENTS, 1), dones, infos, self._avail
         dones = np.repeat(done.astype(bool)[:, None], N_AGENTS, axis=1)
         return obs, share_obs, rew.reshape(self.num_envs, N_AGENTS, 1).copy(), dones, infos, self._avail.copy()
 
-    def step_async(self, actions):
-        self._pending = actions
-
-    def step_wait(self):
-        return self.step(self._pending)
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
 
     def close(self):
         if not self.closed:

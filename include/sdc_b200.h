@@ -27,6 +27,7 @@ extern "C" {
 #define SDC_N_AGENTS 3          /* agent_ls, agent_dc, agent_bat            sustaindc_env.py:107 */
 #define SDC_OBS_DIM 26          /* rows zero-padded to the widest agent      harlsustaindc_env.py:25-26 */
 #define SDC_SHARE_DIM 29        /* nonoverlapping shared obs                 harlsustaindc_env.py:78-85 */
+#define SDC_OBS_COMPACT 53      /* agent_ls[26] | agent_dc[14] | agent_bat[13], unpadded   sustaindc_env.py:302-433 */
 #define SDC_INFO_STRIDE 64      /* info table rows (59 used, see info_layout.py) */
 #define SDC_YEAR_STEPS 35040    /* 365 d x 96 quarter-hours                  utils/managers.py:183-185 */
 #define SDC_TRACE_PAD 64        /* readable slack after the last trace sample */
@@ -161,6 +162,26 @@ int sdc_step(sdc_env* env, const int32_t* actions_dev, float* obs_dev, float* sh
 int sdc_step_host(sdc_env* env, const int32_t* actions, float* obs, float* share, float* rew,
                   uint8_t* done, float* info, float* term_obs);
 int sdc_reset_host(sdc_env* env, const uint8_t* mask, float* obs, float* share);
+/* The same call in two halves -- what ShareVecEnv.step_async / step_wait are (harl/envs/env_wrappers.py:104-127): _begin
+ * enqueues the copies and the step on the handle's stream and returns, sdc_step_host_end waits and delivers. */
+int sdc_step_host_begin(sdc_env* env, const int32_t* actions, float* obs, float* share, float* rew, uint8_t* done, float* info,
+                        float* term_obs);
+int sdc_step_host_end(sdc_env* env);
+
+/* Compact outputs: obs53[N, SDC_OBS_COMPACT] = the three UNPADDED rows agent_ls[26] | agent_dc[14] | agent_bat[13] of every env
+ * (sustaindc_env.py:302-433), term53 likewise for finished envs.  The zero padding to [3,26] and the HARL shared row
+ * (harlsustaindc_env.py:25-26,78-85) are pure functions of these 53 floats: sdc_expand_obs rebuilds both on the host.  Half the
+ * bytes of the padded call -- which is what a host-buffer caller pays for over PCIe. */
+int sdc_step_compact(sdc_env* env, const int32_t* actions_dev, float* obs53_dev, float* rew_dev, uint8_t* done_dev, float* info_dev,
+                     float* term53_dev, void* stream);
+int sdc_step_compact_host(sdc_env* env, const int32_t* actions, float* obs53, float* rew, uint8_t* done, float* info, float* term53);
+int sdc_step_compact_host_begin(sdc_env* env, const int32_t* actions, float* obs53, float* rew, uint8_t* done, float* info, float* term53);
+int sdc_host_buffers_compact(sdc_env* env, float** obs53, float** term53);      /* page-locked, like sdc_host_buffers */
+void sdc_expand_obs(const float* obs53, int64_t n, float* obs /*[n,3,26] or NULL*/, float* share /*[n,29] or NULL*/);
+/* With sdc_set_tuning(env, "lazy_info", 1) a host step keeps its info table on the device; this copies columns
+ * [first_col, first_col + n_cols) of the LAST host step to out[n_cols][N] (host).  The runners read a dozen of the 59
+ * columns per step (harl/envs/sustaindc/sustaindc_logger.py:86-101), not 16 MB. */
+int sdc_fetch_info(sdc_env* env, int32_t first_col, int32_t n_cols, float* out);
 /* The handle's own page-locked HOST buffers, laid out like the sdc_step_host arguments (actions[N,3] int32,
  * obs[N,3,26], share[N,29], rew[N,3], done[N], info[SDC_INFO_STRIDE][N], term_obs[N,3,26]); valid until
  * sdc_destroy.  Passing these same pointers to sdc_step_host / sdc_reset_host makes the transfers go
@@ -203,7 +224,8 @@ int64_t sdc_launch_count(sdc_env* env);
  * out[0] = number of timed steps, out[1] = sum of k_step ms, out[2] = 0 (episode resets run inside k_step),
  * out[3] = max k_step ms, and clears the accumulators. */
 int sdc_kernel_times(sdc_env* env, double* out4);
-/* tuning knob for experiments: "unit_envs", "unroll", "prefetch", "blocks_per_sm", "timing" */
+/* knobs: "unit_envs" (8 / 16 / 32), "blocks_per_sm", "timing", "phases" (diagnostic clocks), "direct_host" (bit 0 obs, 1 share,
+ * 2 terminal rows written by the kernel straight into the handle's pinned buffers), "lazy_info" */
 int sdc_set_tuning(sdc_env* env, const char* key, int32_t value);
 
 #ifdef __cplusplus

@@ -13,7 +13,7 @@ lines = []          # (file, line, source, samples, inst, reasons dict)
 for r in rows:
     if not r:
         continue
-    if r[0] == "File Name":
+    if r[0] in ("File Name", "File Path"):
         fname = r[1].split("/")[-1]
         continue
     if r[0] == "Line No":

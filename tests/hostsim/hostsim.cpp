@@ -112,20 +112,26 @@ static void scan_refresh(const sdc::State& S, int env, const sdc::ScanRequest& r
     }
 }
 
-static const char* launch_reset(Context&, const sdc::State& S, const int32_t* list, const int32_t* count, float* obs, float* share, void*);
+static void reset_envs(const sdc::State& S, const int32_t* list, int count, float* obs, float* share, float* obs_c);
+static void store_rows(const float* row, int env, float* obs, float* share, float* obs_c) {
+    if (obs) memcpy(obs + (size_t)env * 3 * SDC_OBS_DIM, row, 3 * SDC_OBS_DIM * sizeof(float));
+    if (share) sdc::share_from_obs(row, share + (size_t)env * SDC_SHARE_DIM);
+    if (obs_c) for (int k = 0; k < SDC_OBS_COMPACT; ++k) obs_c[(size_t)env * SDC_OBS_COMPACT + k] = row[sdc::compact_to_padded(k)];
+}
 
 static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs& a, void*) {
     for (int k = 0; k < 16; ++k) a.ctr_next[k] = 0;
     const int N = S.n_envs;
     for (int env = 0; env < N; ++env) {
-        ObsRow obs{a.obs + (size_t)env * 3 * SDC_OBS_DIM};
+        float row78[3 * SDC_OBS_DIM];
+        ObsRow obs{row78};
         InfoCol info{a.info, N, env};
         sdc::StepResult st;
         const sdc::Tables T{S.loc, S.dc};
         sdc::ObsDeferred od;
         sdc::physics_step(S, T, env, a.actions[env * 3 + 0], a.actions[env * 3 + 1], a.actions[env * 3 + 2], info, st, od);
         sdc::emit_obs(S, T, env, od, obs);
-        sdc::share_from_obs(obs.row, a.share + (size_t)env * SDC_SHARE_DIM);
+        store_rows(row78, env, a.obs, a.share, a.obs_c);
         sdc::ScanRequest rq; sdc::ScanResult rs; sdc::Moments mo;
         rs.s1 = rs.s2 = 0.f; rs.cnt[0] = rs.cnt[1] = 0; rs.ext[0] = rs.ext[1] = 0.f; rs.recentred = 0;
         sdc::QView Q;
@@ -148,7 +154,7 @@ static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs&
         }
         if (rq.kind == sdc::SCAN_PLAIN) {
             scan_plain(S, env, rq, rs);
-            a.ctr[4] += 1;
+            a.ctr[4] += 1; a.pass_total[0] += 1;
         } else if (rq.kind == sdc::SCAN_REFRESH) {
             sdc::RefreshRaw raw;
             std::vector<float> coll[2], band[2];
@@ -156,7 +162,7 @@ static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs&
             const float* sorted[2] = {coll[0].data(), coll[1].data()};
             const float* bands[2] = {band[0].data(), band[1].data()};
             sdc::refresh_commit(S, env, rq, raw, sorted, bands, Q, rs, 0, 1);
-            a.ctr[5] += 1;
+            a.ctr[5] += 1; a.pass_total[1] += 1;
         }
         sdc::RewardInputs en{e_rel, st.nci_next, st.ls_penalty};
         float alt3[3] = {0.f, 0.f, 0.f};
@@ -168,7 +174,7 @@ static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs&
         for (int j = 0; j < 2; ++j) { S.q_a[env * 2 + j] = Q.a[j]; S.q_m[env * 2 + j] = Q.m[j]; }
         a.done[env] = (uint8_t)st.terminal;
         if (st.terminal) {
-            if (a.term_obs) memcpy(a.term_obs + (size_t)env * 3 * SDC_OBS_DIM, obs.row, 3 * SDC_OBS_DIM * sizeof(float));
+            store_rows(row78, env, a.term_obs, nullptr, a.term_c);
             a.reset_list[a.ctr[1]++] = env;
         }
         double* M = a.metrics;
@@ -185,7 +191,8 @@ static const char* launch_step(Context& cx, const sdc::State& S, const StepArgs&
         M[sdc::M_REWARD_SUM] += (double)r[0] + r[1] + r[2]; M[sdc::M_REWARD_LS] += r[0]; M[sdc::M_REWARD_DC] += r[1];
         M[sdc::M_OVERDUE] += st.overdue; M[sdc::M_TOTAL_KW] += st.total_kw;
     }
-    launch_reset(cx, S, a.reset_list, a.ctr + 1, a.obs, a.share, nullptr);     // the CUDA kernel does this with worker CTAs
+    (void)cx;
+    reset_envs(S, a.reset_list, a.ctr[1], a.obs, a.share, a.obs_c);             // the CUDA kernel does this inside the launch
     for (int i = 0; i < a.ctr[1]; ++i) a.reset_list[i] = -1;
     return nullptr;
 }
@@ -203,8 +210,8 @@ static void generate_weather(const sdc::State& S, int env, int t0, int roll, uin
     const sdc::LocTables& L = S.loc[S.loc_id[env]];
     const int n = SDC_YEAR_STEPS;
     const uint64_t seed = S.seed[env];
-    std::vector<float> inc(sdc::kNoiseThreads * sdc::kNoiseSeg, 0.f);
-    for (int seg = 0; seg < sdc::kNoiseThreads; ++seg) {    // one PCG32 stream per segment, two normals per pair of draws
+    std::vector<float> inc(sdc::kNoiseSegs * sdc::kNoiseSeg, 0.f);
+    for (int seg = 0; seg < sdc::kNoiseSegs; ++seg) {    // one PCG32 stream per segment, two normals per pair of draws
         sdc::Pcg32 g = sdc::noise_stream(seed, episode, (uint32_t)seg);
         for (int q = 0; q < sdc::kNoiseSeg; q += 2) {
             float z[2];
@@ -215,7 +222,7 @@ static void generate_weather(const sdc::State& S, int env, int t0, int roll, uin
     }
     std::vector<double> walk(n);
     double acc = 0.0;
-    for (int i = 0; i < sdc::kNoiseThreads; ++i) {          // same segment structure as the kernel
+    for (int i = 0; i < sdc::kNoiseSegs; ++i) {             // same segment structure as the kernel
         double seg = 0.0;
         for (int j = i * sdc::kNoiseSeg; j < (i + 1) * sdc::kNoiseSeg && j < n; ++j) { seg += (double)inc[j]; walk[j] = acc + seg; }
         acc += seg;
@@ -245,7 +252,12 @@ static void generate_weather(const sdc::State& S, int env, int t0, int roll, uin
 }
 
 static const char* launch_reset(Context&, const sdc::State& S, const int32_t* list, const int32_t* count, float* obs, float* share, void*) {
-    for (int i = 0; i < *count; ++i) {
+    reset_envs(S, list, *count, obs, share, nullptr);
+    return nullptr;
+}
+
+static void reset_envs(const sdc::State& S, const int32_t* list, int count, float* obs, float* share, float* obs_c) {
+    for (int i = 0; i < count; ++i) {
         const int env = list[i];
         int day, hour, roll = 0;
         if (S.pend_valid[env] & 1) {
@@ -261,13 +273,13 @@ static const char* launch_reset(Context&, const sdc::State& S, const int32_t* li
         S.pend_valid[env] = 0;
         S.episode[env] += 1;
         memset(S.ls_ring + (size_t)env * (S.ls_mask + 1), 0, S.ls_mask + 1);
-        ObsRow o{obs + (size_t)env * 3 * SDC_OBS_DIM};
+        float row78[3 * SDC_OBS_DIM];
+        ObsRow o{row78};
         const int t0 = day * 96 + hour * 4;
         sdc::reset_scalars(S, env, t0);
         sdc::reset_observation(S, env, t0, window, S.t_min[env], S.t_max[env], o);
-        sdc::share_from_obs(o.row, share + (size_t)env * SDC_SHARE_DIM);
+        store_rows(row78, env, obs, share, obs_c);
     }
-    return nullptr;
 }
 
 static const char* launch_rebuild(Context&, const sdc::State& S, void*) {

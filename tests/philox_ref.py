@@ -34,7 +34,7 @@ def episode_start(seed, episode, day_lo, day_hi):
     return int(day_lo + int(r[0]) % (day_hi - day_lo + 1)), int(r[1]) % 24, int(r[2]) % 14
 
 
-N_SEG, SEG = 256, 140          # sdc_core.h kNoiseThreads, kNoiseSeg
+N_SEG, SEG = 256, 140          # sdc_core.h kNoiseSegs, kNoiseSeg
 
 
 def noise_increments(seed, episode, n=35040):

@@ -171,6 +171,61 @@ def test_small_rack_geometry_trips_the_outlet_guard(lib):
         eng.close()
 
 
+def test_compact_async_lazy_and_view_paths_agree_with_the_plain_call(lib):
+    """sdc_step_compact_host (53 unpadded floats per env) + sdc_expand_obs, the begin / end pair behind step_async /
+    step_wait, the lazy info table (sdc_fetch_info) and the zero-copy `output_views` mode all return what the plain
+    padded, eager, copying call returns."""
+    from dc_rl_b200.dc_config import size_datacenter
+    from dc_rl_b200.engine import Engine
+    from dc_rl_b200.vec_env import CudaShareVecEnv
+    from replay import location_traces
+    N, T = 70, 110
+    kw = dict(months=np.arange(N) % 12, seeds=np.arange(N, dtype=np.uint64) + 3, days_per_episode=1, lib=lib)
+    a_eng = Engine(N, [location_traces("az")], [size_datacenter("az")[0]], **kw)
+    c_eng = Engine(N, [location_traces("az")], [size_datacenter("az")[0]], **kw)
+    a_eng.reset_host(); c_eng.reset_host()
+    rng = np.random.RandomState(2)
+    n_done = 0
+    for s in range(T):
+        act = rng.randint(0, 3, size=(N, 3)).astype(np.int32)
+        obs, share, rew, done, info, term = a_eng.step_host(act)
+        o53, r2, d2, i2, t53 = c_eng.step_compact_host(act, want_info=True)
+        assert np.array_equal(rew, r2) and np.array_equal(done, d2) and np.array_equal(info, i2)
+        eo, es = c_eng.expand_obs(o53)
+        assert np.array_equal(eo, obs) and np.array_equal(es, share)
+        fin = np.nonzero(done)[0]
+        if len(fin):
+            n_done += len(fin)
+            assert np.array_equal(c_eng.expand_obs(t53[fin], want_share=False)[0], term[fin])
+    assert n_done >= N
+    a_eng.close(); c_eng.close()
+    # vec-env level: eager + copies (reference-like) vs lazy info + views + step_async / step_wait
+    args = {"location": "ny", "traces": location_traces("ny"), "days_per_episode": 1, "nonoverlapping_shared_obs_space": True}
+    plain = CudaShareVecEnv(dict(args, info="eager"), 9, seed=1, lib=lib)
+    fast = CudaShareVecEnv(dict(args, output_views=True), 9, seed=1, lib=lib)
+    o1, s1, _ = plain.reset(); o2, s2, _ = fast.reset()
+    assert np.array_equal(o1, o2) and np.array_equal(s1, s2)
+    for s in range(100):
+        act = rng.randint(0, 3, size=(9, 3, 1))
+        r1 = plain.step(act)
+        fast.step_async(act)
+        r2 = fast.step_wait()
+        for x, y in zip(r1[:4], r2[:4]):
+            assert x.shape == y.shape and x.dtype == y.dtype and np.array_equal(x, y)
+        assert np.array_equal(r1[4].column("dc_water_usage"), r2[4].column("dc_water_usage"))
+        assert r1[4][3][1]["bat_SOC"] == r2[4][3][1]["bat_SOC"] and len(r2[4]) == 9
+        if r1[3].any():
+            assert np.array_equal(r1[4][2][0]["original_obs"], r2[4][2][0]["original_obs"])
+    touched = fast.step(act)[4]
+    touched.column("bat_SOC")                    # read while current: stays readable afterwards
+    stale = fast.step(act)[4]                    # never read ...
+    fast.step(act)
+    assert touched.column("bat_SOC").shape == (9,)
+    with pytest.raises(RuntimeError, match="earlier step"):
+        stale.column("bat_SOC")                  # ... and its table has been overwritten on the device by now
+    plain.close(); fast.close()
+
+
 def test_make_env_month_and_seed_rules(lib):
     """harl/utils/envs_tools.py:56-67,95: month by rank unless pinned; seed + rank*1000 / seed*50000 + rank*10000."""
     from dc_rl_b200.dc_config import start_day_range
