@@ -18,7 +18,7 @@ A "step" = one sdc_step over all envs of a rank.  One JSON line:
                   rewards, dones, the 59-column info table, terminal observations); CUDA events around the K timed steps,
                   max over ranks.  `value_core_outputs`: the same without info / terminal observations (round-1 definition).
   e2e             the same metric through the host-buffer C-ABI call a numpy caller makes (sdc_step_compact_host: actions
-                  in; the 53 unpadded observation floats, rewards, dones and terminal rows out), H2D + D2H inside the timed
+                  in; the 29 distinct observation values per env, rewards, dones and terminal rows out), H2D + D2H inside the timed
                   region.  `e2e_padded`: sdc_step_host (obs[N,3,26] + share[N,29]); `e2e_vec_env`: CudaShareVecEnv.step, the
                   object harl.runners drive (zero-copy views / reference-like copies).
   roofline        `achieved` / `frac`: algorithmic bytes (4*H + 1024 = 41 024 B per env-step, the fixed
@@ -393,9 +393,9 @@ def main():
             "config": dict(cfg, settle_steps=args.settle, settle_s=round(t_settle, 2), numa=placement),
             "value_core_outputs": value_core,
             "e2e": {"value": e2e_compact, "unit": "env-steps/s", "h2d_bytes_per_step": n * 3 * 4,
-                    "d2h_bytes_per_step": n * (53 + 3) * 4 + n, "steps": e2e_steps,
-                    "call": "sdc_step_compact_host (numpy actions in; 53 unpadded observation floats, rewards, dones out; terminal rows of "
-                            "finished envs; pinned host buffers of the handle)"},
+                    "d2h_bytes_per_step": n * (29 + 3) * 4 + n, "steps": e2e_steps,
+                    "call": "sdc_step_compact_host (numpy actions in; the 29 distinct observation values per env (sdc_expand_obs rebuilds obs[N,3,26] "
+                            "and share_obs bit for bit), rewards, dones, terminal rows of finished envs out; pinned host buffers of the handle)"},
             "e2e_padded": {"value": e2e_padded, "unit": "env-steps/s", "d2h_bytes_per_step": n * (78 + 29 + 3) * 4 + n,
                            "call": "sdc_step_host (obs[N,3,26] + share_obs[N,29] + rewards + dones)"},
             "e2e_vec_env": {"value": e2e_vec_views, "copies": e2e_vec_copy, "unit": "env-steps/s",

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 MAX_RACK_CLASSES = 32
-N_AGENTS, OBS_DIM, SHARE_DIM, INFO_STRIDE, OBS_COMPACT = 3, 26, 29, 64, 53
+N_AGENTS, OBS_DIM, SHARE_DIM, INFO_STRIDE, OBS_COMPACT = 3, 26, 29, 64, 29
 YEAR_STEPS, TRACE_PAD, HIST_CAP, N_METRICS = 35040, 64, 10000, 16
 LIST_CAP, TAIL_CAP = 128, 128
 HVAC_BINS = 4096          # sdc_core.h kListCap / kTailCap (state inspection only)

@@ -1222,8 +1222,8 @@ constexpr int kNoiseSeg = 140;                            // even segment length
 // Buffers and knobs of one step launch (all device pointers; see sdc_step in include/sdc_b200.h).
 struct StepArgs {
     const int32_t* actions; float* obs; float* share; float* rew; uint8_t* done; float* info; float* term_obs;
-    // compact outputs (sdc_step_compact): the three unpadded rows back to back, [N][SDC_OBS_COMPACT]; obs / share / term_obs
-    // may then be null
+    // compact outputs (sdc_step_compact): the env's 29 distinct observation values, [N][SDC_OBS_COMPACT]; obs / share /
+    // term_obs may then be null
     float* obs_c; float* term_c;
     // this step's counters (ctr) and the next step's (ctr_next, zeroed by this launch):
     //   [0] unit tickets  [1] finished envs appended to reset_list  [2] units past the scalar phase
@@ -1248,8 +1248,9 @@ struct StepArgs {
     int32_t unit_envs, blocks_per_sm;
 };
 
-// compact column c of [agent_ls 26 | agent_dc 14 | agent_bat 13] -> column of the zero-padded [3][26] row
-SDC_HD int compact_to_padded(int c) { return c < 40 ? c : c + 12; }
+// compact column c of [agent_ls 26 | workload(t+1) | norm T(t+1) | SoC] -> column of the zero-padded [3][26] row
+// (agent_dc[11], agent_dc[13], agent_bat[12]; every other dc / bat entry repeats an agent_ls entry, sustaindc_env.py:302-433)
+SDC_HD int compact_to_padded(int c) { return c < 26 ? c : (c == 26 ? SDC_OBS_DIM + 11 : (c == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 12)); }
 
 // HARL shared observation (harl/envs/sustaindc/harlsustaindc_env.py:78-85): ls[0:26] | dc[11] | dc[13] |
 // last element of the zero-padded battery row (always 0.0).

@@ -908,10 +908,10 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                     }
                 }
                 if (a.obs_c) {
-                    // compact rows: 53 floats per env, no padding, no shared row -- half the bytes of obs + share, which is what a
-                    // host caller pays for over PCIe
+                    // compact rows: the 29 distinct observation values per env (no padding, no repeated columns, no shared row) --
+                    // 116 B instead of the 428 B of obs + share, which is what a host caller pays for over PCIe
                     const int total = n_here * SDC_OBS_COMPACT;
-                    float4* dst4 = reinterpret_cast<float4*>(a.obs_c + (size_t)env0 * SDC_OBS_COMPACT);   // env0 * 53 * 4 B: 16-byte aligned for env0 % 4 == 0
+                    float4* dst4 = reinterpret_cast<float4*>(a.obs_c + (size_t)env0 * SDC_OBS_COMPACT);   // env0 * 29 * 4 B: 16-byte aligned for env0 % 4 == 0
                     for (int i = lane; i < total / 4; i += 32) {
                         float v[4];
 #pragma unroll

@@ -206,8 +206,9 @@ class Engine:
         return self.step_host_end()
 
     def step_compact_host(self, actions, want_info=False, want_term=True):
-        """Compact host call: (obs53[N,53], rew[N,3], done[N], info | None, term53[N,53] | None) -- the three unpadded
-        observation rows back to back; `expand_obs` rebuilds the padded rows and the shared observation."""
+        """Compact host call: (obsc[N,29], rew[N,3], done[N], info | None, termc[N,29] | None) -- the 29 distinct observation
+        values of every env (agent_ls[26] | workload(t+1) | norm T(t+1) | SoC; include/sdc_b200.h); `expand_obs` rebuilds the
+        padded rows and the shared observation bit for bit."""
         b = self._host_buffers()
         a = b["actions"]
         a[...] = np.asarray(actions).reshape(self.n_envs, N_AGENTS)
@@ -216,13 +217,13 @@ class Engine:
         self.host_step_id = getattr(self, "host_step_id", 0) + 1
         return b["obs_c"], b["rew"], b["done"], (b["info"] if want_info else None), (b["term_c"] if want_term else None)
 
-    def step_compact_device(self, actions, obs53, rew, done, info=None, term53=None, stream=None):
-        self._check(self.lib.sdc_step_compact(self._h, _ptr(actions), _ptr(obs53), _ptr(rew), _ptr(done), _ptr(info), _ptr(term53),
+    def step_compact_device(self, actions, obsc, rew, done, info=None, termc=None, stream=None):
+        self._check(self.lib.sdc_step_compact(self._h, _ptr(actions), _ptr(obsc), _ptr(rew), _ptr(done), _ptr(info), _ptr(termc),
                                               _ptr(stream)))
 
-    def expand_obs(self, obs53, want_share=True):
+    def expand_obs(self, obsc, want_share=True):
         """Host utility: compact rows -> (obs[n,3,26] zero padded, share[n,29] | None)."""
-        c = np.ascontiguousarray(obs53, np.float32).reshape(-1, OBS_COMPACT)
+        c = np.ascontiguousarray(obsc, np.float32).reshape(-1, OBS_COMPACT)
         obs = np.empty((len(c), N_AGENTS, OBS_DIM), np.float32)
         share = np.empty((len(c), SHARE_DIM), np.float32) if want_share else None
         self.lib.sdc_expand_obs(_ptr(c), len(c), _ptr(obs), _ptr(share))

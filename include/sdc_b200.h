@@ -27,7 +27,7 @@ extern "C" {
 #define SDC_N_AGENTS 3          /* agent_ls, agent_dc, agent_bat            sustaindc_env.py:107 */
 #define SDC_OBS_DIM 26          /* rows zero-padded to the widest agent      harlsustaindc_env.py:25-26 */
 #define SDC_SHARE_DIM 29        /* nonoverlapping shared obs                 harlsustaindc_env.py:78-85 */
-#define SDC_OBS_COMPACT 53      /* agent_ls[26] | agent_dc[14] | agent_bat[13], unpadded   sustaindc_env.py:302-433 */
+#define SDC_OBS_COMPACT 29      /* the DISTINCT observation values of an env: agent_ls[26] | workload(t+1) | norm T(t+1) | SoC */
 #define SDC_INFO_STRIDE 64      /* info table rows (59 used, see info_layout.py) */
 #define SDC_YEAR_STEPS 35040    /* 365 d x 96 quarter-hours                  utils/managers.py:183-185 */
 #define SDC_TRACE_PAD 64        /* readable slack after the last trace sample */
@@ -168,16 +168,19 @@ int sdc_step_host_begin(sdc_env* env, const int32_t* actions, float* obs, float*
                         float* term_obs);
 int sdc_step_host_end(sdc_env* env);
 
-/* Compact outputs: obs53[N, SDC_OBS_COMPACT] = the three UNPADDED rows agent_ls[26] | agent_dc[14] | agent_bat[13] of every env
- * (sustaindc_env.py:302-433), term53 likewise for finished envs.  The zero padding to [3,26] and the HARL shared row
- * (harlsustaindc_env.py:25-26,78-85) are pure functions of these 53 floats: sdc_expand_obs rebuilds both on the host.  Half the
- * bytes of the padded call -- which is what a host-buffer caller pays for over PCIe. */
-int sdc_step_compact(sdc_env* env, const int32_t* actions_dev, float* obs53_dev, float* rew_dev, uint8_t* done_dev, float* info_dev,
-                     float* term53_dev, void* stream);
-int sdc_step_compact_host(sdc_env* env, const int32_t* actions, float* obs53, float* rew, uint8_t* done, float* info, float* term53);
-int sdc_step_compact_host_begin(sdc_env* env, const int32_t* actions, float* obs53, float* rew, uint8_t* done, float* info, float* term53);
-int sdc_host_buffers_compact(sdc_env* env, float** obs53, float** term53);      /* page-locked, like sdc_host_buffers */
-void sdc_expand_obs(const float* obs53, int64_t n, float* obs /*[n,3,26] or NULL*/, float* share /*[n,29] or NULL*/);
+/* Compact outputs: obsc[N, SDC_OBS_COMPACT] holds the 29 DISTINCT values of an env's three observations.  The reference builds
+ * agent_dc's 14 and agent_bat's 13 entries from the same time / carbon-intensity / workload / temperature values as agent_ls's
+ * 26 (sustaindc_env.py:302-433): dc = ls[0:10] | ls[13] | workload(t+1) | ls[14] | norm T(t+1), bat = ls[0:10] | ls[13] | ls[14] | SoC.
+ * So obsc = agent_ls[26] | workload(t+1) | norm T(t+1) | SoC -- the HARL shared row (harlsustaindc_env.py:78-85) with the
+ * battery's SoC in its last slot instead of the padding zero.  The padded [3,26] rows and the shared row are column
+ * selections of these 29 floats: sdc_expand_obs rebuilds both on the host, bit for bit.  termc likewise for finished envs.
+ * 129 bytes per env-step cross PCIe instead of 441. */
+int sdc_step_compact(sdc_env* env, const int32_t* actions_dev, float* obsc_dev, float* rew_dev, uint8_t* done_dev, float* info_dev,
+                     float* termc_dev, void* stream);
+int sdc_step_compact_host(sdc_env* env, const int32_t* actions, float* obsc, float* rew, uint8_t* done, float* info, float* termc);
+int sdc_step_compact_host_begin(sdc_env* env, const int32_t* actions, float* obsc, float* rew, uint8_t* done, float* info, float* termc);
+int sdc_host_buffers_compact(sdc_env* env, float** obsc, float** termc);      /* page-locked, like sdc_host_buffers */
+void sdc_expand_obs(const float* obsc, int64_t n, float* obs /*[n,3,26] or NULL*/, float* share /*[n,29] or NULL*/);
 /* With sdc_set_tuning(env, "lazy_info", 1) a host step keeps its info table on the device; this copies columns
  * [first_col, first_col + n_cols) of the LAST host step to out[n_cols][N] (host).  The runners read a dozen of the 59
  * columns per step (harl/envs/sustaindc/sustaindc_logger.py:86-101), not 16 MB. */

@@ -172,7 +172,7 @@ def test_small_rack_geometry_trips_the_outlet_guard(lib):
 
 
 def test_compact_async_lazy_and_view_paths_agree_with_the_plain_call(lib):
-    """sdc_step_compact_host (53 unpadded floats per env) + sdc_expand_obs, the begin / end pair behind step_async /
+    """sdc_step_compact_host (the 29 distinct observation values per env) + sdc_expand_obs, the begin / end pair behind step_async /
     step_wait, the lazy info table (sdc_fetch_info) and the zero-copy `output_views` mode all return what the plain
     padded, eager, copying call returns."""
     from dc_rl_b200.dc_config import size_datacenter
@@ -189,14 +189,14 @@ def test_compact_async_lazy_and_view_paths_agree_with_the_plain_call(lib):
     for s in range(T):
         act = rng.randint(0, 3, size=(N, 3)).astype(np.int32)
         obs, share, rew, done, info, term = a_eng.step_host(act)
-        o53, r2, d2, i2, t53 = c_eng.step_compact_host(act, want_info=True)
+        oc, r2, d2, i2, tc = c_eng.step_compact_host(act, want_info=True)
         assert np.array_equal(rew, r2) and np.array_equal(done, d2) and np.array_equal(info, i2)
-        eo, es = c_eng.expand_obs(o53)
+        eo, es = c_eng.expand_obs(oc)
         assert np.array_equal(eo, obs) and np.array_equal(es, share)
         fin = np.nonzero(done)[0]
         if len(fin):
             n_done += len(fin)
-            assert np.array_equal(c_eng.expand_obs(t53[fin], want_share=False)[0], term[fin])
+            assert np.array_equal(c_eng.expand_obs(tc[fin], want_share=False)[0], term[fin])
     assert n_done >= N
     a_eng.close(); c_eng.close()
     # vec-env level: eager + copies (reference-like) vs lazy info + views + step_async / step_wait
