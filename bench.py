@@ -364,6 +364,21 @@ def main():
     e2e_vec_views = host_timed(lambda a: vec_views.step(a))
     vec_copy = CudaShareVecEnv(vec_args, n, engine=eng)
     e2e_vec_copy = host_timed(lambda a: vec_copy.step(a))
+    # ---- what the host link gives all ranks at once: device -> pinned host copies issued concurrently by every rank ----
+    link_bytes = 256 << 20
+    d_src = torch.empty(link_bytes, dtype=torch.uint8, device=dev)
+    h_dst = torch.empty(link_bytes, dtype=torch.uint8, pin_memory=True)
+    h_dst.copy_(d_src, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        h_dst.copy_(d_src, non_blocking=True)
+    barrier()
+    link_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(link_s, op=dist.ReduceOp.MAX)
+    link_gbs_rank = 4 * link_bytes / float(link_s.item()) / 1e9          # per rank, with all ranks copying
+    del d_src, h_dst
     clocks = sampler.summary() if sampler else None
     err = int(np.bitwise_or.reduce(eng.read_state("err")))
 
@@ -394,6 +409,10 @@ def main():
             "value_core_outputs": value_core,
             "e2e": {"value": e2e_compact, "unit": "env-steps/s", "h2d_bytes_per_step": n * 3 * 4,
                     "d2h_bytes_per_step": n * (29 + 3) * 4 + n, "steps": e2e_steps,
+                    "host_link": {"d2h_gbs_per_rank_all_ranks_copying": link_gbs_rank, "aggregate_gbs": link_gbs_rank * world,
+                                  "link_bound_value": n * world / ((n * (29 + 3) * 4 + n + n * 12) / (link_gbs_rank * 1e9)),
+                                  "note": "a 256 MB device -> pinned-host copy repeated by every rank at once; link_bound_value = env-steps/s if "
+                                          "the step's H2D + D2H bytes moved at that rate and nothing else took time"},
                     "call": "sdc_step_compact_host (numpy actions in; the 29 distinct observation values per env (sdc_expand_obs rebuilds obs[N,3,26] "
                             "and share_obs bit for bit), rewards, dones, terminal rows of finished envs out; pinned host buffers of the handle)"},
             "e2e_padded": {"value": e2e_padded, "unit": "env-steps/s", "d2h_bytes_per_step": n * (78 + 29 + 3) * 4 + n,

@@ -60,6 +60,7 @@ class Engine:
         """locations: list of traces.LocationTraces; dc_params: list of _lib.DcParams (one per (dc_config,
         location) pair); loc_id / cfg_id / months / seeds: per-env arrays (scalars broadcast)."""
         self.lib = lib or default_lib()
+        self.device = int(device)
         self.n_envs = int(n_envs)
         self.ep_len = int(days_per_episode) * 96
         self.locations, self.dc_params = list(locations), list(dc_params)

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 from . import info_layout
-from ._lib import N_AGENTS, OBS_DIM, SHARE_DIM
+from ._lib import INFO_STRIDE, N_AGENTS, OBS_DIM, SHARE_DIM
 from .dc_config import load_dc_config, size_datacenter
 from .engine import Engine
 from .traces import LocationTraces, location_key
@@ -325,6 +325,45 @@ class CudaShareVecEnv:
         if not self.closed:
             self.engine.close()
             self.closed = True
+
+    # ---- device-resident surface: torch CUDA tensors in, torch CUDA tensors out, nothing crosses PCIe -----
+    def _torch_buffers(self):
+        if not hasattr(self, "_tt"):
+            import torch
+            dev = torch.device("cuda", self.engine.device)
+            n = self.num_envs
+            z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)      # noqa: E731
+            self._tt = dict(dev=dev, obs=z(n, N_AGENTS, OBS_DIM), share=z(n, SHARE_DIM), rew=z(n, N_AGENTS), done=z(n, dt=torch.uint8),
+                            info=z(INFO_STRIDE, n), term=z(n, N_AGENTS, OBS_DIM))
+        return self._tt
+
+    def reset_torch(self):
+        """reset() with device-resident results: (obs[N,3,26], share_obs[N,29]) torch CUDA tensors owned by the env."""
+        import torch
+        t = self._torch_buffers()
+        self.engine.reset_device(t["obs"], t["share"], stream=torch.cuda.current_stream(t["dev"]).cuda_stream)
+        return t["obs"], t["share"]
+
+    def step_torch(self, actions, want_info=False):
+        """step() for a device-resident rollout: `actions` is a CUDA tensor [N,3] (any integer / float dtype); returns
+        (obs[N,3,26], share_obs[N,29], rewards[N,3], dones[N] uint8) CUDA tensors owned by the env and overwritten by the
+        next call, enqueued on torch's current stream -- no host round trip, no synchronisation.  Auto-reset as in
+        step(); the pre-reset observations of finished envs are in `terminal_obs_torch`; with want_info the [64,N] info
+        table is in `info_torch` (row order: info_layout.INFO_COLUMNS)."""
+        import torch
+        t = self._torch_buffers()
+        a = actions.reshape(self.num_envs, N_AGENTS).to(device=t["dev"], dtype=torch.int32).contiguous()
+        self.engine.step_device(a, t["obs"], t["share"], t["rew"], t["done"], t["info"] if want_info else None, t["term"],
+                                torch.cuda.current_stream(t["dev"]).cuda_stream)
+        return t["obs"], t["share"], t["rew"], t["done"]
+
+    @property
+    def terminal_obs_torch(self):
+        return self._torch_buffers()["term"]
+
+    @property
+    def info_torch(self):
+        return self._torch_buffers()["info"]
 
     # ---- extras --------------------------------------------------------------------------------
     def metrics(self, clear=False):
