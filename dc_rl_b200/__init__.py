@@ -12,6 +12,8 @@ _LAZY = {
     "HARLSustainDCEnv": "harl_env",
     "make_train_env": "harl_env",
     "make_eval_env": "harl_env",
+    "SustainDCPettingZooEnv": "ptzoo_env",
+    "SustainDCLogger": "logger",
 }
 
 

@@ -197,7 +197,12 @@ def main():
     else:
         if hasattr(runner.logger, "attach"):
             runner.logger.attach(runner.envs)
-        insert, step = runner.insert, runner.envs.step
+        insert, step, collect = runner.insert, runner.envs.step, runner.collect
+        stats["t_rollout"] = 0.0
+
+        def timed_collect(i):
+            stats["t_c0"] = time.perf_counter()
+            return collect(i)
 
         def timed_step(actions):
             t0 = time.perf_counter()
@@ -212,16 +217,18 @@ def main():
             stats["insert_calls"] += 1
             stats["env_steps"] += N
             stats["t_last"] = time.perf_counter()
-        runner.insert, runner.envs.step = counted_insert, timed_step
+            stats["t_rollout"] += stats["t_last"] - stats["t_c0"]          # collect -> envs.step -> logger.per_step -> insert
+        runner.insert, runner.envs.step, runner.collect = counted_insert, timed_step, timed_collect
         t0 = time.perf_counter()
         runner.run()
-        # rollout time = wall time minus nothing: the reference's own FPS counts collection AND training (base_logger.py:86)
-        rate = stats["env_steps"] / (time.perf_counter() - t0)
+        stats["wall_with_training"] = time.perf_counter() - t0            # what the reference's own FPS line counts (base_logger.py:86)
+        rate = stats["env_steps"] / stats["t_rollout"]
         mode = "unmodified OnPolicyHARunner.run()"
     runner.close() if hasattr(runner, "close") else None
     print(json.dumps({"config": "configs[4]: HAPPO rollout through harl.runners", "mode": mode, "n_envs": N, "episode_length": T,
                       "episodes": a.episodes, "env_steps": stats["env_steps"], "env_steps_per_s_into_buffers": rate,
-                      "env_step_call_s": stats["t_env"], "logger": type(runner.logger).__module__}))
+                      "env_step_call_s": stats["t_env"], "env_steps_per_s_through_envs_step": (stats["env_steps"] / stats["t_env"]) if stats["t_env"] else None,
+                      "wall_with_training_s": stats.get("wall_with_training"), "logger": type(runner.logger).__module__}))
 
 
 if __name__ == "__main__":

@@ -267,6 +267,27 @@ def test_single_env_gym_surface(lib):
     env.close()
 
 
+def test_pettingzoo_parallel_env_surface(lib):
+    """harl/envs/sustaindc/sustaindc_ptzoo.py:5-101: dict-keyed spaces, reset -> obs dict, step -> five agent-keyed dicts."""
+    from dc_rl_b200 import SustainDCPettingZooEnv
+    from replay import location_traces
+    cfg = {"location": "wa", "month": 9, "days_per_episode": 1, "traces": location_traces("wa"), "partial_obs": True,
+           "nonoverlapping_shared_obs_space": True}
+    with pytest.raises(NotImplementedError):
+        SustainDCPettingZooEnv(dict(cfg, partial_obs=False), lib=lib)
+    env = SustainDCPettingZooEnv(cfg, lib=lib)
+    assert env.possible_agents == ["agent_ls", "agent_dc", "agent_bat"] and env.share_observation_space["agent_dc"].shape == (29,)
+    assert env.observation_space("agent_bat").shape == (13,) and env.action_space("agent_ls").n == 3
+    obs = env.reset(seed=3)
+    assert set(obs) == set(env.possible_agents) and obs["agent_ls"].shape == (26,)
+    for s in range(96):
+        o, r, d, t, info = env.step({"agent_ls": 1, "agent_dc": 1, "agent_bat": 2})
+        assert set(o) == set(r) == set(d) == set(t) == set(info) == set(env.possible_agents)
+        assert not any(d.values()) and all(t.values()) == (s == 95)
+        assert info["agent_dc"]["dc_crac_setpoint"] == 18.0           # do-nothing actions keep the set-point
+    env.close()
+
+
 def test_requires_data_or_explicit_synthetic(lib):
     from dc_rl_b200.vec_env import CudaShareVecEnv
     old = os.environ.pop("SDC_DATA_ROOT", None)
