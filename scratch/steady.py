@@ -39,3 +39,12 @@ cnt = int(pc[12]); nres, npass, ngen = cnt & 0xffff, (cnt >> 16) & 0xffff, (cnt 
 print("worker jobs over 100 steps (counts mod 65536): %d resets x %.0f clk, %d passes x %.0f clk, %d generations x %.0f clk" % (
     nres, pc[5] / max(nres, 1), npass, pc[7] / max(npass, 1), ngen, pc[6] / max(ngen, 1)))
 print("err", int(np.bitwise_or.reduce(eng.read_state("err"))))
+# timeline of single steps in the steady state (phase clocks cleared before each)
+for k in range(5):
+    eng.set_tuning(phases=1)
+    torch.cuda.synchronize(); e0.record(); eng.step_device(acts[k], obs, share, rew, done, None, None, st); e1.record(); torch.cuda.synchronize()
+    p1 = eng.read_state("phase_clocks").astype(np.float64)
+    cnt = int(p1[12])
+    print("single step: event %.1f us; first CTA start -> last unit done %.1f us -> last CTA done %.1f us; slowest unit %.0f clk (before barrier %.0f); jobs: %d passes x %.0f clk, %d generations x %.0f clk" % (
+        e0.elapsed_time(e1) * 1e3, (p1[14] - p1[13]) / 1e3, (p1[15] - p1[13]) / 1e3, p1[10], p1[11],
+        (cnt >> 16) & 0xffff, p1[7] / max((cnt >> 16) & 0xffff, 1), (cnt >> 32) & 0xffff, p1[6] / max((cnt >> 32) & 0xffff, 1)))
