@@ -38,7 +38,7 @@ constexpr int kBandTarget = 96;       // a refresh narrows the bands when one ho
 constexpr int kBandSparse = 40;       // ... and widens them when both hold fewer than this (the bands are sorted: a step's cost does
                                       // not depend on their population, a wide band is re-centred less often)
 constexpr int kAlphaOff = 12;         // narrowest tail band: alpha = 0.5 / 2^12 of the IQR
-constexpr int kPassJobBytes = 192;     // size of one maintenance-pass record (sdc_kernels.cu PassJob)
+constexpr int kPassJobBytes = 272;     // size of one window-pass record (sdc_kernels.cu PassJob)
 constexpr int kTailRetry = 200;       // steps of plain scans before another attempt at tail sets that did not fit
 constexpr double kSpMin = 15.0, kSpMax = 21.6;   // utils/make_envs_pyenv.py:124-126
 

@@ -170,7 +170,8 @@ struct GlobalInfoSink {
 // Parameters and results of the pass in flight (one at a time per CTA).
 struct PassJob {
     // request (written by the lane that owns the env)
-    int env, n, kind, pad;
+    int env, n, kind;
+    int finish;                             // the step's reward waits for this pass: the CTA that runs it prices the step (finish_step)
     double lo64, hi64;                      // the step's fences in fp64: where the rebuilt bands are split
     float lo, hi, shift, tl, th, tl2, th2;
     int dir[2]; float thr[2];
@@ -179,6 +180,9 @@ struct PassJob {
     int q_a[2], q_m[2];
     // results (written by warp 0)
     sdc::ScanResult rs;
+    // finish == 1: what reward_finish needs besides the request and the results
+    int m_ok; float alt3[3];
+    double q1, m_c1, m_c2, m_c0, energy, nci_next, ls_penalty;
 };
 static_assert(sizeof(PassJob) <= sdc::kPassJobBytes && sdc::kPassJobBytes % 16 == 0, "maintenance pass record size");
 struct PassShared {
@@ -190,7 +194,6 @@ struct PassShared {
     float red_f[kWarpsPerBlock][4];         // s1, s2, ext0, ext1
     double red_d[kWarpsPerBlock][6];        // S1, S2, far sums
     int red_i[kWarpsPerBlock][6];           // cnt0, cnt1, below0, below1, far counts
-    unsigned slow[kWarpsPerBlock];          // lanes of each warp that asked for a pass this round
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -396,6 +399,27 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
     }
     if (tid == 0) ps.job.rs = rs;
     __syncthreads();                                                     // results visible; `win`, `scr`, partials free again
+}
+
+// The env of a finish job could not price its step without the window (a bracket ran out on one side, or the bands no
+// longer contain the fences): the lane that owns it handed over the inputs of reward_finish, and the thread that holds the
+// pass results does what that lane would have done after a synchronous pass -- bracket cursors, the three rewards, reward sums.
+__device__ __noinline__ void finish_step(const sdc::State& S, const StepArgs& a, const PassJob& J) {
+    const int env = J.env;
+    sdc::ScanRequest rq;
+    rq.kind = J.kind; rq.n = J.n; rq.dir[0] = J.dir[0]; rq.dir[1] = J.dir[1]; rq.degenerate = J.degenerate; rq.q1 = J.q1; rq.shift = J.shift;
+    sdc::Moments M; M.c1 = J.m_c1; M.c2 = J.m_c2; M.c0 = J.m_c0; M.ok = J.m_ok;
+    sdc::RewardInputs en; en.energy = J.energy; en.nci_next = J.nci_next; en.ls_penalty = J.ls_penalty;
+    sdc::QView Q;
+    Q.lst[0] = S.qlist + (size_t)env * 2 * sdc::kListCap; Q.lst[1] = Q.lst[0] + sdc::kListCap;
+    Q.a[0] = J.q_a[0]; Q.a[1] = J.q_a[1]; Q.m[0] = J.q_m[0]; Q.m[1] = J.q_m[1];
+    float r3[3];
+    sdc::reward_finish(S, env, rq, J.rs, M, en, J.alt3, Q, r3);
+    reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
+    reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
+    a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
+    atomicAdd(a.metrics + sdc::M_REWARD_SUM, (double)r3[0] + r3[1] + r3[2]);
+    atomicAdd(a.metrics + sdc::M_REWARD_LS, (double)r3[0]); atomicAdd(a.metrics + sdc::M_REWARD_DC, (double)r3[1]);
 }
 
 // =================================================================================================
@@ -658,21 +682,29 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
     if (blockIdx.x == 0 && threadIdx.x < 16) a.ctr_next[threadIdx.x] = 0;
 
     // ------------------------------------------------------------------------------------------------------------
-    // Rounds (CTA-synchronous).  In a round every warp takes a unit of U consecutive envs from the ticket counter,
-    // one lane per env:
+    // Units.  A warp takes a unit of U consecutive envs, one lane per env:
     //   physics (load shifting, data centre, battery, traces) -> the step's energy
     //   reward normaliser, incremental: window append, quartile brackets, moments, tail bands (sdc_core.h)
-    // then the CTA as a whole streams the windows of the few envs whose incremental state ran out of slack (TMA bulk
-    // copy into shared memory, all 256 threads scan, sort and commit), and the warps finish their units: rewards,
-    // observations, logger sums, hand-over of finished envs to the reset workers.
+    //   rewards, observations, logger sums, resets of finished envs.
+    // An env whose incremental state ran out of slack publishes a window pass to the job queue (served by the worker
+    // CTAs: TMA bulk copy of the window into shared memory, all 256 threads scan, sort and commit); the rare env that
+    // cannot price this step without its window leaves the pricing to the CTA that runs the pass (finish_step).
     // ------------------------------------------------------------------------------------------------------------
     if (a.phase_clocks && threadIdx.x == 0) atomicMin(a.phase_clocks + 13, gtime_ns());
+    // Warps run their units independently: nothing inside a unit meets the rest of the CTA.  The first unit of a warp is
+    // its slot in the grid (no round trip to the ticket counter at the head of the launch); further ones -- batches larger
+    // than one resident round -- come from the counter.
+    const int n_first = min(n_unit_ctas * kWarpsPerBlock, n_units);
+    bool first_round = true;
     if (blockIdx.x < n_unit_ctas) for (;;) {
-        int unit = 0;
-        if (lane == 0) unit = atomicAdd(a.ctr + 0, 1);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
-        const bool have_unit = unit < n_units;
-        if (!__syncthreads_or(have_unit)) break;
+        int unit = blockIdx.x * kWarpsPerBlock + warp;
+        if (!first_round) {
+            if (lane == 0) unit = n_first + atomicAdd(a.ctr + 0, 1);
+            unit = __shfl_sync(0xffffffffu, unit, 0);
+        }
+        first_round = false;
+        if (unit >= n_units) break;                                     // warp-uniform
+        constexpr bool have_unit = true;
         const int env0 = unit * U;
         const int env = env0 + lane;
         const bool active = have_unit && lane < U && env < N;
@@ -817,32 +849,34 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                 }
             }
         }
-        // ---- everything that does not depend on a window pass happens BEFORE the CTA meets for the passes, so the wait
-        //      for the slowest warp of the CTA is filled with work: rewards of the incremental lanes, observations, sums ----
-        {
-            const unsigned sync_mask = __ballot_sync(0xffffffffu, slow_lane);
-            if (lane == 0) ps.slow[warp] = sync_mask;
-        }
         float r3[3] = {0.f, 0.f, 0.f};
-        if (active && !slow_lane) {
+        if (active) {
             const int kind = rq.kind;
-            rq.kind = sdc::SCAN_SKIP;              // no pass results to apply: price the step from the incremental state
-            sdc::reward_finish(S, env, rq, rs, M, en, alt3, Q, r3);
-            reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
-            reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
-            a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
-            if (async_lane) {
-                // publish the maintenance pass: record first, then its tag (the pass CTA rewrites q_a / q_m / brackets /
-                // bands / moments of this env, all of which this lane has finished writing)
+            if (!slow_lane) {
+                rq.kind = sdc::SCAN_SKIP;          // no pass results to apply: price the step from the incremental state
+                sdc::reward_finish(S, env, rq, rs, M, en, alt3, Q, r3);
+                reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
+                reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
+                a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
+            }
+            if (wants_pass) {
+                // Publish the pass: record first, then its tag.  The pass CTA rewrites q_a / q_m / brackets / bands / moments of
+                // this env, all of which this lane (and, for the edits, its warp: __syncwarp above) has finished writing.  A
+                // slow lane also hands over what reward_finish needs: the pass CTA prices the step, stores the rewards and the
+                // bracket cursors and adds the reward sums -- this warp does not wait for it.
                 const int idx = atomicAdd(a.ctr + 10, 1);
                 PassJob J;
-                J.env = env; J.n = rq.n; J.kind = kind; J.pad = 0; J.lo64 = rq.lo64; J.hi64 = rq.hi64;
+                J.env = env; J.n = rq.n; J.kind = kind; J.finish = slow_lane ? 1 : 0; J.lo64 = rq.lo64; J.hi64 = rq.hi64;
                 J.lo = rq.lo; J.hi = rq.hi; J.shift = rq.shift; J.tl = rq.tl; J.th = rq.th; J.tl2 = rq.tl2; J.th2 = rq.th2;
-                J.dir[0] = 0; J.dir[1] = 0; J.thr[0] = 0.f; J.thr[1] = 0.f;
+                J.dir[0] = slow_lane ? rq.dir[0] : 0; J.dir[1] = slow_lane ? rq.dir[1] : 0;
+                J.thr[0] = slow_lane ? rq.thr[0] : 0.f; J.thr[1] = slow_lane ? rq.thr[1] : 0.f;
                 J.rc[0] = rq.rc[0]; J.rc[1] = rq.rc[1]; J.k[0] = rq.k[0]; J.k[1] = rq.k[1];
                 J.ca[0] = rq.ca[0]; J.ca[1] = rq.ca[1]; J.cb[0] = rq.cb[0]; J.cb[1] = rq.cb[1];
                 J.tails = rq.tails; J.degenerate = rq.degenerate;
                 J.q_a[0] = Q.a[0]; J.q_a[1] = Q.a[1]; J.q_m[0] = Q.m[0]; J.q_m[1] = Q.m[1];
+                J.m_ok = M.ok; J.alt3[0] = alt3[0]; J.alt3[1] = alt3[1]; J.alt3[2] = alt3[2];
+                J.q1 = rq.q1; J.m_c1 = M.c1; J.m_c2 = M.c2; J.m_c0 = M.c0;
+                J.energy = en.energy; J.nci_next = en.nci_next; J.ls_penalty = en.ls_penalty;
                 reinterpret_cast<PassJob*>(reinterpret_cast<unsigned char*>(a.pass_jobs) + (size_t)idx * sdc::kPassJobBytes)[0] = J;
                 __threadfence();
                 *reinterpret_cast<volatile int32_t*>(a.pass_ready + idx) = a.seq;
@@ -935,40 +969,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
             }
         }
         const long long tk2c = clock64();
-        // ---- window passes for the envs that need one (whole CTA per env) ----
-        __syncthreads();                      // the step's ring / bracket / band updates of all warps are visible CTA-wide
-#pragma unroll 1
-        for (int w = 0; w < kWarpsPerBlock; ++w) {
-            unsigned mask = ps.slow[w];       // uniform across the CTA
-#pragma unroll 1
-            while (mask) {
-                const int l = __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (warp == w && lane == l) {
-                    PassJob& J = ps.job;
-                    J.env = env; J.n = rq.n; J.kind = rq.kind; J.pad = 0; J.lo64 = rq.lo64; J.hi64 = rq.hi64;
-                    J.lo = rq.lo; J.hi = rq.hi; J.shift = rq.shift; J.tl = rq.tl; J.th = rq.th; J.tl2 = rq.tl2; J.th2 = rq.th2;
-                    J.dir[0] = rq.dir[0]; J.dir[1] = rq.dir[1]; J.thr[0] = rq.thr[0]; J.thr[1] = rq.thr[1];
-                    J.rc[0] = rq.rc[0]; J.rc[1] = rq.rc[1]; J.k[0] = rq.k[0]; J.k[1] = rq.k[1];
-                    J.ca[0] = rq.ca[0]; J.ca[1] = rq.ca[1]; J.cb[0] = rq.cb[0]; J.cb[1] = rq.cb[1];
-                    J.tails = rq.tails; J.degenerate = rq.degenerate;
-                    J.q_a[0] = Q.a[0]; J.q_a[1] = Q.a[1]; J.q_m[0] = Q.m[0]; J.q_m[1] = Q.m[1];
-                }
-                __syncthreads();
-                window_pass(S, ps, win, scr, hits, hit_cap, pass_phase);
-                pass_phase ^= 1u;
-                if (warp == w && lane == l) rs = ps.job.rs;
-                __syncthreads();              // the owner has its results before the next owner overwrites the slot
-            }
-        }
-        const long long tk3 = clock64();
-        // ---- rewards of the envs that had a pass; reward sums ----
-        if (slow_lane) {
-            sdc::reward_finish(S, env, rq, rs, M, en, alt3, Q, r3);
-            reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
-            reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
-            a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
-        }
+        const long long tk3 = tk2c;
+        // ---- reward sums (the envs priced by a pass CTA add theirs there) ----
         if (have_unit) {
             const double m_sum = warp_sum((double)r3[0] + r3[1] + r3[2]), m_ls = warp_sum((double)r3[0]), m_dc = warp_sum((double)r3[1]);
             if (lane == 0) {
@@ -1084,6 +1086,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
                 __syncthreads();
                 window_pass(S, ps, win, scr, hits, hit_cap, pass_phase);
                 pass_phase ^= 1u;
+                if (threadIdx.x == 0 && ps.job.finish) finish_step(S, a, ps.job);
             } else {
                 pregen_one_env(S, env, runbuf, rsh);
                 __syncthreads();
