@@ -730,23 +730,28 @@ SDC_HD void edit_apply(float* B, const ListEdit& ed) {
 }
 
 // first / last: B[0], B[m-1] (cached by the caller)
-SDC_HD void list_remove(const float* B, int& a, int& m, float o, float first, float last, ListEdit& ed, int& err) {
+// hint_rm: find_equal's answer when the caller already has it (the CUDA kernel searches warp-cooperatively), kNoHint otherwise
+constexpr int kNoHint = -2;
+SDC_HD void list_remove(const float* B, int& a, int& m, float o, float first, float last, ListEdit& ed, int& err, int hint_rm = kNoHint) {
     if (m == 0) { err |= SDC_F_BRACKET; return; }
     if (o < first) { a -= 1; return; }
     if (o > last) return;
-    const int i = find_equal(B, m, o);
+    const int i = hint_rm != kNoHint ? hint_rm : find_equal(B, m, o);
     if (i == m) { err |= SDC_F_BRACKET; return; }
     ed.rm = i;
     m -= 1;
 }
 
 // m: length after the removal; k_after: rank that must stay inside the list (chooses the side to drop from when the list is full)
-SDC_HD void list_insert(const float* B, int& a, int& m, float e, int n_after, int k_after, float first, float last, ListEdit& ed) {
+// hint_pos: the number of values <= e in R when the caller already has it, kNoHint otherwise
+SDC_HD void list_insert(const float* B, int& a, int& m, float e, int n_after, int k_after, float first, float last, ListEdit& ed,
+                        int hint_pos = kNoHint) {
     if (ed.rm >= 0 && m > 0) { first = removed_at(B, ed.rm, 0); last = removed_at(B, ed.rm, m - 1); }
     if (m > 0 && e < first && a > 0) { a += 1; return; }
     if (m > 0 && e > last && a + m < n_after - 1) return;           // ranks above the list, list not at the top
     // e belongs inside the list (or extends a list that reaches the end of the window): position after ties in R
     int lo = 0, hi = m;
+    if (hint_pos != kNoHint) lo = hi = hint_pos;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (removed_at(B, ed.rm, mid) <= e) lo = mid + 1; else hi = mid; }
     const int pos = lo;
     if (m == kListCap) {
@@ -771,8 +776,15 @@ SDC_HD void list_insert(const float* B, int& a, int& m, float e, int n_after, in
 // invariant, and a fresh window -- whose spread is a tiny fraction of the energy itself, so that z = (E - mean) / std
 // amplifies the storage rounding of absolute values -- is represented (nearly) exactly.  On return `energy` is the
 // relative value, which is what reward_finish prices.
-SDC_HDN void reward_prepare(const State& S, int env, double& energy, int len, int head, float evicted, QView& Q, ScanRequest& rq,
-                            ListEdit* edits) {
+// Two halves so that the CUDA kernel can run the searches inside the brackets (the evicted value's index, the new value's
+// position: a chain of dependent round trips for a single lane) with the whole warp in between:
+//   reward_prepare_a  window append, the cached ends of both brackets, which lists need a search (PrepState::search)
+//   reward_prepare_c  bracket updates (with the searches' answers as hints, or searching itself), quartiles, fences
+struct PrepState { float first[2], last[2]; uint32_t fc; int err; int search[2]; };
+struct ListHints { int rm[2], pos[2]; };
+
+SDC_HDN void reward_prepare_a(const State& S, int env, double& energy, int len, int head, float evicted, const QView& Q, ScanRequest& rq,
+                              PrepState& ps) {
     int err = 0;
     double ref = S.hist_ref[env];
     if (len == 0) { ref = (fabs(energy) <= 3.0e38) ? energy : 0.0; S.hist_ref[env] = ref; }
@@ -788,15 +800,26 @@ SDC_HDN void reward_prepare(const State& S, int env, double& energy, int len, in
     S.hist_len[env] = len; S.hist_head[env] = head;
     const int n = len;
     rq.n = n; rq.degenerate = 0; rq.e = e; rq.o = o; rq.evict = evict;
-    const uint32_t fc = S.fast_cfg[env];
+    ps.fc = S.fast_cfg[env];
     // The ends of both brackets are read together, before any store to the lists: almost every step only compares
     // against them (each a dependent L2 / DRAM round trip otherwise).
-    float first[2], last[2];
     for (int j = 0; j < 2; ++j) {
         const int m = Q.m[j];
-        first[j] = m > 0 ? Q.lst[j][0] : 0.f;
-        last[j] = m > 0 ? Q.lst[j][m - 1] : 0.f;
+        ps.first[j] = m > 0 ? Q.lst[j][0] : 0.f;
+        ps.last[j] = m > 0 ? Q.lst[j][m - 1] : 0.f;
+        // bit 0: the evicted value lies inside the list (its index is needed); bit 1: so does the new one (its position)
+        ps.search[j] = m > 0 ? ((evict && o >= ps.first[j] && o <= ps.last[j]) ? 1 : 0) | ((e >= ps.first[j] && e <= ps.last[j]) ? 2 : 0) : 0;
     }
+    ps.err = err;
+}
+
+SDC_HDN void reward_prepare_c(const State& S, int env, QView& Q, ScanRequest& rq, ListEdit* edits, const PrepState& ps, const ListHints& hints) {
+    int err = ps.err;
+    const int n = rq.n;
+    const float e = rq.e, o = rq.o;
+    const bool evict = rq.evict != 0;
+    const uint32_t fc = ps.fc;
+    const float* first = ps.first; const float* last = ps.last;
     double qv[2] = {0.0, 0.0};
     for (int j = 0; j < 2; ++j) {
         float* lst = Q.lst[j];
@@ -808,9 +831,9 @@ SDC_HDN void reward_prepare(const State& S, int env, double& energy, int len, in
         rq.k[j] = k;
         ListEdit& ed = edits[j];
         ed.rm = -1; ed.drop = 0; ed.ins = -1; ed.val = 0.f; ed.m0 = m;
-        if (evict) list_remove(lst, a, m, o, first[j], last[j], ed, err);
+        if (evict) list_remove(lst, a, m, o, first[j], last[j], ed, err, hints.rm[j]);
         if (m == 0 && ed.rm < 0) { ed.ins = 0; ed.val = e; a = 0; m = 1; }   // first value ever
-        else list_insert(lst, a, m, e, n, k, first[j], last[j], ed);
+        else list_insert(lst, a, m, e, n, k, first[j], last[j], ed, hints.pos[j]);
         const bool plain = edit_trivial(ed);                     // contents unchanged: the cached ends are valid
         if (n >= 2) {
             const int r = k - a;
@@ -844,6 +867,15 @@ SDC_HDN void reward_prepare(const State& S, int env, double& energy, int len, in
     rq.shift = (float)(0.5 * (qv[0] + qv[1]));
     rq.degenerate = (qv[0] == qv[1]);
     if (err) flag_error(S, env, err);
+}
+
+// serial statement (host build)
+SDC_HDN void reward_prepare(const State& S, int env, double& energy, int len, int head, float evicted, QView& Q, ScanRequest& rq,
+                            ListEdit* edits) {
+    PrepState ps;
+    reward_prepare_a(S, env, energy, len, head, evicted, Q, rq, ps);
+    ListHints h; h.rm[0] = h.rm[1] = h.pos[0] = h.pos[1] = kNoHint;
+    reward_prepare_c(S, env, Q, rq, edits, ps, h);
 }
 
 // Incremental side of the normaliser: updates the window moments, the tail bands and the far-tail aggregates with
@@ -1244,6 +1276,7 @@ struct StepArgs {
     unsigned long long* hvac_hist;      // [SDC_HVAC_BINS] counts of positive HVAC power samples
     float hvac_bins_per_kw;             // SDC_HVAC_BINS / range
     unsigned long long* phase_clocks;   // optional [16]: summed per-warp clock64 deltas of the k_step phases (diagnostics)
+    uint32_t* unit_log;                 // optional [units][8]: per-unit phase clocks, SM id, start time (diagnostics, with phase_clocks)
     unsigned long long* pass_total;     // [4] running totals of ctr[4..7] (window passes: plain, refresh, by brackets, by tails)
     int32_t unit_envs, blocks_per_sm;
 };

@@ -634,7 +634,7 @@ __device__ __forceinline__ void reset_one_env(const sdc::State& S, int env, cons
 // =================================================================================================
 // k_reset: explicit resets (sdc_reset), one CTA per listed env
 // =================================================================================================
-__global__ void __launch_bounds__(kResetThreads) k_reset(const sdc::State S, const int32_t* __restrict__ list,
+__global__ void __launch_bounds__(kResetThreads) k_reset(const __grid_constant__ sdc::State S, const int32_t* __restrict__ list,
                                                          const int32_t* __restrict__ count, float* obs, float* share) {
     extern __shared__ double runbuf[];              // [run_buf_doubles] walk values inside the episode window / 30-day slice
     __shared__ ResetShared sh;
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(kResetThreads) k_reset(const sdc::State S, con
 // =================================================================================================
 // k_step
 // =================================================================================================
-__global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, const StepArgs a, const int n_unit_ctas, const int hit_cap,
+__global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant__ sdc::State S, const __grid_constant__ StepArgs a, const int n_unit_ctas, const int hit_cap,
                                                           const int table_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -709,6 +709,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         const int env = env0 + lane;
         const bool active = have_unit && lane < U && env < N;
         const long long tk0 = clock64();
+        const unsigned long long t_unit0 = a.unit_log ? gtime_ns() : 0ull;
+        unsigned n_edits = 0;                           // diagnostics: bracket edits | band edits << 8 | passes asked << 16
         sdc::StepResult st;
         sdc::ObsDeferred od;
         sdc::RewardInputs en;
@@ -716,6 +718,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         sdc::ScanResult rs;
         sdc::Moments M;
         sdc::QView Q;
+        sdc::PrepState prep; prep.search[0] = prep.search[1] = 0; prep.err = 0; prep.fc = 0u;
+        prep.first[0] = prep.first[1] = prep.last[0] = prep.last[1] = 0.f;
         sdc::ListEdit edits[2];
         edits[0].rm = edits[1].rm = -1; edits[0].drop = edits[1].drop = 0; edits[0].ins = edits[1].ins = -1;
         edits[0].val = edits[1].val = 0.f; edits[0].m0 = edits[1].m0 = 0;
@@ -735,8 +739,9 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         sdc::BandPlan bp; bp.rm[0] = bp.rm[1] = bp.ins[0] = bp.ins[1] = 0;
         sdc::BandDone bd; bd.rm[0] = bd.rm[1] = bd.pos[0] = bd.pos[1] = -1;
         prefetch_env(S, T, env, active, 3);
+        int2 qa = make_int2(0, 0), qm = make_int2(0, 0);
         if (active) {
-            const int2 qa = reinterpret_cast<const int2*>(S.q_a)[env], qm = reinterpret_cast<const int2*>(S.q_m)[env];
+            qa = reinterpret_cast<const int2*>(S.q_a)[env]; qm = reinterpret_cast<const int2*>(S.q_m)[env];
             {
                 const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
                 GlobalInfoSink info{a.info, N, env};
@@ -749,10 +754,49 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
             }
             tk1 = clock64();
             Q.a[0] = qa.x; Q.a[1] = qa.y; Q.m[0] = qm.x; Q.m[1] = qm.y;
-            if (S.append_history) {                    // utils/reward_creator.py:62-63: only default_ls_reward grows the window
-                sdc::reward_prepare(S, env, en.energy, st.hist_len, st.hist_head, st.evicted, Q, rq, edits);   // en.energy -> relative
-                sdc::reward_plan_a(S, env, rq, M, bp);
+            if (S.append_history)                      // utils/reward_creator.py:62-63: only default_ls_reward grows the window
+                sdc::reward_prepare_a(S, env, en.energy, st.hist_len, st.hist_head, st.evicted, Q, rq, prep);   // en.energy -> relative
+        }
+        __syncwarp();
+        // A sample that leaves / enters INSIDE a bracket (~2.4 % per env and list) needs its index / position in the sorted
+        // list: for the env's lane alone that is a linear search in batches plus a binary search, ~25 dependent round
+        // trips (7.5 k clocks per edit while 31 lanes wait).  The whole warp does it instead: one coalesced load of the
+        // list (four values per lane), a ballot for the evicted value, a ballot count of the values <= the new one.
+        sdc::ListHints hints; hints.rm[0] = hints.rm[1] = hints.pos[0] = hints.pos[1] = sdc::kNoHint;
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+            unsigned need = __ballot_sync(0xffffffffu, active && S.append_history && prep.search[j] != 0);
+            while (need) {
+                const int l = __ffs(need) - 1;
+                need &= need - 1;
+                const int want_rm = __shfl_sync(0xffffffffu, prep.search[j], l) & 1;
+                const float o_l = __shfl_sync(0xffffffffu, rq.o, l), e_l = __shfl_sync(0xffffffffu, rq.e, l);
+                const int m0 = __shfl_sync(0xffffffffu, Q.m[j], l);
+                const float* B = S.qlist + ((size_t)(env0 + l) * 2 + j) * sdc::kListCap;
+                float v[sdc::kListCap / 32];
+#pragma unroll
+                for (int t = 0; t < sdc::kListCap / 32; ++t) { const int i = lane + 32 * t; v[t] = i < m0 ? B[i] : SDC_INF_F; }
+                int rm = -1;
+                if (want_rm) {
+                    rm = m0;                           // not found: list_remove flags the bracket
+#pragma unroll
+                    for (int t = sdc::kListCap / 32 - 1; t >= 0; --t) {
+                        const unsigned hit = __ballot_sync(0xffffffffu, lane + 32 * t < m0 && v[t] == o_l);
+                        if (hit) rm = 32 * t + __ffs(hit) - 1;
+                    }
+                }
+                int pos = 0;
+#pragma unroll
+                for (int t = 0; t < sdc::kListCap / 32; ++t) {
+                    const int i = lane + 32 * t;
+                    pos += __popc(__ballot_sync(0xffffffffu, i < m0 && i != rm && v[t] <= e_l));
+                }
+                if (lane == l) { hints.rm[j] = want_rm ? rm : sdc::kNoHint; hints.pos[j] = pos; }
             }
+        }
+        if (active && S.append_history) {
+            sdc::reward_prepare_c(S, env, Q, rq, edits, prep, hints);
+            sdc::reward_plan_a(S, env, rq, M, bp);
         }
         __syncwarp();
         // Planned bracket edits (a value entered / left inside a bracket: ~10 % of the env-steps) are applied by the whole
@@ -760,6 +804,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {
             unsigned need = __ballot_sync(0xffffffffu, active && !sdc::edit_trivial(edits[j]));
+            n_edits += __popc(need);
             while (need) {
                 const int l = __ffs(need) - 1;
                 need &= need - 1;
@@ -784,6 +829,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
 #pragma unroll 1
         for (int sd = 0; sd < 2; ++sd) {
             unsigned need = __ballot_sync(0xffffffffu, active && (bp.rm[sd] | bp.ins[sd]));
+            n_edits += __popc(need) << 8;
             while (need) {
                 const int l = __ffs(need) - 1;
                 need &= need - 1;
@@ -837,6 +883,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
         const bool async_lane = wants_pass && !slow_lane;
         {
             const unsigned slow = __ballot_sync(0xffffffffu, wants_pass);
+            n_edits += __popc(slow) << 16;
             const unsigned n_refresh = __popc(__ballot_sync(0xffffffffu, active && rq.kind == sdc::SCAN_REFRESH));
             const unsigned n_lists = __popc(__ballot_sync(0xffffffffu, active && (rq.rc[0] || rq.rc[1])));
             const unsigned n_tails = __popc(__ballot_sync(0xffffffffu, active && rq.kind == sdc::SCAN_REFRESH && !M.ok && rq.tails));
@@ -1025,7 +1072,13 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const sdc::State S, co
             atomicAdd(a.phase_clocks + 4, 1ull);                              // units
             atomicMax(a.phase_clocks + 14, gtime_ns());                       // timeline: last unit done
             atomicMax(a.phase_clocks + 10, (unsigned long long)(tk4 - tk0));  // slowest unit (clocks)
-            atomicMax(a.phase_clocks + 11, (unsigned long long)(tk2c - tk0)); // slowest unit before the barrier
+            atomicMax(a.phase_clocks + 11, (unsigned long long)(tk2c - tk0)); // slowest unit up to its observations
+            if (a.unit_log) {
+                unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                uint32_t* L = a.unit_log + (size_t)unit * 8;
+                L[0] = (uint32_t)(tk1 - tk0); L[1] = (uint32_t)(tk2 - tk1); L[2] = (uint32_t)(tk2b - tk2); L[3] = (uint32_t)(tk2c - tk2b);
+                L[4] = (uint32_t)(tk4 - tk2c); L[5] = smid | ((uint32_t)blockIdx.x << 16); L[6] = (uint32_t)(t_unit0 & 0xffffffffu); L[7] = n_edits;
+            }
         }
     }
 
@@ -1113,7 +1166,7 @@ __global__ void k_build_reset_list(int n_envs, const uint8_t* __restrict__ mask,
 // k_rebuild: exact brackets from a full sort (prefill / resume / debug cross-check)
 // =================================================================================================
 constexpr int kSortThreads = 512;
-__global__ void __launch_bounds__(kSortThreads) k_rebuild(const sdc::State S) {
+__global__ void __launch_bounds__(kSortThreads) k_rebuild(const __grid_constant__ sdc::State S) {
     extern __shared__ float buf[];                  // next pow2 >= hist_cap floats
     const int env = blockIdx.x;
     const int n = S.hist_len[env];

@@ -20,7 +20,7 @@ _STATE_DTYPES = {
     "t_min": np.float64, "t_max": np.float64, "weather": np.float64, "ls_head": np.int32, "ls_len": np.int32,
     "ls_sum": np.int32, "ls_bins": np.uint16, "ls_ring": np.uint8, "setpoint": np.float64, "dc_run": np.int32,
     "dc_scale": np.int32, "dc_last": np.int8, "bat_load": np.float64, "hist": np.float32, "hist_ref": np.float64, "hist_len": np.int32,
-    "hist_head": np.int32, "phase_clocks": np.uint64, "qlist": np.float32, "q_a": np.int32, "q_m": np.int32, "err": np.int32,
+    "hist_head": np.int32, "phase_clocks": np.uint64, "unit_log": np.uint32, "qlist": np.float32, "q_a": np.int32, "q_m": np.int32, "err": np.int32,
     "mom_s1": np.float64, "mom_s2": np.float64, "mom_c0": np.float64, "tails": np.float32, "tail_n": np.int32, "tail_nb": np.int32, "tail_bs": np.float64,
     "tail_thr": np.float32, "agg_n": np.int32, "agg_s": np.float64, "fast_cfg": np.uint32, "counters": np.int32, "pass_stats": np.int32, "pass_total": np.uint64,
     "pend_valid": np.uint8, "pend_weather": np.float64, "cur_buf": np.uint8, "pend_obs": np.float32, "metrics": np.float64, "hvac_hist": np.uint64,
@@ -269,6 +269,8 @@ class Engine:
                    "tail_n": 2, "tail_nb": 2, "tail_bs": 4, "tail_thr": 4, "agg_n": 2, "agg_s": 4, "tails": 2 * _lib.TAIL_CAP}.get(name, 1)
         if name == "phase_clocks":
             out = np.zeros(16, dt)
+        elif name == "unit_log":
+            out = np.zeros(((n + 7) // 8) * 8, dt)
         elif name == "counters":
             out = np.zeros(64, dt)
         elif name in ("pass_stats", "pass_total"):
@@ -283,6 +285,8 @@ class Engine:
         out = out[:got // dt.itemsize]
         if name in ("phase_clocks", "counters", "pass_stats", "pass_total", "metrics", "hvac_hist"):
             return out
+        if name == "unit_log":
+            return out.reshape(-1, 8)
         if name == "tails":
             return out.reshape(n, 2, _lib.TAIL_CAP)              # [env][side][slot], each band sorted ascending
         return out.reshape(n, -1) if out.size != n else out
