@@ -276,8 +276,8 @@ SDC_HDN void emit_obs_rows(double cos_h, double sin_h, double w, double w_next, 
 // All trace reads are issued first, in one straight-line batch, so that their memory latencies overlap: a dependent
 // global read costs ~1-2 us under load (profiles/r01_summary.md).
 template <class Sink>
-SDC_HDN void build_obs(const State& S, const Tables& T, int env, int t, const LsStats& ls, double soc, const Norms& nm, Sink& sink) {
-    const LocTables& L = T.loc[S.loc_id[env]];
+SDC_HDN void build_obs(const State& S, const Tables& T, int env, int t, const LsStats& ls, double soc, const Norms& nm, Sink& sink, int loc = -1) {
+    const LocTables& L = T.loc[loc >= 0 ? loc : S.loc_id[env]];     // callers that already know the location pass it (one dependent load less)
     const double w = L.workload[t], w_next = L.workload[t + 1];
     const int hq = t % 96;
     const double cos_h = S.hour_cos[hq], sin_h = S.hour_sin[hq];
@@ -320,7 +320,7 @@ struct StepResult {
 };
 
 // What the observation builder needs from the scalar phase (the observations are built after the normaliser).
-struct ObsDeferred { LsStats ls; double soc; Norms nm; int tn; };
+struct ObsDeferred { LsStats ls; double soc; Norms nm; int tn; int loc; };
 
 // The part of StepResult the reward needs (kept small: it lives in registers across the window passes).
 struct RewardInputs { double energy, nci_next, ls_penalty; };
@@ -369,7 +369,8 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
     nm.cmin = S.ci_min[env]; nm.crng = S.ci_max[env] - nm.cmin;
     nm.tmin = S.t_min[env]; nm.trng = S.t_max[env] - nm.tmin; nm.wrel = weather_cur(S, env) - t0;
     const int h_len = S.hist_len[env], h_head = S.hist_head[env];
-    const LocTables& L = T.loc[S.loc_id[env]];
+    const int loc = S.loc_id[env];
+    const LocTables& L = T.loc[loc];
     const sdc_dc_params& P = T.dc[S.cfg_id[env]];
     // ---- level 2: reads whose address depends on level 1 ----
     const int q = t;                                     // quarter-hour stamp == trace index
@@ -583,7 +584,7 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
     const int step_in_ep = step0 + 1;
     S.t[env] = tn; S.step_in_ep[env] = step_in_ep;
     const int terminal = step_in_ep >= S.ep_len;
-    od.ls = ls; od.soc = soc; od.nm = nm; od.tn = tn;
+    od.ls = ls; od.soc = soc; od.nm = nm; od.tn = tn; od.loc = loc;
     const double inv_crng = 1.0 / nm.crng;
     const double nci_next = (ci_fut[0] - nm.cmin) * inv_crng;
     info(I_OUTSIDE_TEMP, (float)outside_next); info(I_DAY, (float)(tn / 96)); info(I_HOUR, (float)((tn % 96) * 0.25));
@@ -604,7 +605,7 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
 // Observations of the step (sustaindc_env.py:578-582), from what physics_step left in `od`.
 template <class ObsSink>
 SDC_HDN void emit_obs(const State& S, const Tables& T, int env, const ObsDeferred& od, ObsSink& obs) {
-    build_obs(S, T, env, od.tn, od.ls, od.soc, od.nm, obs);
+    build_obs(S, T, env, od.tn, od.ls, od.soc, od.nm, obs, od.loc);
 }
 
 // ---- reward normaliser (utils/reward_creator.py:16-45) without a window pass per step ----------
@@ -783,8 +784,16 @@ SDC_HD void list_insert(const float* B, int& a, int& m, float e, int n_after, in
 struct PrepState { float first[2], last[2]; uint32_t fc; int err; int search[2]; };
 struct ListHints { int rm[2], pos[2]; };
 
+// bracket ends, for callers that want them in flight early (the CUDA kernel loads them before the physics)
+SDC_HD void load_list_ends(const QView& Q, PrepState& ps) {
+    for (int j = 0; j < 2; ++j) {
+        const int m = Q.m[j];
+        ps.first[j] = m > 0 ? Q.lst[j][0] : 0.f;
+        ps.last[j] = m > 0 ? Q.lst[j][m - 1] : 0.f;
+    }
+}
 SDC_HDN void reward_prepare_a(const State& S, int env, double& energy, int len, int head, float evicted, const QView& Q, ScanRequest& rq,
-                              PrepState& ps) {
+                              PrepState& ps, bool ends_loaded = false) {
     int err = 0;
     double ref = S.hist_ref[env];
     if (len == 0) { ref = (fabs(energy) <= 3.0e38) ? energy : 0.0; S.hist_ref[env] = ref; }
@@ -803,10 +812,9 @@ SDC_HDN void reward_prepare_a(const State& S, int env, double& energy, int len, 
     ps.fc = S.fast_cfg[env];
     // The ends of both brackets are read together, before any store to the lists: almost every step only compares
     // against them (each a dependent L2 / DRAM round trip otherwise).
+    if (!ends_loaded) load_list_ends(Q, ps);
     for (int j = 0; j < 2; ++j) {
         const int m = Q.m[j];
-        ps.first[j] = m > 0 ? Q.lst[j][0] : 0.f;
-        ps.last[j] = m > 0 ? Q.lst[j][m - 1] : 0.f;
         // bit 0: the evicted value lies inside the list (its index is needed); bit 1: so does the new one (its position)
         ps.search[j] = m > 0 ? ((evict && o >= ps.first[j] && o <= ps.last[j]) ? 1 : 0) | ((e >= ps.first[j] && e <= ps.last[j]) ? 2 : 0) : 0;
     }
@@ -956,10 +964,10 @@ SDC_HDN void reward_plan_c(const State& S, int env, ScanRequest& rq, Moments& M,
         int err = 0;
         int n[2] = {S.tail_n[2 * env], S.tail_n[2 * env + 1]}, nb[2] = {S.tail_nb[2 * env], S.tail_nb[2 * env + 1]};
         double b1[2] = {S.tail_bs[4 * env], S.tail_bs[4 * env + 2]}, b2[2] = {S.tail_bs[4 * env + 1], S.tail_bs[4 * env + 3]};
+        float near_lo[2][2];           // per side: the band values just below / at the split, loaded together (see below)
 #pragma unroll
         for (int sd = 0; sd < 2; ++sd) {
             const bool below = sd == 0;
-            const float* p = tail_ptr(S, env, sd);
             // bookkeeping of the edits phase B applied: the lower band's beyond-set is its first nb values, the upper band's its last nb
             if (bp.rm[sd]) {
                 if (bd.rm[sd] < 0) { err |= SDC_F_BRACKET; valid = false; }
@@ -975,16 +983,43 @@ SDC_HDN void reward_plan_c(const State& S, int env, ScanRequest& rq, Moments& M,
                     n[sd] += 1;
                 }
             }
-            // the values the fence crossed since the last step (usually none or one)
+        }
+        // The values the fence crossed since the last step (usually none or one).  The two band values on either side of each
+        // split decide the common case; all four are loaded before any of them is used (four dependent round trips otherwise).
+        if (valid) {
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+                const float* p = tail_ptr(S, env, sd);
+                const int s = sd == 0 ? nb[sd] : n[sd] - nb[sd];                 // first index past (lower) / of (upper) the beyond-set
+                near_lo[sd][0] = s > 0 ? p[s - 1] : 0.f;
+                near_lo[sd][1] = s < n[sd] ? p[s] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            const bool below = sd == 0;
+            const float* p = tail_ptr(S, env, sd);
             const double fence = below ? rq.lo64 : rq.hi64;
             if (valid) {
                 if (below) {
-                    while (nb[sd] > 0 && !((double)p[nb[sd] - 1] < fence)) { nb[sd] -= 1; const double y = (double)p[nb[sd]] - c0; b1[sd] -= y; b2[sd] = fma(-y, y, b2[sd]); }
-                    while (nb[sd] < n[sd] && (double)p[nb[sd]] < fence) { const double y = (double)p[nb[sd]] - c0; b1[sd] += y; b2[sd] = fma(y, y, b2[sd]); nb[sd] += 1; }
+                    int k = nb[sd];
+                    if (k > 0 && !((double)near_lo[sd][0] < fence)) {
+                        k -= 1; { const double y = (double)near_lo[sd][0] - c0; b1[sd] -= y; b2[sd] = fma(-y, y, b2[sd]); }
+                        while (k > 0 && !((double)p[k - 1] < fence)) { k -= 1; const double y = (double)p[k] - c0; b1[sd] -= y; b2[sd] = fma(-y, y, b2[sd]); }
+                    } else if (k < n[sd] && (double)near_lo[sd][1] < fence) {
+                        { const double y = (double)near_lo[sd][1] - c0; b1[sd] += y; b2[sd] = fma(y, y, b2[sd]); } k += 1;
+                        while (k < n[sd] && (double)p[k] < fence) { const double y = (double)p[k] - c0; b1[sd] += y; b2[sd] = fma(y, y, b2[sd]); k += 1; }
+                    }
+                    nb[sd] = k;
                 } else {
                     int sx = n[sd] - nb[sd];                                     // first index of the beyond-set
-                    while (sx < n[sd] && !((double)p[sx] > fence)) { const double y = (double)p[sx] - c0; b1[sd] -= y; b2[sd] = fma(-y, y, b2[sd]); sx += 1; }
-                    while (sx > 0 && (double)p[sx - 1] > fence) { sx -= 1; const double y = (double)p[sx] - c0; b1[sd] += y; b2[sd] = fma(y, y, b2[sd]); }
+                    if (sx < n[sd] && !((double)near_lo[sd][1] > fence)) {
+                        { const double y = (double)near_lo[sd][1] - c0; b1[sd] -= y; b2[sd] = fma(-y, y, b2[sd]); } sx += 1;
+                        while (sx < n[sd] && !((double)p[sx] > fence)) { const double y = (double)p[sx] - c0; b1[sd] -= y; b2[sd] = fma(-y, y, b2[sd]); sx += 1; }
+                    } else if (sx > 0 && (double)near_lo[sd][0] > fence) {
+                        sx -= 1; { const double y = (double)near_lo[sd][0] - c0; b1[sd] += y; b2[sd] = fma(y, y, b2[sd]); }
+                        while (sx > 0 && (double)p[sx - 1] > fence) { sx -= 1; const double y = (double)p[sx] - c0; b1[sd] += y; b2[sd] = fma(y, y, b2[sd]); }
+                    }
                     nb[sd] = n[sd] - sx;
                 }
                 if (nb[sd] == 0) { b1[sd] = 0.0; b2[sd] = 0.0; }                 // no rounding residue survives an empty set

@@ -108,6 +108,27 @@ __device__ __forceinline__ int warp_sum(int v) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Sums of 16 values over the warp with 16 shuffles instead of 16 x 5: every exchange step halves the number of values a lane
+// carries (it keeps the half its lane bit selects and receives the partner's copy of that half).  On return lane l holds the
+// warp sum of value (l >> 1) bit-reversed over four bits -- warp_sum16_slot(l) -- in both lanes of a pair.
+__device__ __forceinline__ double warp_sum16(double (&v)[16], int lane) {
+#pragma unroll
+    for (int step = 0; step < 4; ++step) {
+        const int half = 8 >> step;                    // values kept after this step
+        const bool up = (lane >> (4 - step)) & 1;      // lane bit 4, 3, 2, 1
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double send = up ? v[i] : v[i + half];
+            const double keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16 >> step);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+// which of the 16 values lane `lane` ends up with: bit 4 of the lane selects the upper 8, bit 3 the upper 4 of those, ...
+__device__ __forceinline__ int warp_sum16_slot(int lane) {
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -654,6 +675,14 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
     // location / dc-parameter tables -> shared memory (removes one level of pointer chasing per env)
     sdc::Tables T{S.loc, S.dc};
     __shared__ PassShared ps;
+    // The first unit of this warp is known here: its normaliser-side reads (which need no table) are put in flight before
+    // the CTA waits for the table copy below.
+    bool early_prefetch = false;
+    if (blockIdx.x < n_unit_ctas) {
+        const int unit = blockIdx.x * kWarpsPerBlock + warp;
+        const int env = unit * U + lane;
+        if (unit * U < S.n_envs) { prefetch_env(S, T, env, lane < U && env < S.n_envs, 2); early_prefetch = true; }
+    }
     {
         const int loc_bytes = S.n_loc * (int)sizeof(sdc::LocTables), dc_bytes = S.n_cfg * (int)sizeof(sdc_dc_params);
         if (loc_bytes + dc_bytes <= table_bytes) {
@@ -738,10 +767,12 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
         float alt3[3] = {0.f, 0.f, 0.f};
         sdc::BandPlan bp; bp.rm[0] = bp.rm[1] = bp.ins[0] = bp.ins[1] = 0;
         sdc::BandDone bd; bd.rm[0] = bd.rm[1] = bd.pos[0] = bd.pos[1] = -1;
-        prefetch_env(S, T, env, active, 3);
-        int2 qa = make_int2(0, 0), qm = make_int2(0, 0);
+        prefetch_env(S, T, env, active, early_prefetch ? 1 : 3);
+        early_prefetch = false;
         if (active) {
-            qa = reinterpret_cast<const int2*>(S.q_a)[env]; qm = reinterpret_cast<const int2*>(S.q_m)[env];
+            const int2 qa = reinterpret_cast<const int2*>(S.q_a)[env], qm = reinterpret_cast<const int2*>(S.q_m)[env];
+            Q.a[0] = qa.x; Q.a[1] = qa.y; Q.m[0] = qm.x; Q.m[1] = qm.y;
+            if (S.append_history) sdc::load_list_ends(Q, prep);     // in flight during the physics; nothing writes the lists before reward_prepare_c
             {
                 const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
                 GlobalInfoSink info{a.info, N, env};
@@ -753,9 +784,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
                 sdc::alt_rewards(S, env, st.energy, ai, alt3);
             }
             tk1 = clock64();
-            Q.a[0] = qa.x; Q.a[1] = qa.y; Q.m[0] = qm.x; Q.m[1] = qm.y;
             if (S.append_history)                      // utils/reward_creator.py:62-63: only default_ls_reward grows the window
-                sdc::reward_prepare_a(S, env, en.energy, st.hist_len, st.hist_head, st.evicted, Q, rq, prep);   // en.energy -> relative
+                sdc::reward_prepare_a(S, env, en.energy, st.hist_len, st.hist_head, st.evicted, Q, rq, prep, true);   // en.energy -> relative
         }
         __syncwarp();
         // A sample that leaves / enters INSIDE a bracket (~2.4 % per env and list) needs its index / position in the sorted
@@ -763,7 +793,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
         // trips (7.5 k clocks per edit while 31 lanes wait).  The whole warp does it instead: one coalesced load of the
         // list (four values per lane), a ballot for the evicted value, a ballot count of the values <= the new one.
         sdc::ListHints hints; hints.rm[0] = hints.rm[1] = hints.pos[0] = hints.pos[1] = sdc::kNoHint;
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 2; ++j) {
             unsigned need = __ballot_sync(0xffffffffu, active && S.append_history && prep.search[j] != 0);
             while (need) {
@@ -801,7 +831,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
         __syncwarp();
         // Planned bracket edits (a value entered / left inside a bracket: ~10 % of the env-steps) are applied by the whole
         // warp, one env at a time: every lane computes its elements of the edited list from the old one, then stores them.
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 2; ++j) {
             unsigned need = __ballot_sync(0xffffffffu, active && !sdc::edit_trivial(edits[j]));
             n_edits += __popc(need);
@@ -826,7 +856,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
         // The step's sample entering / the evicted one leaving a tail band (~2 % of the env-steps): sorted removal / insertion
         // by the whole warp -- every lane holds four band slots, ballots find the evicted value and count the values <= the
         // new one (insertion after ties), then the edited band is written back like a bracket.
-#pragma unroll 1
+#pragma unroll
         for (int sd = 0; sd < 2; ++sd) {
             unsigned need = __ballot_sync(0xffffffffu, active && (bp.rm[sd] | bp.ins[sd]));
             n_edits += __popc(need) << 8;
@@ -934,9 +964,9 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
         if (have_unit) {
             // logger sums (harl/envs/sustaindc/sustaindc_logger.py:86-101): warp reduce, one atomic per metric.  Done while
             // the step's results are still in registers (after the long observation code they come back from spills).
-            double m[13];
+            double m[16];
 #pragma unroll
-            for (int k = 0; k < 13; ++k) m[k] = 0.0;
+            for (int k = 0; k < 16; ++k) m[k] = 0.0;
             if (active) {
                 m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
                 m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
@@ -950,11 +980,9 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
             constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
                                       sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
                                       sdc::M_OVERDUE, sdc::M_TOTAL_KW};
-#pragma unroll
-            for (int k = 0; k < 13; ++k) {
-                const double v = warp_sum(m[k]);
-                if (lane == 0) atomicAdd(a.metrics + slot[k], v);
-            }
+            const double tot = warp_sum16(m, lane);              // lane l: the sum of metric warp_sum16_slot(l)
+            const int k = warp_sum16_slot(lane);
+            if (!(lane & 1) && k < 13) atomicAdd(a.metrics + slot[k], tot);
         }
         {
             // Observation rows go through a shared-memory tile (odd row stride: conflict-free) and leave as contiguous
