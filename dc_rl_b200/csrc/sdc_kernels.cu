@@ -767,6 +767,21 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
         float alt3[3] = {0.f, 0.f, 0.f};
         sdc::BandPlan bp; bp.rm[0] = bp.rm[1] = bp.ins[0] = bp.ins[1] = 0;
         sdc::BandDone bd; bd.rm[0] = bd.rm[1] = bd.pos[0] = bd.pos[1] = -1;
+        // the unit's 96 action ids as three contiguous 128-byte rows (they may sit in pinned host memory: a host call without
+        // an H2D copy), handed to their lanes by shuffles
+        int a_ls = 0, a_dc = 0, a_bat = 0;
+        {
+            int raw[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const size_t i = (size_t)env0 * 3 + lane + 32 * k; raw[k] = i < (size_t)N * 3 ? a.actions[i] : 0; }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int e = 3 * lane + c, from = e & 31, k = e >> 5;
+                const int v0 = __shfl_sync(0xffffffffu, raw[0], from), v1 = __shfl_sync(0xffffffffu, raw[1], from), v2 = __shfl_sync(0xffffffffu, raw[2], from);
+                const int v = k == 0 ? v0 : (k == 1 ? v1 : v2);
+                if (c == 0) a_ls = v; else if (c == 1) a_dc = v; else a_bat = v;
+            }
+        }
         prefetch_env(S, T, env, active, early_prefetch ? 1 : 3);
         early_prefetch = false;
         if (active) {
@@ -774,7 +789,6 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
             Q.a[0] = qa.x; Q.a[1] = qa.y; Q.m[0] = qm.x; Q.m[1] = qm.y;
             if (S.append_history) sdc::load_list_ends(Q, prep);     // in flight during the physics; nothing writes the lists before reward_prepare_c
             {
-                const int a_ls = a.actions[env * 3 + 0], a_dc = a.actions[env * 3 + 1], a_bat = a.actions[env * 3 + 2];
                 GlobalInfoSink info{a.info, N, env};
                 sdc::physics_step(S, T, env, a_ls, a_dc, a_bat, info, st, od);
             }
@@ -908,6 +922,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
         // record goes to a global queue served by whichever CTA is free.  Only the rare env that cannot price this step
         // without the window keeps the CTA-synchronous path.
         const bool wants_pass = active && rq.kind != sdc::SCAN_SKIP;
+        // the window of an env that asks for a pass is on its way into L2 before a worker CTA picks the job up
+        if (wants_pass) l2_prefetch_bulk(S.hist + (size_t)env * S.hist_cap, ((unsigned)rq.n * 4u + 15u) & ~15u);
         const bool moments_needed = rq.n >= 2 && !rq.degenerate;
         const bool slow_lane = wants_pass && ((moments_needed && !M.ok) || rq.dir[0] || rq.dir[1]);
         const bool async_lane = wants_pass && !slow_lane;
@@ -930,11 +946,10 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
         if (active) {
             const int kind = rq.kind;
             if (!slow_lane) {
-                rq.kind = sdc::SCAN_SKIP;          // no pass results to apply: price the step from the incremental state
-                sdc::reward_finish(S, env, rq, rs, M, en, alt3, Q, r3);
+                // the bracket cursors are final here (pricing from the incremental state does not move them) and must be in
+                // memory before the pass is published: a re-centring pass overwrites them
                 reinterpret_cast<int2*>(S.q_a)[env] = make_int2(Q.a[0], Q.a[1]);
                 reinterpret_cast<int2*>(S.q_m)[env] = make_int2(Q.m[0], Q.m[1]);
-                a.rew[env * 3 + 0] = r3[0]; a.rew[env * 3 + 1] = r3[1]; a.rew[env * 3 + 2] = r3[2];
             }
             if (wants_pass) {
                 // Publish the pass: record first, then its tag.  The pass CTA rewrites q_a / q_m / brackets / bands / moments of
@@ -957,6 +972,21 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
                 reinterpret_cast<PassJob*>(reinterpret_cast<unsigned char*>(a.pass_jobs) + (size_t)idx * sdc::kPassJobBytes)[0] = J;
                 __threadfence();
                 *reinterpret_cast<volatile int32_t*>(a.pass_ready + idx) = a.seq;
+            }
+            if (!slow_lane) {
+                rq.kind = sdc::SCAN_SKIP;          // no pass results to apply: price the step from the incremental state
+                sdc::reward_finish(S, env, rq, rs, M, en, alt3, Q, r3);
+            }
+        }
+        {
+            // rewards leave as three contiguous 128-byte rows per unit (the rows may be pinned host memory, where 4-byte
+            // stores at a 12-byte stride are three partial writes per sector); the slots of envs priced by a pass CTA are skipped
+            const unsigned own = __ballot_sync(0xffffffffu, active && !slow_lane);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int idx = lane + 32 * k, src = idx / 3, comp = idx - 3 * src;
+                const float v0 = __shfl_sync(0xffffffffu, r3[0], src), v1 = __shfl_sync(0xffffffffu, r3[1], src), v2 = __shfl_sync(0xffffffffu, r3[2], src);
+                if ((own >> src) & 1u) a.rew[(size_t)env0 * 3 + idx] = comp == 0 ? v0 : (comp == 1 ? v1 : v2);
             }
         }
         const long long tk2b = clock64();

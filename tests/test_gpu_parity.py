@@ -90,15 +90,16 @@ def test_state_blob_roundtrip(lib):
 
 
 def test_host_buffer_modes_agree(lib):
-    """sdc_step_host on the handle's pinned buffers: kernel stores straight into host memory (direct_host = 3, default),
-    staged device buffers + D2H (0), and caller-owned pageable arrays all return the same step results."""
+    """sdc_step_host on the handle's pinned buffers: every output stored by the kernel straight into host memory and the
+    actions read from there (direct_host = 31, default), observations only (3), rewards / dones too (15), staged device
+    buffers + copies (0), and caller-owned pageable arrays all return the same step results."""
     import ctypes as C
     from dc_rl_b200.dc_config import size_datacenter
     from dc_rl_b200.engine import Engine, _ptr
     from replay import location_traces
     N = 700
     outs = []
-    for mode in (3, 0, "own"):
+    for mode in (31, 3, 15, 0, "own"):
         eng = Engine(N, [location_traces("az")], [size_datacenter("az")[0]], months=np.arange(N) % 12,
                      seeds=np.arange(N, dtype=np.uint64) + 3, days_per_episode=1, lib=lib)
         if mode != "own":
