@@ -209,7 +209,8 @@ static_assert(sizeof(PassJob) <= sdc::kPassJobBytes && sdc::kPassJobBytes % 16 =
 struct PassShared {
     unsigned long long bar;                 // mbarrier of the bulk copy
     PassJob job;
-    int fill[5];                            // slots handed out: lower band, upper band, collect list 0, collect list 1, hit list
+    int fill[5];                            // slots handed out: lower band, upper band, collect list 0, collect list 1, (unused)
+    int bkt_cnt[64], bkt_off[64], bkt_fill[64];   // bucket sort of the collected values: population, first slot, next free slot
     int band_pn[kWarpsPerBlock];            // rebuilt bands: per-warp partials of the values beyond the fence (count, sums about
     double band_p1[kWarpsPerBlock], band_p2[kWarpsPerBlock];   // the new centre); warps 0-3 lower band, 4-7 upper band
     float red_f[kWarpsPerBlock][4];         // s1, s2, ext0, ext1
@@ -242,7 +243,8 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uns
 // env's band arrays) with the far-tail aggregates, all values inside the re-centring intervals of the brackets (into
 // `scr`, then sorted) and the single-rank fallback -- then warp 0 commits the env's new incremental state.
 // `win` = hist_cap floats of shared memory.  Called by all threads of the CTA; `phase` = parity of the mbarrier.
-__device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, float* win, float* scr, float* hits, int hit_cap, unsigned phase) {
+__device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, float* win, float* scr, float* hits, int hit_cap, unsigned phase,
+                                         uint32_t* clk_log = nullptr) {
     float* band_scr = scr + 2 * sdc::kCollectCap;                        // [2][kTailCap] band values, sorted by warps 0 / 1 below
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PassJob& J = ps.job;
@@ -272,8 +274,10 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
     int cnt0 = 0, cnt1 = 0, below0 = 0, below1 = 0, far_n0 = 0, far_n1 = 0;
     float ext0 = dir0 == sdc::SCAN_ABOVE ? SDC_INF_F : -SDC_INF_F, ext1 = dir1 == sdc::SCAN_ABOVE ? SDC_INF_F : -SDC_INF_F;
     double far_a0 = 0.0, far_b0 = 0.0, far_a1 = 0.0, far_b1 = 0.0;
+    const long long tp0 = clock64();
     if (warp == 0) mbar_wait(&ps.bar, phase);                            // one warp polls; the others sleep at the barrier
     __syncthreads();                                                     // the window is in shared memory, fill[] zeroed
+    const long long tp1 = clock64();
     // Per value: accumulate + one combined "is it interesting" test.  The rare hits (a few hundred of 10 000) are only
     // parked in a shared-memory list inside the loop -- with ~5 % hits nearly every warp iteration contains one, and a
     // divergent 80-instruction classification per iteration tripled the cost of the scan -- and classified densely
@@ -293,23 +297,51 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
         if (x >= ca0 && x <= cb0) { const int pos = atomicAdd(&ps.fill[2], 1); if (pos < sdc::kCollectCap) scr[pos] = x; }
         if (x >= ca1 && x <= cb1) { const int pos = atomicAdd(&ps.fill[3], 1); if (pos < sdc::kCollectCap) scr[sdc::kCollectCap + pos] = x; }
     };
-#pragma unroll 4
-    for (int i = tid; i < n; i += kStepThreads) {
-        const float x = win[i];
-        const float d = fminf(fmaxf(x, lo), hi) - shift;
-        s1 += d; s2 = fmaf(d, d, s2);
-        if (refresh) { const double y = (double)x - c0; S1 += y; S2 = fma(y, y, S2); }
-        below0 += x < ca0; below1 += x < ca1;
-        if (x < quiet_lo || x > quiet_hi || (x >= ca0 && x <= cb0) || (x >= ca1 && x <= cb1)) {
-            const int pos = atomicAdd(&ps.fill[4], 1);
-            if (pos < hit_cap) hits[pos] = x; else classify(x);
+    // Every warp parks its hits in its own slice of the list: the slot is the warp's running count plus the lane's rank among
+    // the hitting lanes of this iteration (a ballot and a popcount) -- a shared counter bumped by an atomic per hit made ~80 %
+    // of the iterations wait for a shared-memory atomic round trip and was 40 % of a pass.
+    const int warp_cap = hit_cap / kWarpsPerBlock;
+    float* my_hits = hits + warp * warp_cap;
+    int n_mine = 0;                                                      // warp-uniform
+    // four consecutive values per thread and trip (one 128-bit shared-memory load; the four values' arithmetic is independent,
+    // which is what an in-order warp needs: the scan was bound by ~10 cycles per dependent instruction, not by issue slots)
+    const int n_iter = (n + 4 * kStepThreads - 1) / (4 * kStepThreads);
+#pragma unroll 2
+    for (int it = 0; it < n_iter; ++it) {
+        const int i0 = (tid + it * kStepThreads) * 4;
+        float xs[4] = {shift, shift, shift, shift};
+        if (i0 < n) { const float4 v = *reinterpret_cast<const float4*>(win + i0); xs[0] = v.x; xs[1] = v.y; xs[2] = v.z; xs[3] = v.w; }
+        bool hit[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float x = xs[q];
+            const bool in = i0 + q < n;
+            if (in) {
+                const float d = fminf(fmaxf(x, lo), hi) - shift;
+                s1 += d; s2 = fmaf(d, d, s2);
+                if (refresh) { const double y = (double)x - c0; S1 += y; S2 = fma(y, y, S2); }
+                below0 += x < ca0; below1 += x < ca1;
+            }
+            hit[q] = in && (x < quiet_lo || x > quiet_hi || (x >= ca0 && x <= cb0) || (x >= ca1 && x <= cb1));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned hm = __ballot_sync(0xffffffffu, hit[q]);
+            if (hm) {
+                if (hit[q]) {
+                    const int pos = n_mine + __popc(hm & ((1u << lane) - 1u));
+                    if (pos < warp_cap) my_hits[pos] = xs[q]; else classify(xs[q]);
+                }
+                n_mine += __popc(hm);
+            }
         }
     }
-    __syncthreads();
+    __syncwarp();
+    const long long tp2 = clock64();
     {
-        const int n_hits = min(ps.fill[4], hit_cap);
+        const int n_hits = min(n_mine, warp_cap);
 #pragma unroll 1
-        for (int i = tid; i < n_hits; i += kStepThreads) classify(hits[i]);
+        for (int i = lane; i < n_hits; i += 32) classify(my_hits[i]);
     }
     // ---- block reduction: warp shuffles, then the per-warp partials through shared memory ----
     s1 = warp_sum(s1); s2 = warp_sum(s2);
@@ -329,6 +361,7 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
         ps.red_i[warp][4] = far_n0; ps.red_i[warp][5] = far_n1;
     }
     __syncthreads();                                                     // partials + all band / collect stores visible
+    const long long tp3 = clock64();
     // Rebuilt bands: rank sort (thread i places value i of its band: the rank is the number of smaller values plus equal ones
     // before it; broadcast reads of shared memory, no barrier) into the free hit list, 128 threads per band, and the split
     // at the requesting step's fence: count and sums about the new centre of the values beyond it (per-warp partials, summed
@@ -384,18 +417,54 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
                 // rank sort of the collected values (typically ~250): every thread places up to two of them; one pass over
                 // the c values per element with broadcast reads and no barrier (a bitonic network needs 36-45 CTA barriers,
                 // which is what a pass's latency was made of)
+                // Bucket sort: 64 equal value buckets over [ca, cb] (the values are spread smoothly over this narrow interval),
+                // population count, prefix, scatter into bucket order, then the rank inside the bucket by comparing with the
+                // bucket's ~4-10 members only -- a plain rank sort compares with all c (c^2 / 256 per thread: a fifth of a pass).
                 const float* buf = scr + j * sdc::kCollectCap;
                 float* out = win + j * sdc::kCollectCap;              // the staged window is no longer needed
-                for (int me = tid; me < c; me += kStepThreads) {
-                    const float x = buf[me];
-                    int r = 0;
-#pragma unroll 4
-                    for (int i = 0; i < c; ++i) { const float y = buf[i]; r += (y < x) | ((y == x) & (i < me)); }
+                float* grp = hits + 2 * sdc::kTailCap;                // [kCollectCap] the values grouped by bucket (after the sorted bands)
+                const float ca = J.ca[j], cb = J.cb[j];
+                const float scale = cb > ca ? 64.f / (cb - ca) : 0.f;
+                if (tid < 64) ps.bkt_cnt[tid] = 0;
+                __syncthreads();
+                float myx[2] = {0.f, 0.f}; int myb[2] = {-1, -1};
+                static_assert(sdc::kCollectCap <= 2 * kStepThreads, "two collected values per thread");
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int me = tid + q * kStepThreads;
+                    if (me < c) {
+                        const float x = buf[me];
+                        myx[q] = x; myb[q] = min(63, max(0, (int)((x - ca) * scale)));
+                        atomicAdd(&ps.bkt_cnt[myb[q]], 1);
+                    }
+                }
+                __syncthreads();
+                if (warp == 0) {                                      // exclusive prefix over the 64 populations, two per lane
+                    const int c0b = ps.bkt_cnt[2 * lane], c1b = ps.bkt_cnt[2 * lane + 1];
+                    int incl = c0b + c1b;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+                    const int excl = incl - (c0b + c1b);
+                    ps.bkt_off[2 * lane] = excl; ps.bkt_off[2 * lane + 1] = excl + c0b;
+                    ps.bkt_fill[2 * lane] = excl; ps.bkt_fill[2 * lane + 1] = excl + c0b;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < 2; ++q) if (myb[q] >= 0) grp[atomicAdd(&ps.bkt_fill[myb[q]], 1)] = myx[q];
+                __syncthreads();
+                for (int g = tid; g < c; g += kStepThreads) {
+                    const float x = grp[g];
+                    const int b = min(63, max(0, (int)((x - ca) * scale)));
+                    const int b_lo = ps.bkt_off[b], b_hi = ps.bkt_fill[b];
+                    int r = b_lo;
+                    for (int i = b_lo; i < b_hi; ++i) { const float y = grp[i]; r += (y < x) | ((y == x) & (i < g)); }
                     out[r] = x;
                 }
             }
         }
         __syncthreads();
+        const long long tp4 = clock64();
+        if (clk_log && tid == 0) { clk_log[0] = (uint32_t)(tp1 - tp0); clk_log[1] = (uint32_t)(tp2 - tp1); clk_log[2] = (uint32_t)(tp3 - tp2); clk_log[3] = (uint32_t)(tp4 - tp3); clk_log[5] = (uint32_t)raw.c[0] | ((uint32_t)raw.c[1] << 16); }
         if (warp == 0) {
             sdc::ScanRequest rl;
             rl.n = n; rl.kind = J.kind; rl.shift = shift; rl.tl = tl; rl.th = th; rl.tl2 = tl2; rl.th2 = th2;
@@ -420,6 +489,7 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
     }
     if (tid == 0) ps.job.rs = rs;
     __syncthreads();                                                     // results visible; `win`, `scr`, partials free again
+    if (clk_log && tid == 0) { clk_log[4] = (uint32_t)(clock64() - tp0); clk_log[6] = (uint32_t)J.kind | ((uint32_t)J.tails << 8) | ((uint32_t)J.rc[0] << 16) | ((uint32_t)J.rc[1] << 17); }
 }
 
 // The env of a finish job could not price its step without the window (a bracket ran out on one side, or the bands no
@@ -1195,7 +1265,10 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
                 int* dst = reinterpret_cast<int*>(&ps.job);
                 for (int i = threadIdx.x; i < (int)(sizeof(PassJob) / 4); i += kStepThreads) dst[i] = __ldcg(src + i);
                 __syncthreads();
-                window_pass(S, ps, win, scr, hits, hit_cap, pass_phase);
+                // diagnostics: the phases of pass job `env` (a ticket index) go to the upper half of the unit log
+                uint32_t* clk_log = (a.unit_log && env < 4096) ? a.unit_log + ((size_t)(((S.n_envs + 7) / 8) / 2) + env) * 8 : nullptr;
+                if (clk_log && (size_t)(clk_log - a.unit_log) + 8 > (size_t)((S.n_envs + 7) / 8) * 8) clk_log = nullptr;
+                window_pass(S, ps, win, scr, hits, hit_cap, pass_phase, clk_log);
                 pass_phase ^= 1u;
                 if (threadIdx.x == 0 && ps.job.finish) finish_step(S, a, ps.job);
             } else {
@@ -1280,7 +1353,7 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     const size_t tile_floats = (size_t)kWarpsPerBlock * 32 * kTileStride;
     size_t smem_floats = pass_floats > tile_floats ? pass_floats : tile_floats;
     const int hit_cap = (int)(smem_floats - pass_floats);
-    if (hit_cap < 2 * sdc::kTailCap) return "k_step: shared memory layout leaves no room for the sorted bands";
+    if (hit_cap < 2 * sdc::kTailCap + sdc::kCollectCap) return "k_step: shared memory layout leaves no room for the sorted bands and the bucket order";
     size_t smem = smem_floats * sizeof(float);
     if (smem < run_buf_bytes(S)) smem = run_buf_bytes(S);                              // reset workers reuse the region
     // shared-memory copy of the location / dc parameter tables: only what this handle needs

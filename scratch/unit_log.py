@@ -46,3 +46,15 @@ for rep in range(3):
         one.sum(), tot[one].mean() if one.any() else 0, L[one, 0].mean() if one.any() else 0, (~one).sum(), tot[~one].mean(), L[~one, 0].mean()))
     worst = np.argsort(-tot)[:8]
     for u in worst: print("   slow unit %4d sm %3d cta %3d: %s edits %d/%d/%d start %d" % (u, sm[u], cta[u], L[u, :5].tolist(), ne[u], nb[u], npass[u], start[u]))
+# phases of the window passes of the last step (upper half of the log: one row per pass ticket)
+Lp = eng.read_state("unit_log")
+half = len(Lp) // 2
+P = Lp[half:half + 4096].astype(np.int64)
+P = P[P[:, 4] > 0]
+if len(P):
+    print("passes logged %d: total clk mean %.0f | TMA wait %.0f  scan %.0f  classify+reduce %.0f  band sort + rank sorts %.0f  commit %.0f | collected c0 mean %.0f c1 mean %.0f" % (
+        len(P), P[:, 4].mean(), P[:, 0].mean(), P[:, 1].mean(), P[:, 2].mean(), P[:, 3].mean(), (P[:, 4] - P[:, :4].sum(1)).mean(),
+        (P[:, 5] & 0xffff)[(P[:, 5] & 0xffff) > 0].mean() if ((P[:, 5] & 0xffff) > 0).any() else 0, (P[:, 5] >> 16)[(P[:, 5] >> 16) > 0].mean() if ((P[:, 5] >> 16) > 0).any() else 0))
+    kinds = P[:, 6]
+    for lab, m in (("re-centre list 0 only", ((kinds >> 16) & 3) == 1), ("list 1 only", ((kinds >> 16) & 3) == 2), ("both lists", ((kinds >> 16) & 3) == 3), ("no list (bands only)", ((kinds >> 16) & 3) == 0)):
+        if m.any(): print("   %-22s %4d passes, total %.0f, sorts %.0f, tails rebuilt in %d" % (lab, m.sum(), P[m, 4].mean(), P[m, 3].mean(), (((kinds[m] >> 8) & 0xff) > 0).sum()))
