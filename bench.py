@@ -60,36 +60,61 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML in-process (no fork next to the launching
+    thread; `sample_now` is also called by the main thread right after the timed launches are enqueued, i.e. while the GPU
+    executes them, so that even a 20-step region has a sample from inside it), nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+        self.index, self.stop_flag, self.rows, self.lock = index, threading.Event(), [], threading.Lock()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
+        except Exception:
+            self.nv = None
+
+    def sample_now(self):
+        try:
+            if self.nv:
+                nv, h = self.nv
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = int(get(h))
+                bits = (0x8, 0x40, 0x20, 0x4)           # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+                row = [str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for b in bits]
+            else:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if not out:
+                    return
+                row = [x.strip() for x in out.split(",")]
+            with self.lock:
+                self.rows.append(row)
+        except Exception:
+            pass
 
     def run(self):
         while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.05)
+            self.sample_now()
+            self.stop_flag.wait(0.02 if self.nv else 0.05)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"]}
         sm = sorted(float(r[0]) for r in self.rows)
         reasons = []
         for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
             if any(r[3 + i].lower().startswith("active") for r in self.rows):
                 reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.nv else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -318,6 +343,8 @@ def main():
             ev[i + 1].record(stream)
             if args.config == 4 and (i + 1) % 1024 == 0:
                 gather_metrics()
+        if sampler:
+            sampler.sample_now()          # the launches above are enqueued, the GPU is executing them
         gather_metrics()
         barrier()
         total_ms = ev[0].elapsed_time(ev[-1])

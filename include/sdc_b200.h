@@ -227,8 +227,10 @@ int64_t sdc_launch_count(sdc_env* env);
  * out[0] = number of timed steps, out[1] = sum of k_step ms, out[2] = 0 (episode resets run inside k_step),
  * out[3] = max k_step ms, and clears the accumulators. */
 int sdc_kernel_times(sdc_env* env, double* out4);
-/* knobs: "unit_envs" (8 / 16 / 32), "blocks_per_sm", "timing", "phases" (diagnostic clocks), "direct_host" (bit 0 obs, 1 share,
- * 2 terminal rows written by the kernel straight into the handle's pinned buffers), "lazy_info" */
+/* knobs: "unit_envs" (8 / 16 / 32), "blocks_per_sm", "timing", "phases" (diagnostic clocks + per-unit / per-pass log),
+ * "direct_host" (host calls on the handle's pinned buffers: bit 0 obs / compact obs, 1 share, 2 terminal rows, 3 rewards + dones
+ * written by the kernel straight into them, 4 actions read from there; default 31 = a host step is one launch and one stream
+ * synchronisation, no copy operation), "lazy_info", "clear_pass_total" */
 int sdc_set_tuning(sdc_env* env, const char* key, int32_t value);
 
 #ifdef __cplusplus
