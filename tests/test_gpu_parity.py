@@ -37,6 +37,16 @@ def test_golden_replay_batched_ragged(lib, n_envs, unit):
     assert w["obs"] <= 1e-6 and w["term_obs"] <= 1e-6 and w["info"] <= 1e-6 and w["rew"] <= 1e-4, w
 
 
+def test_golden_replay_more_units_than_one_resident_round(lib):
+    """20 000 envs at 8 envs per warp are 2 500 units: more than the 2 072 unit warps of one resident grid, so the first
+    round takes its units from the grid slots and the rest from the ticket counter.  Every env replays the same golden
+    trajectory (first episode boundary included) and must agree with it."""
+    from replay import replay
+    w = replay("wa_m9_s3", lib, n_envs=20000, unit_envs=8, max_steps=200)
+    assert w["err_flags"] == 0
+    assert w["obs"] <= 1e-6 and w["term_obs"] <= 1e-6 and w["info"] <= 1e-6 and w["rew"] <= 1e-4, w
+
+
 def test_long_replay_window_saturates(lib):
     """11 000 steps: the 10 000-sample reward window fills, wraps, and the rolling quartile brackets stay exact."""
     from replay import replay
