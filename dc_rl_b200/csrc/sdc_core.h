@@ -356,7 +356,7 @@ SDC_HD void alt_rewards(const State& S, int env, double energy, const AltInputs&
 // reward normaliser).  InfoSink: void operator()(int col, float v).
 template <class InfoSink>
 SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, int a_dc, int a_bat, InfoSink& info,
-                          StepResult& out, ObsDeferred& od) {
+                          StepResult& out, ObsDeferred& od, bool load_evicted = true) {
     // ---- level 1: every per-env scalar, issued back to back (no stores in between) ----
     const int t = S.t[env], t0 = S.t0[env], step0 = S.step_in_ep[env];
     int head = S.ls_head[env], len = S.ls_len[env], sum = S.ls_sum[env];
@@ -385,7 +385,10 @@ SDC_HDN void physics_step(const State& S, const Tables& T, int env, int a_ls, in
 #pragma unroll
     for (int i = 0; i < 8; ++i) ci_fut[i] = L.ci[t + 2 + i];
     out.hist_len = h_len; out.hist_head = h_head;
-    out.evicted = S.hist[(size_t)env * S.hist_cap + h_head];
+    // The sample the window append will evict: a DRAM miss whose value this function would have to STORE into `out` right
+    // away (an output struct passed by reference lives in memory) -- the CUDA kernel reads it after the physics instead, from
+    // the L2 line its prefetch brought in.
+    out.evicted = load_evicted ? S.hist[(size_t)env * S.hist_cap + h_head] : 0.f;
     int err = 0;
     if (t + 18 > SDC_YEAR_STEPS) err |= SDC_F_TRACE_DOMAIN;    // the reference crashes here
     // Out-of-range action ids saturate to {0, 2}.  All branches below test the RAW ids and the reported

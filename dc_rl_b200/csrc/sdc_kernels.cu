@@ -164,6 +164,11 @@ __device__ __forceinline__ void prefetch_env(const sdc::State& S, const sdc::Tab
     prefetch_line(S.hist + (size_t)env * S.hist_cap + hh);
     prefetch_line(L.ci + t - 16); prefetch_line(L.ci + t); prefetch_line(L.ci + t + 9);
     prefetch_line(L.workload + t); prefetch_line(L.ns + t); prefetch_line(L.sh + t);
+    if (S.step_in_ep[env] + 1 >= S.ep_len) {          // the env finishes in this step: its reset reads the staged episode
+        const float* po = S.pend_obs + (size_t)env * kObsRow;
+        prefetch_line(po); prefetch_line(po + 32); prefetch_line(po + 64); prefetch_line(po + kObsRow - 1);
+        prefetch_line(S.pend_tmin + env); prefetch_line(S.pend_tmax + env); prefetch_line(S.pend_day + env); prefetch_line(S.pend_hour + env);
+    }
     }
     if (!(what & 2)) return;
     // reward normaliser: the bracket positions it will look at and the rows of the two tail bands
@@ -860,7 +865,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
             if (S.append_history) sdc::load_list_ends(Q, prep);     // in flight during the physics; nothing writes the lists before reward_prepare_c
             {
                 GlobalInfoSink info{a.info, N, env};
-                sdc::physics_step(S, T, env, a_ls, a_dc, a_bat, info, st, od);
+                sdc::physics_step(S, T, env, a_ls, a_dc, a_bat, info, st, od, false);
+                st.evicted = S.hist[(size_t)env * S.hist_cap + st.hist_head];     // prefetched into L2 at the start of the unit
             }
             en.energy = st.energy; en.nci_next = st.nci_next; en.ls_penalty = st.ls_penalty;
             if (sdc::any_alt_reward(S)) {
