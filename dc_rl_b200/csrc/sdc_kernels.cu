@@ -90,7 +90,7 @@ static void range_pop() { nvtxRangePop(); }
 constexpr int kStepThreads = 256;
 constexpr int kWarpsPerBlock = kStepThreads / 32;
 constexpr int kObsRow = 3 * SDC_OBS_DIM;          // 78 floats per env
-constexpr int kTileStride = kObsRow + 1;          // odd row stride of the shared-memory observation tile
+constexpr int kTileStride = SDC_OBS_COMPACT;      // the shared-memory observation tile holds COMPACT rows (29 floats: odd stride, conflict-free)
 constexpr int kTableBytes = 8192;                 // shared-memory copy of the location / dc parameter tables
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -565,6 +565,30 @@ struct RowSink {
     float* row;
     __device__ __forceinline__ void operator()(int agent, int idx, float v) { row[agent * SDC_OBS_DIM + idx] = v; }
 };
+// Keeps only the 29 distinct values of the three rows (agent_ls[26] | agent_dc[11] | agent_dc[13] | agent_bat[12], see
+// sdc::compact_to_padded): every other dc / bat entry repeats an agent_ls entry or is padding.  The call sites pass constant
+// (agent, idx), so the dropped stores vanish at compile time.
+struct CompactSink {
+    float* row;
+    __device__ __forceinline__ void operator()(int agent, int idx, float v) {
+        if (agent == 0) row[idx] = v;
+        else if (agent == 1 && idx == 11) row[26] = v;
+        else if (agent == 1 && idx == 13) row[27] = v;
+        else if (agent == 2 && idx == 12) row[28] = v;
+    }
+};
+// column of the zero-padded [3][26] row -> compact column, -1 = padding zero (inverse of sdc::compact_to_padded plus the repeats)
+__host__ __device__ constexpr int padded_to_compact(int col) {
+    return col < 26 ? col
+         : col < 52 ? (col - 26 < 10 ? col - 26 : (col - 26 == 10 ? 13 : (col - 26 == 11 ? 26 : (col - 26 == 12 ? 14 : (col - 26 == 13 ? 27 : -1)))))
+                    : (col - 52 < 10 ? col - 52 : (col - 52 == 10 ? 13 : (col - 52 == 11 ? 14 : (col - 52 == 12 ? 28 : -1))));
+}
+// One env's rows from its COMPACT row (shared memory): padded obs, HARL shared row, compact row.  p2c: padded_to_compact as a table.
+__device__ __forceinline__ void store_env_rows_compact(const float* crow, int env, const OutPtrs& o, int t, int n_thr, const signed char* p2c) {
+    if (o.obs) for (int k = t; k < kObsRow; k += n_thr) { const int c = p2c[k]; o.obs[(size_t)env * kObsRow + k] = c >= 0 ? crow[c] : 0.f; }
+    if (o.share) for (int k = t; k < SDC_SHARE_DIM; k += n_thr) o.share[(size_t)env * SDC_SHARE_DIM + k] = k < 28 ? crow[k] : 0.f;
+    if (o.obs_c) for (int k = t; k < SDC_OBS_COMPACT; k += n_thr) o.obs_c[(size_t)env * SDC_OBS_COMPACT + k] = crow[k];
+}
 
 struct ResetShared {
     double red[kResetThreads / 32];
@@ -750,6 +774,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
     // location / dc-parameter tables -> shared memory (removes one level of pointer chasing per env)
     sdc::Tables T{S.loc, S.dc};
     __shared__ PassShared ps;
+    __shared__ signed char p2c[kObsRow + 2];               // padded column -> compact column (-1: padding zero)
+    if (threadIdx.x < kObsRow) p2c[threadIdx.x] = (signed char)padded_to_compact(threadIdx.x);
     // The first unit of this warp is known here: its normaliser-side reads (which need no table) are put in flight before
     // the CTA waits for the table copy below.
     bool early_prefetch = false;
@@ -1002,7 +1028,6 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
         if (wants_pass) l2_prefetch_bulk(S.hist + (size_t)env * S.hist_cap, ((unsigned)rq.n * 4u + 15u) & ~15u);
         const bool moments_needed = rq.n >= 2 && !rq.degenerate;
         const bool slow_lane = wants_pass && ((moments_needed && !M.ok) || rq.dir[0] || rq.dir[1]);
-        const bool async_lane = wants_pass && !slow_lane;
         {
             const unsigned slow = __ballot_sync(0xffffffffu, wants_pass);
             n_edits += __popc(slow) << 16;
@@ -1091,12 +1116,13 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
             if (!(lane & 1) && k < 13) atomicAdd(a.metrics + slot[k], tot);
         }
         {
-            // Observation rows go through a shared-memory tile (odd row stride: conflict-free) and leave as contiguous
-            // 128-bit stores; 107 scattered 4-byte stores per env would keep the LSU busy for ~50 k cycles per unit.
-            // The tile shares its memory with the window-pass buffers (used only after the barrier below).
+            // The 29 distinct observation values of every env go through a shared-memory tile of compact rows (odd row stride:
+            // conflict-free) and leave as contiguous 128-bit stores: the padded [3][26] rows and the shared row are column
+            // selections of the compact row (p2c table), the compact output IS the tile.  A 29-column tile instead of a
+            // 79-column one is what lets the kernel run with 54 KB of shared memory per CTA, i.e. with twice the L1.
             float* tile = reinterpret_cast<float*>(smem_raw + table_bytes) + (size_t)warp * 32 * kTileStride;
             if (active) {
-                RowSink sink{tile + lane * kTileStride};
+                CompactSink sink{tile + lane * kTileStride};
                 sdc::emit_obs(S, T, env, od, sink);
                 a.done[env] = (uint8_t)finished;
             }
@@ -1109,43 +1135,38 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
                     for (int i = lane; i < total / 4; i += 32) {
                         float v[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) { const int f = 4 * i + q; const int e = f / kObsRow; v[q] = tile[e * kTileStride + (f - e * kObsRow)]; }
+                        for (int q = 0; q < 4; ++q) {
+                            const int f = 4 * i + q; const int e = f / kObsRow; const int c = p2c[f - e * kObsRow];
+                            v[q] = c >= 0 ? tile[e * kTileStride + c] : 0.f;
+                        }
                         dst4[i] = make_float4(v[0], v[1], v[2], v[3]);
                     }
-                    for (int f = (total & ~3) + lane; f < total; f += 32) { const int e = f / kObsRow; a.obs[(size_t)env0 * kObsRow + f] = tile[e * kTileStride + (f - e * kObsRow)]; }
+                    for (int f = (total & ~3) + lane; f < total; f += 32) {
+                        const int e = f / kObsRow; const int c = p2c[f - e * kObsRow];
+                        a.obs[(size_t)env0 * kObsRow + f] = c >= 0 ? tile[e * kTileStride + c] : 0.f;
+                    }
                 }
                 if (a.share) {
                     float* dsh = a.share + (size_t)env0 * SDC_SHARE_DIM;
                     for (int f = lane; f < n_here * SDC_SHARE_DIM; f += 32) {
                         const int e = f / SDC_SHARE_DIM, k = f - e * SDC_SHARE_DIM;
-                        const int src = k < 26 ? k : (k == 26 ? SDC_OBS_DIM + 11 : (k == 27 ? SDC_OBS_DIM + 13 : 2 * SDC_OBS_DIM + 25));
-                        dsh[f] = tile[e * kTileStride + src];
+                        dsh[f] = k < 28 ? tile[e * kTileStride + k] : 0.f;      // ls[0:26] | dc[11] | dc[13] | the battery row's padding zero
                     }
                 }
                 if (a.obs_c) {
-                    // compact rows: the 29 distinct observation values per env (no padding, no repeated columns, no shared row) --
-                    // 116 B instead of the 428 B of obs + share, which is what a host caller pays for over PCIe
+                    // compact rows: 116 B instead of the 428 B of obs + share, which is what a host caller pays for over the host
+                    // link -- the tile's own layout, copied as it is
                     const int total = n_here * SDC_OBS_COMPACT;
                     float4* dst4 = reinterpret_cast<float4*>(a.obs_c + (size_t)env0 * SDC_OBS_COMPACT);   // env0 * 29 * 4 B: 16-byte aligned for env0 % 4 == 0
-                    for (int i = lane; i < total / 4; i += 32) {
-                        float v[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int f = 4 * i + q; const int e = f / SDC_OBS_COMPACT;
-                            v[q] = tile[e * kTileStride + sdc::compact_to_padded(f - e * SDC_OBS_COMPACT)];
-                        }
-                        dst4[i] = make_float4(v[0], v[1], v[2], v[3]);
-                    }
-                    for (int f = (total & ~3) + lane; f < total; f += 32) {
-                        const int e = f / SDC_OBS_COMPACT;
-                        a.obs_c[(size_t)env0 * SDC_OBS_COMPACT + f] = tile[e * kTileStride + sdc::compact_to_padded(f - e * SDC_OBS_COMPACT)];
-                    }
+                    const float4* src4 = reinterpret_cast<const float4*>(tile);                             // warp * 32 * 29 * 4 B: 16-byte aligned
+                    for (int i = lane; i < total / 4; i += 32) dst4[i] = src4[i];
+                    for (int f = (total & ~3) + lane; f < total; f += 32) a.obs_c[(size_t)env0 * SDC_OBS_COMPACT + f] = tile[f];
                 }
                 unsigned fin = __ballot_sync(0xffffffffu, finished != 0);
                 while (fin && (a.term_obs || a.term_c)) {
                     const int l = __ffs(fin) - 1;
                     fin &= fin - 1;
-                    store_env_rows(tile + l * kTileStride, env0 + l, OutPtrs{a.term_obs, nullptr, a.term_c}, lane, 32);
+                    store_env_rows_compact(tile + l * kTileStride, env0 + l, OutPtrs{a.term_obs, nullptr, a.term_c}, lane, 32, p2c);
                 }
             }
         }
@@ -1357,7 +1378,9 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     // observation tiles (whatever they leave beyond scratch + window is the hit list).
     const size_t pass_floats = (size_t)2 * sdc::kCollectCap + 2 * sdc::kTailCap + (S.hist_cap > 2 * sdc::kCollectCap ? S.hist_cap : 2 * sdc::kCollectCap);
     const size_t tile_floats = (size_t)kWarpsPerBlock * 32 * kTileStride;
-    size_t smem_floats = pass_floats > tile_floats ? pass_floats : tile_floats;
+    constexpr size_t kHitFloats = 2048;            // parked hits of a pass (256 per warp; overflow is classified in place), then the sorted
+                                                   // bands + the bucket order of the collected values
+    size_t smem_floats = pass_floats + kHitFloats > tile_floats ? pass_floats + kHitFloats : tile_floats;
     const int hit_cap = (int)(smem_floats - pass_floats);
     if (hit_cap < 2 * sdc::kTailCap + sdc::kCollectCap) return "k_step: shared memory layout leaves no room for the sorted bands and the bucket order";
     size_t smem = smem_floats * sizeof(float);
