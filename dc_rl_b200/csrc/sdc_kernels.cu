@@ -1102,18 +1102,20 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
                 m[0] = st.energy; m[1] = st.co2; m[2] = st.water; m[3] = st.tasks_in_queue; m[4] = st.tasks_dropped;
                 m[5] = st.ite_kw; m[6] = st.ct_kw; m[7] = st.comp_kw; m[8] = st.hvac_kw; m[9] = 1.0; m[10] = st.terminal;
                 m[11] = st.overdue; m[12] = st.total_kw;
+                // reward sums ride along (the envs priced by a pass CTA contribute zero here and add theirs there)
+                m[13] = (double)r3[0] + r3[1] + r3[2]; m[14] = (double)r3[0]; m[15] = (double)r3[1];
                 if (st.hvac_kw > 0.0) {             // fire-and-forget reduction; the logger's p90 comes from these bins
                     int bin = (int)(st.hvac_kw * (double)a.hvac_bins_per_kw);
                     bin = bin < 0 ? 0 : (bin >= SDC_HVAC_BINS ? SDC_HVAC_BINS - 1 : bin);
                     atomicAdd(a.hvac_hist + bin, 1ull);
                 }
             }
-            constexpr int slot[13] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
+            constexpr int slot[16] = {sdc::M_ENERGY, sdc::M_CO2, sdc::M_WATER, sdc::M_TASKS_IN_QUEUE, sdc::M_TASKS_DROPPED,
                                       sdc::M_ITE_KW, sdc::M_CT_KW, sdc::M_COMP_KW, sdc::M_HVAC_KW, sdc::M_STEPS, sdc::M_EPISODES,
-                                      sdc::M_OVERDUE, sdc::M_TOTAL_KW};
+                                      sdc::M_OVERDUE, sdc::M_TOTAL_KW, sdc::M_REWARD_SUM, sdc::M_REWARD_LS, sdc::M_REWARD_DC};
             const double tot = warp_sum16(m, lane);              // lane l: the sum of metric warp_sum16_slot(l)
             const int k = warp_sum16_slot(lane);
-            if (!(lane & 1) && k < 13) atomicAdd(a.metrics + slot[k], tot);
+            if (!(lane & 1)) atomicAdd(a.metrics + slot[k], tot);
         }
         {
             // The 29 distinct observation values of every env go through a shared-memory tile of compact rows (odd row stride:
@@ -1172,14 +1174,6 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
         }
         const long long tk2c = clock64();
         const long long tk3 = tk2c;
-        // ---- reward sums (the envs priced by a pass CTA add theirs there) ----
-        if (have_unit) {
-            const double m_sum = warp_sum((double)r3[0] + r3[1] + r3[2]), m_ls = warp_sum((double)r3[0]), m_dc = warp_sum((double)r3[1]);
-            if (lane == 0) {
-                atomicAdd(a.metrics + sdc::M_REWARD_SUM, m_sum); atomicAdd(a.metrics + sdc::M_REWARD_LS, m_ls);
-                atomicAdd(a.metrics + sdc::M_REWARD_DC, m_dc);
-            }
-        }
         // Finished envs.  The normal case: the look-ahead generation of the previous launch staged the next episode WITH its
         // reset observation, and the reset is done right here by the env's own warp -- flip the weather buffer, clear the
         // queue ring, copy the staged observation over the terminal one (which already went to term_obs), reset the
