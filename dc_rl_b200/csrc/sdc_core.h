@@ -1334,10 +1334,12 @@ SDC_HD void share_from_obs(const float* obs78, float* share29) {
 
 // ---- reset of the scalar sub-env state (sustaindc_env.py:436-531) ----------------------------
 // The weather window / norms must already be in place. Set-point and reward window survive.
-SDC_HD void reset_scalars(const State& S, int env, int t0) {
-    const LocTables& L = S.loc[S.loc_id[env]];
+// `Lk`: the env's location tables when the caller has them at hand (the CUDA kernel: its shared-memory copy), else looked up
+SDC_HD void reset_scalars(const State& S, int env, int t0, const LocTables* Lk = nullptr) {
+    const LocTables& L = Lk ? *Lk : S.loc[S.loc_id[env]];
+    const double cmin = L.ci_min30[t0], cmax = L.ci_max30[t0];         // both loads before the first store
     S.t[env] = t0; S.t0[env] = t0; S.step_in_ep[env] = 0;
-    S.ci_min[env] = L.ci_min30[t0]; S.ci_max[env] = L.ci_max30[t0];
+    S.ci_min[env] = cmin; S.ci_max[env] = cmax;
     S.ls_head[env] = t0; S.ls_len[env] = 0; S.ls_sum[env] = 0;
     S.ls_bins[env * 4 + 0] = 0; S.ls_bins[env * 4 + 1] = 0; S.ls_bins[env * 4 + 2] = 0; S.ls_bins[env * 4 + 3] = 0;
     S.dc_run[env] = 0; S.dc_scale[env] = 1; S.dc_last[env] = 2;              // dc_gym.py:114-116

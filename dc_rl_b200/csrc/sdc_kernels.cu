@@ -168,6 +168,7 @@ __device__ __forceinline__ void prefetch_env(const sdc::State& S, const sdc::Tab
         const float* po = S.pend_obs + (size_t)env * kObsRow;
         prefetch_line(po); prefetch_line(po + 32); prefetch_line(po + 64); prefetch_line(po + kObsRow - 1);
         prefetch_line(S.pend_tmin + env); prefetch_line(S.pend_tmax + env); prefetch_line(S.pend_day + env); prefetch_line(S.pend_hour + env);
+        prefetch_line(S.pend_valid + env); prefetch_line(S.episode + env);
     }
     }
     if (!(what & 2)) return;
@@ -1191,12 +1192,20 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
                 uint4* ring = reinterpret_cast<uint4*>(S.ls_ring + (size_t)e * (S.ls_mask + 1));
                 for (int k = lane; k < (S.ls_mask + 1) / 16; k += 32) ring[k] = make_uint4(0u, 0u, 0u, 0u);
                 store_env_rows(S.pend_obs + (size_t)e * kObsRow, e, OutPtrs{a.obs, a.share, a.obs_c}, lane, 32);
+                const int loc_l = __shfl_sync(0xffffffffu, od.loc, l);
                 if (lane == 0) {
-                    S.t_min[e] = S.pend_tmin[e]; S.t_max[e] = S.pend_tmax[e];
-                    S.cur_buf[e] ^= 1;
+                    // every load first (one round trip to lines the unit prefetched), then the stores: loads interleaved with
+                    // stores to arrays the compiler cannot prove distinct run one after the other, and the envs that finish
+                    // are the stragglers of a step
+                    const double tmin = S.pend_tmin[e], tmax = S.pend_tmax[e];
+                    const int pd = S.pend_day[e], ph = S.pend_hour[e];
+                    const uint8_t cb = S.cur_buf[e];
+                    const uint32_t ep = S.episode[e];
+                    S.t_min[e] = tmin; S.t_max[e] = tmax;
+                    S.cur_buf[e] = cb ^ 1;
                     S.pend_valid[e] = 0;
-                    S.episode[e] += 1;
-                    sdc::reset_scalars(S, e, S.pend_day[e] * 96 + S.pend_hour[e] * 4);
+                    S.episode[e] = ep + 1;
+                    sdc::reset_scalars(S, e, pd * 96 + ph * 4, &T.loc[loc_l]);
                 }
             }
             if (__any_sync(0xffffffffu, finished && !fast)) {
