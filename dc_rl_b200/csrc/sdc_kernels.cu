@@ -631,18 +631,42 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
     const int cnt = max(0, min(sdc::kNoiseSeg, n - j0));    // even for every thread (n and the segment length are even)
     const int jw = n - 96 * roll, c_lo = 96 * roll - t0, c_hi = c_lo - n;
     sdc::Pcg32 g = sdc::noise_stream(seed, ep, (uint32_t)tid);
+    // Only ~1 thread in 12 owns a segment with samples inside the kept window: the others run the walk without the position
+    // arithmetic and the conditional store (a third of the loop's instructions).
+    bool keeps = false;
+    {
+        const int lo_a = j0, hi_a = min(j0 + cnt, jw);                 // samples before the wrap: k = j + c_lo
+        const int lo_b = max(j0, jw), hi_b = j0 + cnt;                 // samples after it: k = j + c_hi
+        if (lo_a < hi_a && lo_a + c_lo < k_keep && hi_a - 1 + c_lo >= 0) keeps = true;
+        if (lo_b < hi_b && lo_b + c_hi < k_keep && hi_b - 1 + c_hi >= 0) keeps = true;
+        keeps = __any_sync(0xffffffffu, keeps);                        // per warp: a warp that ran both loops would take twice as long
+    }
+    if (keeps) {
 #pragma unroll 2
-    for (int q = 0; q < cnt; q += 2) {
-        float z[2];
-        const uint32_t a = sdc::pcg32_next(g), b = sdc::pcg32_next(g);
-        sdc::noise_normals2(a, b, z);
+        for (int q = 0; q < cnt; q += 2) {
+            float z[2];
+            const uint32_t a = sdc::pcg32_next(g), b = sdc::pcg32_next(g);
+            sdc::noise_normals2(a, b, z);
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int j = j0 + q + u;
-            run += (double)(0.02f * z[u]);
-            sum_run += run; sum_run2 = fma(run, run, sum_run2);
-            const int k = j + (j >= jw ? c_hi : c_lo);
-            if ((unsigned)k < (unsigned)k_keep) runbuf[k] = run;
+            for (int u = 0; u < 2; ++u) {
+                const int j = j0 + q + u;
+                run += (double)(0.02f * z[u]);
+                sum_run += run; sum_run2 = fma(run, run, sum_run2);
+                const int k = j + (j >= jw ? c_hi : c_lo);
+                if ((unsigned)k < (unsigned)k_keep) runbuf[k] = run;
+            }
+        }
+    } else {
+#pragma unroll 2
+        for (int q = 0; q < cnt; q += 2) {
+            float z[2];
+            const uint32_t a = sdc::pcg32_next(g), b = sdc::pcg32_next(g);
+            sdc::noise_normals2(a, b, z);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                run += (double)(0.02f * z[u]);
+                sum_run += run; sum_run2 = fma(run, run, sum_run2);
+            }
         }
     }
     sh.seg_off[tid] = run;
@@ -671,15 +695,33 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
     // emit: roll, clip, window, 30-day min/max (managers.py:598-608), one window position per thread and trip
     const sdc::LocTables& L = S.loc[S.loc_id[env]];
     double tmin = INFINITY, tmax = -INFINITY;
-    for (int k = tid; k < max(k_keep, S.win_len); k += kResetThreads) {
-        if (k < k_keep) {
-            int j = t0 + k - 96 * roll; if (j < 0) j += n;
-            const double noise = (sh.seg_off[j / sdc::kNoiseSeg] + runbuf[k]) * scale;     // segment offset + position inside it
-            const double vt = fmin(fmax(L.temp_base[j] + noise, 0.0), 45.0);
-            if (k < k_norm) { tmin = fmin(tmin, vt); tmax = fmax(tmax, vt); }
-            if (k < k_win) { wt[k] = vt; ww[k] = fmin(fmax(L.wetb_base[j] + noise, 0.0), 45.0); }
+    // four positions per thread and trip, all trace loads of a trip in flight together (the loop was a chain of ~12 L2 round
+    // trips per thread)
+    constexpr int kEmitUnroll = 4;
+    const int k_max = max(k_keep, S.win_len);
+    for (int kb = tid; kb < k_max; kb += kEmitUnroll * kResetThreads) {
+        double tb[kEmitUnroll], wb[kEmitUnroll], nz[kEmitUnroll];
+#pragma unroll
+        for (int u = 0; u < kEmitUnroll; ++u) {
+            const int k = kb + u * kResetThreads;
+            tb[u] = wb[u] = nz[u] = 0.0;
+            if (k < k_keep) {
+                int j = t0 + k - 96 * roll; if (j < 0) j += n;
+                tb[u] = L.temp_base[j];
+                if (k < k_win) wb[u] = L.wetb_base[j];
+                nz[u] = (sh.seg_off[j / sdc::kNoiseSeg] + runbuf[k]) * scale;     // segment offset + position inside it
+            }
         }
-        if (k >= k_win && k < S.win_len) { wt[k] = 0.0; ww[k] = 0.0; }    // beyond the year end (flagged domain) / padding
+#pragma unroll
+        for (int u = 0; u < kEmitUnroll; ++u) {
+            const int k = kb + u * kResetThreads;
+            if (k < k_keep) {
+                const double vt = fmin(fmax(tb[u] + nz[u], 0.0), 45.0);
+                if (k < k_norm) { tmin = fmin(tmin, vt); tmax = fmax(tmax, vt); }
+                if (k < k_win) { wt[k] = vt; ww[k] = fmin(fmax(wb[u] + nz[u], 0.0), 45.0); }
+            }
+            if (k >= k_win && k < S.win_len) { wt[k] = 0.0; ww[k] = 0.0; }    // beyond the year end (flagged domain) / padding
+        }
     }
     tmin = block_minmax(tmin, true, sh.red);
     tmax = block_minmax(tmax, false, sh.red);
