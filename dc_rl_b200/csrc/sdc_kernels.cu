@@ -641,12 +641,36 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
         if (lo_b < hi_b && lo_b + c_hi < k_keep && hi_b - 1 + c_hi >= 0) keeps = true;
         keeps = __any_sync(0xffffffffu, keeps);                        // per warp: a warp that ran both loops would take twice as long
     }
-    if (keeps) {
+    // The kept samples of a thread are one contiguous range of its segment (the window is contiguous in trace index, and the
+    // two pieces a wrapped window has in walk index lie at opposite ends of the walk): sample q goes to runbuf[q + k_off] for
+    // q in [q_lo, q_hi).  Should both mappings ever apply to one segment, the warp takes the per-sample form.
+    int q_lo = 0, q_hi = 0, k_off = 0;
+    bool generic = false;
+    {
+        const int a_lo = max(0, -c_lo - j0), a_hi = min(cnt, min(jw, k_keep - c_lo) - j0);
+        const int b_lo = max(0, max(jw, -c_hi) - j0), b_hi = min(cnt, k_keep - c_hi - j0);
+        if (a_lo < a_hi && b_lo < b_hi) generic = true;
+        else if (a_lo < a_hi) { q_lo = a_lo; q_hi = a_hi; k_off = j0 + c_lo; }
+        else if (b_lo < b_hi) { q_lo = b_lo; q_hi = b_hi; k_off = j0 + c_hi; }
+        generic = __any_sync(0xffffffffu, generic);
+    }
+    if (keeps && !generic) {
 #pragma unroll 2
         for (int q = 0; q < cnt; q += 2) {
             float z[2];
-            const uint32_t a = sdc::pcg32_next(g), b = sdc::pcg32_next(g);
-            sdc::noise_normals2(a, b, z);
+            sdc::noise_pair(g, z);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                run += (double)(0.02f * z[u]);
+                sum_run += run; sum_run2 = fma(run, run, sum_run2);
+                if (q + u >= q_lo && q + u < q_hi) runbuf[q + u + k_off] = run;
+            }
+        }
+    } else if (keeps) {
+#pragma unroll 2
+        for (int q = 0; q < cnt; q += 2) {
+            float z[2];
+            sdc::noise_pair(g, z);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int j = j0 + q + u;
@@ -660,8 +684,7 @@ __device__ __forceinline__ void generate_episode(const sdc::State& S, int env, d
 #pragma unroll 2
         for (int q = 0; q < cnt; q += 2) {
             float z[2];
-            const uint32_t a = sdc::pcg32_next(g), b = sdc::pcg32_next(g);
-            sdc::noise_normals2(a, b, z);
+            sdc::noise_pair(g, z);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 run += (double)(0.02f * z[u]);

@@ -215,8 +215,7 @@ static void generate_weather(const sdc::State& S, int env, int t0, int roll, uin
         sdc::Pcg32 g = sdc::noise_stream(seed, episode, (uint32_t)seg);
         for (int q = 0; q < sdc::kNoiseSeg; q += 2) {
             float z[2];
-            const uint32_t a = sdc::pcg32_next(g), b = sdc::pcg32_next(g);
-            sdc::noise_normals2(a, b, z);
+            sdc::noise_pair(g, z);
             inc[seg * sdc::kNoiseSeg + q] = 0.02f * z[0]; inc[seg * sdc::kNoiseSeg + q + 1] = 0.02f * z[1];
         }
     }

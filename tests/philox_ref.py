@@ -39,24 +39,24 @@ N_SEG, SEG = 256, 140          # sdc_core.h kNoiseSegs, kNoiseSeg
 
 def noise_increments(seed, episode, n=35040):
     """The n fp32 random-walk increments 0.02f * N(0,1) of one episode, as float64.  Segment i (samples 140 i ...) draws
-    from its own PCG32 stream (XSH-RR 64/32) seeded by the Philox block (i, episode, RS_NOISE); two normals per pair of
-    draws: radius from the top 24 bits of the first, angle in [-pi, pi) from the second read as int32 (Box-Muller)."""
+    from its own PCG32 stream (XSH-RR 64/32) seeded by the Philox block (i, episode, RS_NOISE); two normals per draw:
+    radius from its top 16 bits, angle in [-pi, pi) from its low 16 bits read as int16 (Box-Muller)."""
     r = env_random(seed, episode, 1, np.arange(N_SEG, dtype=np.uint32)).astype(np.uint64)
     state = r[:, 0] | (r[:, 1] << np.uint64(32))
     inc = (r[:, 2] | (r[:, 3] << np.uint64(32))) | np.uint64(1)
     mult = np.uint64(6364136223846793005)
-    draws = np.zeros((N_SEG, SEG), np.uint32)
+    draws = np.zeros((N_SEG, SEG // 2), np.uint32)
     with np.errstate(over="ignore"):
-        for q in range(SEG):
+        for q in range(SEG // 2):
             old = state
             state = old * mult + inc
             xs = (((old >> np.uint64(18)) ^ old) >> np.uint64(27)).astype(np.uint32)
             rot = (old >> np.uint64(59)).astype(np.uint32)
             draws[:, q] = (xs >> rot) | (xs << ((np.uint32(32) - rot) & np.uint32(31)))
     f32 = np.float32
-    a, b = draws[:, 0::2], draws[:, 1::2]
-    u1 = ((a >> 8).astype(f32) + f32(0.5)) * f32(1.0 / 16777216.0)
-    th = b.view(np.int32).astype(f32) * f32(1.4629180792671596e-9)
+    a = draws
+    u1 = ((a >> 16).astype(f32) + f32(0.5)) * f32(1.0 / 65536.0)
+    th = (a & np.uint32(0xFFFF)).astype(np.uint16).view(np.int16).astype(f32) * f32(9.587379924285257e-5)
     rad = np.sqrt(f32(-2.0) * np.log(u1)).astype(f32)
     z = np.empty((N_SEG, SEG), f32)
     z[:, 0::2], z[:, 1::2] = rad * np.cos(th).astype(f32), rad * np.sin(th).astype(f32)
