@@ -336,9 +336,28 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
             if (hm) {
                 if (hit[q]) {
                     const int pos = n_mine + __popc(hm & ((1u << lane) - 1u));
-                    if (pos < warp_cap) my_hits[pos] = xs[q]; else classify(xs[q]);
+                    if (pos < warp_cap) my_hits[pos] = xs[q];                // beyond the slice: classified by the second loop below
                 }
                 n_mine += __popc(hm);
+            }
+        }
+    }
+    // A warp with more hits than its slice holds (a window in the middle of a regime change: thousands of tail values) walks
+    // its values once more and classifies the hits it could not park.  Kept out of the loop above on purpose: the
+    // classification is ~100 instructions, and eight inlined copies of it made the scan loop a 19 KB instruction stream.
+    if (n_mine > warp_cap) {
+        int n_seen = 0;
+#pragma unroll 1
+        for (int it = 0; it < n_iter; ++it) {
+            const int i0 = (tid + it * kStepThreads) * 4;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                const bool in = i0 + q < n;
+                const float x = in ? win[i0 + q] : shift;
+                const bool hit = in && (x < quiet_lo || x > quiet_hi || (x >= ca0 && x <= cb0) || (x >= ca1 && x <= cb1));
+                const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                if (hit && n_seen + __popc(hm & ((1u << lane) - 1u)) >= warp_cap) classify(x);
+                n_seen += __popc(hm);
             }
         }
     }
