@@ -183,7 +183,7 @@ def rolling_quartiles_with_ties_and_small_windows(lib):
         assert not eng.read_state("err").any()
 
 
-def incremental_normaliser_under_drift(lib, steps=1300, N=48):
+def incremental_normaliser_under_drift(lib, steps=1300, N=48, cap=2000, names=("drift", "heavy", "ties")):
     """The incremental reward normaliser (brackets + moments + tail sets, sdc_core.h) against a direct numpy statement
     of utils/reward_creator.py:16-45 on the env's window, under conditions that force its refresh machinery: a
     pre-filled window far from the real energies (drift: re-centring, moving fences), heavy tails (tail sets
@@ -194,8 +194,7 @@ def incremental_normaliser_under_drift(lib, steps=1300, N=48):
     from replay import location_traces
     col_e, col_ci = info_layout.COL["bat_total_energy_with_battery_KWh"], info_layout.COL["norm_CI"]
     stats = {}
-    for name in ("drift", "heavy", "ties"):
-        cap = 2000
+    for name in names:
         eng = Engine(N, [location_traces("ny")], [size_datacenter("ny")[0]], months=np.arange(N) % 12, days_per_episode=3,
                      hist_cap=cap, lib=lib)
         rng = np.random.RandomState(hash(name) % 1000)
@@ -228,7 +227,8 @@ def incremental_normaliser_under_drift(lib, steps=1300, N=48):
         stats[name] = dict(worst=worst, plain=int(scans[0]), refresh=int(scans[1]), env_steps=N * steps,
                            valid=int((eng.read_state("tail_n").reshape(N, 2)[:, 0] >= 0).sum()))
     # the point of the design: in the well-behaved case almost no env-step needs a window pass
-    assert stats["drift"]["plain"] + stats["drift"]["refresh"] < 0.1 * stats["drift"]["env_steps"], stats
+    if "drift" in stats:
+        assert stats["drift"]["plain"] + stats["drift"]["refresh"] < 0.1 * stats["drift"]["env_steps"], stats
     return stats
 
 

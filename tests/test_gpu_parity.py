@@ -89,6 +89,15 @@ def test_incremental_normaliser_under_drift(lib):
     print(scenarios.incremental_normaliser_under_drift(lib))
 
 
+def test_incremental_normaliser_full_window_heavy_tails_and_ties(lib):
+    """The same check at the full window length (H = 10 000) for the two distributions that flood a window pass: heavy
+    tails (thousands of values beyond the band thresholds) and heavy ties (thousands of equal values inside a re-centring
+    interval) -- more hits than a warp's slice of the parked-hit list holds, i.e. the pass's second classification loop."""
+    from scenarios import incremental_normaliser_under_drift
+    stats = incremental_normaliser_under_drift(lib, steps=200, N=16, cap=10000, names=("heavy", "ties"))
+    assert stats["heavy"]["refresh"] + stats["heavy"]["plain"] > 0 and stats["ties"]["refresh"] + stats["ties"]["plain"] > 0, stats
+
+
 def test_prefill_and_constant_history_branches(lib):
     import scenarios
     scenarios.prefill_and_constant_history_branches(lib)
