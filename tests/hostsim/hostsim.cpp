@@ -211,7 +211,7 @@ static void generate_weather(const sdc::State& S, int env, int t0, int roll, uin
     const int n = SDC_YEAR_STEPS;
     const uint64_t seed = S.seed[env];
     std::vector<float> inc(sdc::kNoiseSegs * sdc::kNoiseSeg, 0.f);
-    for (int seg = 0; seg < sdc::kNoiseSegs; ++seg) {    // one PCG32 stream per segment, two normals per pair of draws
+    for (int seg = 0; seg < sdc::kNoiseSegs; ++seg) {    // one PCG32 stream per segment, two normals per draw
         sdc::Pcg32 g = sdc::noise_stream(seed, episode, (uint32_t)seg);
         for (int q = 0; q < sdc::kNoiseSeg; q += 2) {
             float z[2];
