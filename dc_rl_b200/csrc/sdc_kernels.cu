@@ -1,17 +1,25 @@
 // sdc_kernels.cu -- CUDA (sm_100a) backend of libsdc_b200.so.
 //
 // Kernels
-//   k_step    one launch per env-step for all N envs.  A warp takes a unit of U consecutive envs, one lane per env:
-//             load-shifting queue, IT/HVAC model, battery, trace gathers, observations, info row (sdc_core.h, fp64
-//             like the reference), then the reward normaliser INCREMENTALLY: window append, exact rolling quartile
-//             brackets, fp64 window moments, tail multisets beyond the IQR fences -> clipped mean / std without
-//             touching the 40 KB window.  Only an env whose incremental state ran out of slack (a few per thousand
-//             env-steps) has its fp32 window streamed once by the whole warp (128-bit loads, warp-shuffle reductions,
-//             ballot compaction into the tail sets / a shared-memory scratch that is bitonic-sorted) -- "refresh".
-//             CTAs without units (and every CTA once the units are gone) serve as episode-reset workers.
-//   k_reset   explicit resets, one CTA per env: start day/hour, year-long weather random walk (Philox), day roll,
-//             clip, 30-day normalisation, queue clear, reset observation (or copies a staged episode).
-//   k_rebuild one CTA per env: full bitonic sort of the window in shared memory -> fresh brackets.
+//   k_step    ONE cooperative launch per env-step for all N envs (grid = what the device holds at once: 2 CTAs of 256 threads
+//             per SM; parameters are __grid_constant__ so that the State struct is read from the constant bank, not copied
+//             to every thread's stack).
+//             UNITS: a warp takes a unit of U consecutive envs, one lane per env -- load-shifting queue, IT / HVAC model,
+//             battery, trace gathers, info row (sdc_core.h, fp64 like the reference), then the reward normaliser
+//             INCREMENTALLY (window append, exact rolling quartile brackets, fp64 window moments, sorted tail bands around
+//             the IQR fences -> clipped mean / std without touching the 40 KB window; samples that enter / leave inside a
+//             bracket or a band are located and edited by the whole warp), rewards, logger sums (one 16-value warp
+//             reduction), the 29 distinct observation values through a shared-memory tile of compact rows, and the reset of
+//             envs that finish (the look-ahead generation staged the next episode with its observation: buffer flip + copy).
+//             No unit warp ever waits for another warp, CTA or job.
+//             WORKERS: CTAs without units from the first cycle, and every CTA once its units are done, serve a job queue --
+//             window passes (an env whose incremental state runs out of slack: its window is staged in shared memory by one
+//             TMA bulk copy, scanned by 256 threads, bucket-sorted, committed; if the step itself cannot be priced without
+//             the window, the pass CTA prices it: finish_step) and the look-ahead generation of the episodes that start two
+//             steps from now (year-long weather random walk from counter-based RNG streams + the reset observation).
+//   k_reset   explicit resets, one CTA per env: start day/hour, weather generation, queue clear, reset observation (or
+//             copies a staged episode).
+//   k_rebuild one CTA per env: full bitonic sort of the window in shared memory -> fresh brackets (set-up / restore).
 //   k_build_reset_list  mask -> env list.
 //
 // No tensor cores: there is no dense contraction on this path (per-env scalar state machines + streaming passes).
@@ -539,7 +547,7 @@ __device__ __noinline__ void finish_step(const sdc::State& S, const StepArgs& a,
 }
 
 // =================================================================================================
-// episode reset of one env by one CTA (used by k_reset and by the reset workers inside k_step)
+// episode reset / generation of one env by one CTA (k_reset, and the worker jobs inside k_step)
 // =================================================================================================
 constexpr int kResetThreads = sdc::kNoiseThreads;   // 256 == kStepThreads
 
@@ -1106,8 +1114,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
         const long long tk2 = clock64();
         // A pass whose result this step's reward does not need (the brackets still hold the quartile ranks and the tail
         // bands still contain the fences: the refresh only restores slack for FUTURE steps) is a maintenance pass: its
-        // record goes to a global queue served by whichever CTA is free.  Only the rare env that cannot price this step
-        // without the window keeps the CTA-synchronous path.
+        // record goes to a global queue served by whichever CTA is free.  The rare env that cannot price this step
+        // without the window (slow_lane) publishes the same record with the inputs of reward_finish: the pass CTA prices it.
         const bool wants_pass = active && rq.kind != sdc::SCAN_SKIP;
         // the window of an env that asks for a pass is on its way into L2 before a worker CTA picks the job up
         if (wants_pass) l2_prefetch_bulk(S.hist + (size_t)env * S.hist_cap, ((unsigned)rq.n * 4u + 15u) & ~15u);
@@ -1461,8 +1469,8 @@ static size_t run_buf_bytes(const sdc::State& S) { return (size_t)(S.win_len > k
 static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& a, void* stream) {
     const int U = a.unit_envs;
     // Dynamic shared memory of k_step after the tables: collect scratch + the staged window (which also receives the sorted
-    // collections: at least 2 x kCollectCap floats) + the parked-hit list.  The fused kernel shares the region with its
-    // observation tiles (whatever they leave beyond scratch + window is the hit list).
+    // collections: at least 2 x kCollectCap floats) + the parked-hit list (worker role); the unit role uses the start of the
+    // same region for its compact observation tiles (30 KB).  54 KB per CTA: two CTAs leave the SM a 124 KB L1.
     const size_t pass_floats = (size_t)2 * sdc::kCollectCap + 2 * sdc::kTailCap + (S.hist_cap > 2 * sdc::kCollectCap ? S.hist_cap : 2 * sdc::kCollectCap);
     const size_t tile_floats = (size_t)kWarpsPerBlock * 32 * kTileStride;
     constexpr size_t kHitFloats = 2048;            // parked hits of a pass (256 per warp; overflow is classified in place), then the sorted
@@ -1471,7 +1479,7 @@ static const char* launch_step(Context& c, const sdc::State& S, const StepArgs& 
     const int hit_cap = (int)(smem_floats - pass_floats);
     if (hit_cap < 2 * sdc::kTailCap + sdc::kCollectCap) return "k_step: shared memory layout leaves no room for the sorted bands and the bucket order";
     size_t smem = smem_floats * sizeof(float);
-    if (smem < run_buf_bytes(S)) smem = run_buf_bytes(S);                              // reset workers reuse the region
+    if (smem < run_buf_bytes(S)) smem = run_buf_bytes(S);                              // episode generation reuses the region
     // shared-memory copy of the location / dc parameter tables: only what this handle needs
     int table_bytes = (int)(S.n_loc * sizeof(sdc::LocTables) + S.n_cfg * sizeof(sdc_dc_params));
     table_bytes = table_bytes <= kTableBytes ? (table_bytes + 127) & ~127 : 0;
