@@ -218,6 +218,7 @@ struct PassJob {
     // finish == 1: what reward_finish needs besides the request and the results
     int m_ok; float alt3[3];
     double q1, m_c1, m_c2, m_c0, energy, nci_next, ls_penalty;
+    unsigned long long t_pub;               // diagnostics (unit_log): when the record was published (globaltimer ns)
 };
 static_assert(sizeof(PassJob) <= sdc::kPassJobBytes && sdc::kPassJobBytes % 16 == 0, "maintenance pass record size");
 struct PassShared {
@@ -522,7 +523,8 @@ __device__ __noinline__ void window_pass(const sdc::State& S, PassShared& ps, fl
     }
     if (tid == 0) ps.job.rs = rs;
     __syncthreads();                                                     // results visible; `win`, `scr`, partials free again
-    if (clk_log && tid == 0) { clk_log[4] = (uint32_t)(clock64() - tp0); clk_log[6] = (uint32_t)J.kind | ((uint32_t)J.tails << 8) | ((uint32_t)J.rc[0] << 16) | ((uint32_t)J.rc[1] << 17); }
+    if (clk_log && tid == 0) { clk_log[7] = (uint32_t)(gtime_ns() - J.t_pub);      // publication -> end of the pass (ns)
+                               clk_log[4] = (uint32_t)(clock64() - tp0); clk_log[6] = (uint32_t)J.kind | ((uint32_t)J.tails << 8) | ((uint32_t)J.rc[0] << 16) | ((uint32_t)J.rc[1] << 17); }
 }
 
 // The env of a finish job could not price its step without the window (a bracket ran out on one side, or the bands no
@@ -1163,6 +1165,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const __grid_constant_
                 J.m_ok = M.ok; J.alt3[0] = alt3[0]; J.alt3[1] = alt3[1]; J.alt3[2] = alt3[2];
                 J.q1 = rq.q1; J.m_c1 = M.c1; J.m_c2 = M.c2; J.m_c0 = M.c0;
                 J.energy = en.energy; J.nci_next = en.nci_next; J.ls_penalty = en.ls_penalty;
+                J.t_pub = a.unit_log ? gtime_ns() : 0ull;
                 reinterpret_cast<PassJob*>(reinterpret_cast<unsigned char*>(a.pass_jobs) + (size_t)idx * sdc::kPassJobBytes)[0] = J;
                 __threadfence();
                 *reinterpret_cast<volatile int32_t*>(a.pass_ready + idx) = a.seq;

@@ -58,3 +58,9 @@ if len(P):
     kinds = P[:, 6]
     for lab, m in (("re-centre list 0 only", ((kinds >> 16) & 3) == 1), ("list 1 only", ((kinds >> 16) & 3) == 2), ("both lists", ((kinds >> 16) & 3) == 3), ("no list (bands only)", ((kinds >> 16) & 3) == 0)):
         if m.any(): print("   %-22s %4d passes, total %.0f, sorts %.0f, tails rebuilt in %d" % (lab, m.sum(), P[m, 4].mean(), P[m, 3].mean(), (((kinds[m] >> 8) & 0xff) > 0).sum()))
+if len(P):
+    lat = P[:, 7].astype(np.float64)                      # ns from publication to the end of the pass
+    run_ns = P[:, 4] / 1.965
+    wait = lat - run_ns
+    print("pass queueing: publication -> pass start ns  mean %.0f  p50 %.0f  p90 %.0f  max %.0f   (pass itself mean %.0f ns)" % (
+        wait.mean(), *np.percentile(wait, [50, 90]), wait.max(), run_ns.mean()))
